@@ -1,0 +1,207 @@
+"""ctypes binding of the C ABI in include/dab_b200.h (libdab_b200.so).
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is present, loading or
+`Handle()` raises.  torch is used only to own device memory and streams (`tensor.data_ptr()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdab_b200.so")
+
+IPC_HANDLE_BYTES = 64
+MAX_ENSEMBLE = 128
+MAX_RANKS = 8
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class DabError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libdab_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CycleConfig(C.Structure):
+    """struct dab_cycle_config (include/dab_b200.h)."""
+    _fields_ = [
+        ("system_dim", C.c_int64),
+        ("ensemble_dim", C.c_int32),
+        ("n_steps", C.c_int32),
+        ("model_dt", C.c_double),
+        ("forcing", C.c_double),
+        ("rho", C.c_double),
+        ("obs_error_sd", C.c_double),
+        ("n_obs_times", C.c_int64),
+        ("n_obs", C.c_int64),
+        ("stationary", C.c_int32),
+        ("n_cycles", C.c_int32),
+        ("t_pad", C.c_int32),
+        ("rank", C.c_int32),
+        ("world", C.c_int32),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "dab_version": (C.c_int, []),
+    "dab_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "dab_destroy": (C.c_int, [_P]),
+    "dab_sync": (C.c_int, [_P]),
+    "dab_last_error": (C.c_char_p, [_P]),
+    "dab_l96_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, _P]),
+    "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
+    "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
+    "dab_etkf_transform_matrix_f64": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
+    "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
+    "dab_cycler_setup": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P]),
+    "dab_cycler_set_state": (C.c_int, [_P, _P, C.c_int]),
+    "dab_cycler_get_state": (C.c_int, [_P, _P, C.c_int]),
+    "dab_cycler_run": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "dab_cycler_stats": (C.c_int, [_P, C.c_int]),
+    "dab_cycler_stats_ptr": (_P, [_P]),
+    "dab_cycler_update": (C.c_int, [_P, C.c_int, _P]),
+    "dab_cycler_ipc_export": (C.c_int, [_P, C.c_int, _P]),
+    "dab_cycler_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "dab_cycler_stream": (_P, [_P]),
+    "dab_cycler_background_ptr": (_P, [_P]),
+    "dab_cycler_kernel_launches": (C.c_int, [_P]),
+    "dab_etkf_cycle_host_f64": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load libdab_b200.so (built in-tree by `_build.build()`); raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            "%s not found: build it with `python -m dataassimbench_b200._build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """Device/host address of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError("cannot take the address of %r" % type(x))
+
+
+class Handle:
+    """RAII wrapper of `dab_handle*`."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        self._h = _P()
+        rc = self._lib.dab_create(C.byref(self._h), int(device))
+        if rc != 0:
+            msg = self._lib.dab_last_error(None)
+            self._h = None
+            raise DabError(rc, msg.decode() if msg else "dab_create failed")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.dab_last_error(self._h)
+            raise DabError(rc, msg.decode() if msg else "?")
+
+    # ---- thin 1:1 wrappers ------------------------------------------------------------
+    def sync(self):
+        self._check(self._lib.dab_sync(self._h))
+
+    def l96_forecast(self, x_in, x_out, traj, N, k, n_steps, dt, F, stream=None):
+        self._check(self._lib.dab_l96_forecast_f64(self._h, _ptr(x_in), _ptr(x_out), _ptr(traj),
+                                                   N, k, n_steps, dt, F, _ptr(stream)))
+
+    def obs_gather(self, X, idx, mask, Yb, N, k, n_y, stream=None):
+        self._check(self._lib.dab_obs_gather_f64(self._h, _ptr(X), _ptr(idx), _ptr(mask), _ptr(Yb),
+                                                 N, k, n_y, _ptr(stream)))
+
+    def etkf_stats(self, X, y, idx, mask, sd, N, k, n_y, stats, stream=None):
+        self._check(self._lib.dab_etkf_stats_f64(self._h, _ptr(X), _ptr(y), _ptr(idx), _ptr(mask),
+                                                 sd, N, k, n_y, _ptr(stats), _ptr(stream)))
+
+    def etkf_transform_matrix(self, stats, k, rho, empty_R, T, lam=None, sweeps=None, stream=None):
+        self._check(self._lib.dab_etkf_transform_matrix_f64(self._h, _ptr(stats), k, rho, int(empty_R),
+                                                            _ptr(T), _ptr(lam), _ptr(sweeps), _ptr(stream)))
+
+    def etkf_analysis(self, Xb, Xa, y, idx, mask, sd, rho, N, k, n_y, stream=None):
+        self._check(self._lib.dab_etkf_analysis_f64(self._h, _ptr(Xb), _ptr(Xa), _ptr(y), _ptr(idx),
+                                                    _ptr(mask), sd, rho, N, k, n_y, _ptr(stream)))
+
+    def cycler_setup(self, cfg, obs_values, system_index, padded_time_idx):
+        self._check(self._lib.dab_cycler_setup(self._h, C.byref(cfg), _ptr(obs_values),
+                                               _ptr(system_index), _ptr(padded_time_idx)))
+
+    def cycler_set_state(self, x, is_host):
+        self._check(self._lib.dab_cycler_set_state(self._h, _ptr(x), int(is_host)))
+
+    def cycler_get_state(self, x, is_host):
+        self._check(self._lib.dab_cycler_get_state(self._h, _ptr(x), int(is_host)))
+
+    def cycler_run(self, c0, c1, out_analysis=None, out_traj=None):
+        self._check(self._lib.dab_cycler_run(self._h, c0, c1, _ptr(out_analysis), _ptr(out_traj)))
+
+    def cycler_stats(self, cycle):
+        self._check(self._lib.dab_cycler_stats(self._h, cycle))
+
+    def cycler_stats_ptr(self):
+        return self._lib.dab_cycler_stats_ptr(self._h)
+
+    def cycler_update(self, cycle, out_analysis_dev=None):
+        self._check(self._lib.dab_cycler_update(self._h, cycle, _ptr(out_analysis_dev)))
+
+    def cycler_ipc_export(self, which):
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.dab_cycler_ipc_export(self._h, which, buf))
+        return bytes(buf.raw)
+
+    def cycler_ipc_import(self, peer_rank, which, handle_bytes):
+        buf = C.create_string_buffer(bytes(handle_bytes), IPC_HANDLE_BYTES)
+        self._check(self._lib.dab_cycler_ipc_import(self._h, peer_rank, which, buf))
+
+    def cycler_stream(self):
+        return self._lib.dab_cycler_stream(self._h)
+
+    def cycler_background_ptr(self):
+        return self._lib.dab_cycler_background_ptr(self._h)
+
+    def kernel_launches(self):
+        return self._lib.dab_cycler_kernel_launches(self._h)
+
+    def etkf_cycle_host(self, cfg, x0, obs_values, system_index, padded_time_idx, out_analysis):
+        self._check(self._lib.dab_etkf_cycle_host_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),
+                                                      _ptr(system_index), _ptr(padded_time_idx),
+                                                      _ptr(out_analysis)))

@@ -1,0 +1,587 @@
+// Engine + C ABI (include/dab_b200.h): owns device workspaces, streams and the cycling loop.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dab_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace dab;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Cycler {
+  bool ready = false;
+  dab_cycle_config cfg{};
+  long long n_loc = 0, n0 = 0, ld_e = 0;
+  int halo_l = 0, halo_r = 0, first_steps = 0;
+  int empty_R = 0;
+  int cur = 0;                             // which Xb buffer holds the current background
+  double* xb[2] = {nullptr, nullptr};      // plain [k][n_loc], separately cudaMalloc'ed (IPC-exportable)
+  DevBuf ext[2];                           // extended-layout analysis buffers
+  DevBuf obs_loc, obs_val, seg, partial, stats, T, lam, info;
+  std::vector<long long> csr_off;          // [n_obs_times + 1]
+  std::vector<int> n_seg;                  // per cycle
+  std::vector<long long> n_rows;           // per cycle
+  int max_grid = 1;
+  const double* peer[kMaxRanks][2];        // peer-mapped Xb buffers
+  bool peer_open[kMaxRanks][2];
+  cudaEvent_t ev_xa[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool copied_pending[2] = {false, false};
+};
+
+}  // namespace
+
+struct dab_handle {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::string err;
+  long launches = 0;
+  DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
+  Cycler cyc;
+};
+
+static std::string g_create_err;
+
+static int fail(dab_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define DAB_CUDA(h, expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail((h), (int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define DAB_ARG(h, cond)                                                                     \
+  do { if (!(cond)) return fail((h), -1, "invalid argument: %s", #cond); } while (0)
+
+static void cycler_free(dab_handle* h) {
+  Cycler& c = h->cyc;
+  for (int r = 0; r < kMaxRanks; ++r)
+    for (int w = 0; w < 2; ++w)
+      if (c.peer_open[r][w]) { cudaIpcCloseMemHandle(const_cast<double*>(c.peer[r][w])); c.peer_open[r][w] = false; }
+  for (int w = 0; w < 2; ++w) {
+    if (c.xb[w]) cudaFree(c.xb[w]);
+    c.xb[w] = nullptr;
+    c.ext[w].release();
+    if (c.ev_xa[w]) cudaEventDestroy(c.ev_xa[w]);
+    if (c.ev_copied[w]) cudaEventDestroy(c.ev_copied[w]);
+    c.ev_xa[w] = c.ev_copied[w] = nullptr;
+    c.copied_pending[w] = false;
+  }
+  c.obs_loc.release(); c.obs_val.release(); c.seg.release(); c.partial.release();
+  c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
+  c.ready = false;
+}
+
+extern "C" {
+
+int dab_version(void) { return 100; }
+
+int dab_create(dab_handle** out, int device) {
+  if (!out) return fail(nullptr, -1, "dab_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice,
+                "dab_create: no CUDA device (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, -1, "dab_create: device %d out of range [0,%d)", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, (int)e, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) return fail(nullptr, (int)e, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (p.major < 10)
+    return fail(nullptr, -2, "dab_create: device %s is sm_%d%d; this library is built for sm_100a only",
+                p.name, p.major, p.minor);
+  dab_handle* h = new dab_handle();
+  h->device = device;
+  h->sms = p.multiProcessorCount;
+  memset(h->cyc.peer, 0, sizeof(h->cyc.peer));
+  memset(h->cyc.peer_open, 0, sizeof(h->cyc.peer_open));
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return 0;
+}
+
+int dab_destroy(dab_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cycler_free(h);
+  h->s_loc.release(); h->s_val.release(); h->s_seg.release();
+  h->s_partial.release(); h->s_stats.release(); h->s_T.release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return 0;
+}
+
+int dab_sync(dab_handle* h) {
+  DAB_ARG(h, h != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, cudaStreamSynchronize(h->stream));
+  DAB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  return 0;
+}
+
+const char* dab_last_error(const dab_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+// ------------------------------------------------------------------------------------ K1
+static int forecast_plain(dab_handle* h, const double* x_in, double* x_out, double* traj,
+                          long long N, int k, int n_steps, double dt, double F, cudaStream_t st,
+                          double* tmp /* [k][N] scratch, needed when chunking */) {
+  const int maxs = l96_max_steps_per_launch();
+  const long long traj_stride = (long long)k * N;
+  if (n_steps == 0) {
+    DAB_CUDA(h, cudaMemcpyAsync(x_out, x_in, sizeof(double) * k * N, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  const int n_chunks = (n_steps + maxs - 1) / maxs;
+  const double* src = x_in;
+  int done = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s = (n_steps - done) < maxs ? (n_steps - done) : maxs;
+    // ping-pong so that the last chunk lands in x_out
+    double* dst = ((n_chunks - 1 - c) % 2 == 0) ? x_out : tmp;
+    DAB_CUDA(h, l96_forecast_launch(src, dst, traj ? traj + (long long)done * traj_stride : nullptr, N, k, s,
+                                    dt, F, N, N, true, 0, 0, 0, traj_stride, h->sms, st));
+    h->launches++;
+    src = dst;
+    done += s;
+  }
+  return 0;
+}
+
+int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj,
+                         int64_t N, int k, int n_steps, double dt, double F, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, x_in != nullptr && x_out != nullptr && x_in != x_out);
+  DAB_ARG(h, N >= 4 && k >= 1 && n_steps >= 0);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* tmp = nullptr;
+  if (n_steps > l96_max_steps_per_launch()) {
+    DAB_CUDA(h, h->s_partial.reserve(sizeof(double) * k * N));
+    tmp = h->s_partial.as<double>();
+  }
+  return forecast_plain(h, x_in, x_out, traj, N, k, n_steps, dt, F, st, tmp);
+}
+
+// ------------------------------------------------------------------------------------ K2
+int dab_obs_gather_f64(dab_handle* h, const double* X, const int64_t* idx, const uint8_t* mask,
+                       double* Yb, int64_t N, int k, int64_t n_y, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, N >= 1 && k >= 1 && n_y >= 0);
+  DAB_ARG(h, n_y == 0 || (X != nullptr && idx != nullptr && Yb != nullptr));
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, gather_launch(X, N, k, reinterpret_cast<const long long*>(idx), mask, n_y, Yb,
+                            static_cast<cudaStream_t>(stream)));
+  if (n_y > 0) h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- K3 / K4
+static int stats_from_arrays(dab_handle* h, const double* X, const double* y, const int64_t* idx,
+                             const uint8_t* mask, double sd, long long N, int k, long long n_y,
+                             double* stats, cudaStream_t st) {
+  DAB_CUDA(h, h->s_loc.reserve(sizeof(int) * (size_t)(n_y > 0 ? n_y : 1)));
+  DAB_CUDA(h, h->s_val.reserve(sizeof(double) * (size_t)(n_y > 0 ? n_y : 1)));
+  DAB_CUDA(h, h->s_seg.reserve(sizeof(long long) * 3));
+  const int grid = contract_grid(n_y, h->sms);
+  DAB_CUDA(h, h->s_partial.reserve(sizeof(double) * contract_partial_doubles(k, grid)));
+  DAB_CUDA(h, pack_obs_launch(reinterpret_cast<const long long*>(idx), mask, y, n_y,
+                              h->s_loc.as<int>(), h->s_val.as<double>(), st));
+  const long long seg[3] = {0, n_y, 0};
+  DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
+  DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
+                              h->s_seg.as<long long>(), 1, n_y, 1.0 / (sd * sd),
+                              h->s_partial.as<double>(), stats, grid, st));
+  h->launches += (n_y > 0 ? 1 : 0) + 2;
+  return 0;
+}
+
+int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, const int64_t* idx,
+                       const uint8_t* mask, double obs_error_sd, int64_t N, int k, int64_t n_y,
+                       double* stats, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, X != nullptr && stats != nullptr && N >= 1 && n_y >= 0);
+  DAB_ARG(h, k >= 2 && k <= DAB_MAX_ENSEMBLE);
+  DAB_ARG(h, obs_error_sd > 0.0);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  return stats_from_arrays(h, X, y, idx, mask, obs_error_sd, N, k, n_y, stats,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, double rho,
+                                  int empty_R, double* T, double* lam, int* sweeps, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, (stats != nullptr || empty_R) && T != nullptr);
+  DAB_ARG(h, k >= 2 && k <= DAB_MAX_ENSEMBLE && rho > 0.0);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, eig_transform_launch(stats, k, rho, empty_R, T, lam, sweeps, static_cast<cudaStream_t>(stream)));
+  h->launches++;
+  return 0;
+}
+
+int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                          const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
+                          int64_t N, int k, int64_t n_y, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, Xb != nullptr && Xa != nullptr && Xb != Xa);
+  DAB_ARG(h, N >= 1 && n_y >= 0 && k >= 2 && k <= DAB_MAX_ENSEMBLE);
+  DAB_ARG(h, rho > 0.0 && (n_y == 0 || obs_error_sd > 0.0));
+  DAB_ARG(h, n_y == 0 || (y != nullptr && idx != nullptr));
+  DAB_ARG(h, N < (1ll << 31));
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DAB_CUDA(h, h->s_stats.reserve(sizeof(double) * ((size_t)k * k + k)));
+  DAB_CUDA(h, h->s_T.reserve(sizeof(double) * (size_t)k * k));
+  const int empty_R = n_y == 0;
+  if (!empty_R) {
+    int rc = stats_from_arrays(h, Xb, y, idx, mask, obs_error_sd, N, k, n_y, h->s_stats.as<double>(), st);
+    if (rc) return rc;
+  }
+  DAB_CUDA(h, eig_transform_launch(h->s_stats.as<double>(), k, rho, empty_R, h->s_T.as<double>(),
+                                   nullptr, nullptr, st));
+  TransformArgs a{};
+  a.T = h->s_T.as<double>();
+  a.src[0] = Xb; a.src_ld = N;
+  a.dst = Xa; a.dst_ld = N; a.dst_base = 0;
+  a.n_loc = N; a.n_global = N; a.n0 = 0;
+  a.halo_l = 0; a.halo_r = 0; a.k = k; a.rank = 0;
+  DAB_CUDA(h, transform_launch(a, h->sms, st));
+  h->launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ the cycler
+int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                     const int64_t* system_index, const int64_t* padded_time_idx) {
+  DAB_ARG(h, h != nullptr && cfg != nullptr);
+  DAB_ARG(h, cfg->system_dim >= 4 && cfg->system_dim < (1ll << 31));
+  DAB_ARG(h, cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= DAB_MAX_ENSEMBLE);
+  DAB_ARG(h, cfg->n_steps >= 0 && cfg->n_cycles >= 0 && cfg->t_pad >= 0);
+  DAB_ARG(h, cfg->rho > 0.0 && cfg->model_dt > 0.0);
+  DAB_ARG(h, cfg->world >= 1 && cfg->world <= DAB_MAX_RANKS && cfg->rank >= 0 && cfg->rank < cfg->world);
+  DAB_ARG(h, cfg->system_dim % cfg->world == 0);
+  DAB_ARG(h, cfg->n_obs_times >= 0 && cfg->n_obs >= 0);
+  DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 || (obs_values != nullptr && system_index != nullptr));
+  DAB_ARG(h, cfg->n_cycles * cfg->t_pad == 0 || padded_time_idx != nullptr);
+  DAB_ARG(h, cfg->world == 1 || cfg->n_steps <= l96_max_steps_per_launch());
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, cudaStreamSynchronize(h->stream));
+  DAB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  cycler_free(h);
+  Cycler& c = h->cyc;
+  c.cfg = *cfg;
+  const int k = cfg->ensemble_dim;
+  c.n_loc = cfg->system_dim / cfg->world;
+  c.n0 = c.n_loc * cfg->rank;
+  const int maxs = l96_max_steps_per_launch();
+  c.first_steps = cfg->n_steps < maxs ? cfg->n_steps : maxs;
+  c.halo_l = 8 * c.first_steps;
+  c.halo_r = 4 * c.first_steps;
+  c.ld_e = (c.halo_l + c.n_loc + c.halo_r + 1) & ~1ll;
+  // the reference's empty-R branch: no observation slot at all (T_pad * n_obs == 0)
+  c.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
+  c.cur = 0;
+  const size_t slab = sizeof(double) * (size_t)k * c.n_loc;
+  for (int w = 0; w < 2; ++w) {
+    DAB_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&c.xb[w]), slab));
+    DAB_CUDA(h, c.ext[w].reserve(sizeof(double) * (size_t)k * c.ld_e));
+    DAB_CUDA(h, cudaMemsetAsync(c.ext[w].p, 0, c.ext[w].bytes, h->stream));
+    DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_xa[w], cudaEventDisableTiming));
+    DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_copied[w], cudaEventDisableTiming));
+  }
+  // ---- observations: CSR over observation times, rows owned by this rank, masked rows dropped
+  const long long nt = cfg->n_obs_times, no = cfg->n_obs;
+  c.csr_off.assign((size_t)nt + 1, 0);
+  std::vector<int> loc;
+  std::vector<double> val;
+  loc.reserve((size_t)(nt * no / cfg->world + 16));
+  val.reserve((size_t)(nt * no / cfg->world + 16));
+  for (long long t = 0; t < nt; ++t) {
+    for (long long o = 0; o < no; ++o) {
+      const double v = obs_values[t * no + o];
+      if (!cfg->stationary && std::isnan(v)) continue;        // loc mask, _dacycler.py:266-268
+      const long long gi = system_index[t * no + o];
+      if (gi < 0 || gi >= cfg->system_dim)
+        return fail(h, -1, "system_index[%lld][%lld] = %lld out of range", t, o, gi);
+      if (gi < c.n0 || gi >= c.n0 + c.n_loc) continue;         // owned by another rank
+      loc.push_back((int)(gi - c.n0));
+      val.push_back(v);
+    }
+    c.csr_off[(size_t)t + 1] = (long long)loc.size();
+  }
+  DAB_CUDA(h, c.obs_loc.reserve(sizeof(int) * (loc.size() + 1)));
+  DAB_CUDA(h, c.obs_val.reserve(sizeof(double) * (val.size() + 1)));
+  if (!loc.empty()) {
+    DAB_CUDA(h, cudaMemcpyAsync(c.obs_loc.p, loc.data(), sizeof(int) * loc.size(), cudaMemcpyHostToDevice, h->stream));
+    DAB_CUDA(h, cudaMemcpyAsync(c.obs_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
+  }
+  // ---- per-cycle segment tables from the padded time indices (0 = masked, t+1 otherwise)
+  const int tp = cfg->t_pad > 0 ? cfg->t_pad : 1;
+  std::vector<long long> seg((size_t)cfg->n_cycles * tp * 3 + 3, 0);
+  c.n_seg.assign((size_t)cfg->n_cycles, 0);
+  c.n_rows.assign((size_t)cfg->n_cycles, 0);
+  long long max_rows = 0;
+  for (int cy = 0; cy < cfg->n_cycles; ++cy) {
+    long long rows = 0;
+    int ns = 0;
+    for (int s = 0; s < cfg->t_pad; ++s) {
+      const long long ti = padded_time_idx[(long long)cy * cfg->t_pad + s];
+      if (ti <= 0) continue;                                    // time mask, _dacycler.py:119
+      if (ti > nt) return fail(h, -1, "padded_time_idx[%d][%d] = %lld exceeds n_obs_times", cy, s, ti);
+      const long long b = c.csr_off[(size_t)ti - 1], e = c.csr_off[(size_t)ti];
+      long long* sg = &seg[((size_t)cy * tp + ns) * 3];
+      sg[0] = b; sg[1] = e - b; sg[2] = rows;
+      rows += e - b;
+      ++ns;
+    }
+    c.n_seg[(size_t)cy] = ns;
+    c.n_rows[(size_t)cy] = rows;
+    if (rows > max_rows) max_rows = rows;
+  }
+  DAB_CUDA(h, c.seg.reserve(sizeof(long long) * seg.size()));
+  DAB_CUDA(h, cudaMemcpyAsync(c.seg.p, seg.data(), sizeof(long long) * seg.size(), cudaMemcpyHostToDevice, h->stream));
+  c.max_grid = contract_grid(max_rows, h->sms);
+  DAB_CUDA(h, c.partial.reserve(sizeof(double) * contract_partial_doubles(k, c.max_grid)));
+  DAB_CUDA(h, c.stats.reserve(sizeof(double) * ((size_t)k * k + k)));
+  DAB_CUDA(h, cudaMemsetAsync(c.stats.p, 0, c.stats.bytes, h->stream));
+  DAB_CUDA(h, c.T.reserve(sizeof(double) * (size_t)k * k));
+  DAB_CUDA(h, c.lam.reserve(sizeof(double) * (size_t)k));
+  DAB_CUDA(h, c.info.reserve(sizeof(int) * 4));
+  DAB_CUDA(h, cudaStreamSynchronize(h->stream));               // host vectors go out of scope
+  h->launches = 0;
+  c.ready = true;
+  return 0;
+}
+
+int dab_cycler_set_state(dab_handle* h, const double* x, int is_host) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready && x != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  Cycler& c = h->cyc;
+  DAB_CUDA(h, cudaMemcpyAsync(c.xb[c.cur], x, sizeof(double) * (size_t)c.cfg.ensemble_dim * c.n_loc,
+                              is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int dab_cycler_get_state(dab_handle* h, double* x, int is_host) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready && x != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  Cycler& c = h->cyc;
+  DAB_CUDA(h, cudaMemcpyAsync(x, c.xb[c.cur], sizeof(double) * (size_t)c.cfg.ensemble_dim * c.n_loc,
+                              is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+  if (is_host) DAB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dab_cycler_stats(dab_handle* h, int cycle) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready);
+  Cycler& c = h->cyc;
+  DAB_ARG(h, cycle >= 0 && cycle < c.cfg.n_cycles);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  if (c.empty_R) return 0;
+  const int k = c.cfg.ensemble_dim;
+  const int tp = c.cfg.t_pad > 0 ? c.cfg.t_pad : 1;
+  const long long rows = c.n_rows[(size_t)cycle];
+  const int grid = contract_grid(rows, h->sms);
+  const int ns = c.n_seg[(size_t)cycle] > 0 ? c.n_seg[(size_t)cycle] : 1;
+  DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
+                              c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
+                              1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd),
+                              c.partial.as<double>(), c.stats.as<double>(), grid, h->stream));
+  h->launches += 2;
+  return 0;
+}
+
+double* dab_cycler_stats_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.stats.as<double>() : nullptr; }
+void* dab_cycler_stream(dab_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+double* dab_cycler_background_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.xb[h->cyc.cur] : nullptr; }
+int dab_cycler_kernel_launches(dab_handle* h) { return h ? (int)h->launches : 0; }
+
+// eig (K4) + transform (K5, fused halo exchange) + forecast (K1).  The analysis of this cycle is
+// left in ext[cycle & 1]; out_host / out_dev optionally receive its slab part.
+static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out_dev, double* out_traj) {
+  Cycler& c = h->cyc;
+  const int k = c.cfg.ensemble_dim;
+  const int eb = cycle & 1;
+  DAB_CUDA(h, eig_transform_launch(c.stats.as<double>(), k, c.cfg.rho, c.empty_R, c.T.as<double>(),
+                                   c.lam.as<double>(), c.info.as<int>(), h->stream));
+  if (c.copied_pending[eb]) {                 // the D2H of cycle-2's analysis still reads ext[eb]
+    DAB_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_copied[eb], 0));
+    c.copied_pending[eb] = false;
+  }
+  TransformArgs a{};
+  a.T = c.T.as<double>();
+  for (int r = 0; r < c.cfg.world; ++r) {
+    if (r == c.cfg.rank) a.src[r] = c.xb[c.cur];
+    else {
+      if (!c.peer_open[r][c.cur]) return fail(h, -3, "peer buffer of rank %d not imported (dab_cycler_ipc_import)", r);
+      a.src[r] = c.peer[r][c.cur];
+    }
+  }
+  a.src_ld = c.n_loc;
+  a.dst = c.ext[eb].as<double>(); a.dst_ld = c.ld_e; a.dst_base = c.halo_l;
+  a.n_loc = c.n_loc; a.n_global = c.cfg.system_dim; a.n0 = c.n0;
+  a.halo_l = c.halo_l; a.halo_r = c.halo_r; a.k = k; a.rank = c.cfg.rank;
+  DAB_CUDA(h, transform_launch(a, h->sms, h->stream));
+  h->launches += 2;
+  const double* xa = c.ext[eb].as<double>() + c.halo_l;
+  if (out_host) {
+    DAB_CUDA(h, cudaEventRecord(c.ev_xa[eb], h->stream));
+    DAB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, c.ev_xa[eb], 0));
+    DAB_CUDA(h, cudaMemcpy2DAsync(out_host, sizeof(double) * c.n_loc, xa, sizeof(double) * c.ld_e,
+                                  sizeof(double) * c.n_loc, k, cudaMemcpyDeviceToHost, h->copy_stream));
+    DAB_CUDA(h, cudaEventRecord(c.ev_copied[eb], h->copy_stream));
+    c.copied_pending[eb] = true;
+  }
+  if (out_dev) {
+    DAB_CUDA(h, cudaMemcpy2DAsync(out_dev, sizeof(double) * c.n_loc, xa, sizeof(double) * c.ld_e,
+                                  sizeof(double) * c.n_loc, k, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  // forecast: ext[eb] -> xb[cur ^ 1]
+  const int S = c.cfg.n_steps;
+  double* nxt = c.xb[c.cur ^ 1];
+  const long long traj_stride = (long long)k * c.n_loc;
+  if (S == 0) {
+    DAB_CUDA(h, cudaMemcpy2DAsync(nxt, sizeof(double) * c.n_loc, xa, sizeof(double) * c.ld_e,
+                                  sizeof(double) * c.n_loc, k, cudaMemcpyDeviceToDevice, h->stream));
+  } else if (S <= c.first_steps) {
+    DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), nxt, out_traj, c.n_loc, k, S, c.cfg.model_dt,
+                                    c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l, -(long long)c.halo_l,
+                                    c.n_loc + c.halo_r, traj_stride, h->sms, h->stream));
+    h->launches++;
+  } else {
+    // long window on one rank: first chunk from the extended buffer, the rest periodic.
+    // chunk outputs alternate between the two Xb buffers and a scratch so the last lands in nxt.
+    DAB_CUDA(h, h->s_partial.reserve(sizeof(double) * (size_t)k * c.n_loc));
+    double* tmp = h->s_partial.as<double>();
+    const int maxs = l96_max_steps_per_launch();
+    const int rest = S - c.first_steps;
+    const int rest_chunks = (rest + maxs - 1) / maxs;
+    double* first_dst = (rest_chunks % 2 == 0) ? nxt : tmp;
+    DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), first_dst, out_traj, c.n_loc, k, c.first_steps,
+                                    c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l,
+                                    -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms, h->stream));
+    h->launches++;
+    const double* src = first_dst;
+    int done = c.first_steps;
+    for (int ch = 0; ch < rest_chunks; ++ch) {
+      const int s = (S - done) < maxs ? (S - done) : maxs;
+      double* dst = (src == tmp) ? nxt : tmp;
+      DAB_CUDA(h, l96_forecast_launch(src, dst, out_traj ? out_traj + (long long)done * traj_stride : nullptr,
+                                      c.n_loc, k, s, c.cfg.model_dt, c.cfg.forcing, c.n_loc, c.n_loc, true,
+                                      0, 0, 0, traj_stride, h->sms, h->stream));
+      h->launches++;
+      src = dst;
+      done += s;
+    }
+  }
+  c.cur ^= 1;
+  return 0;
+}
+
+int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready);
+  DAB_ARG(h, cycle >= 0 && cycle < h->cyc.cfg.n_cycles);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  return cycler_update(h, cycle, nullptr, out_analysis_dev, nullptr);
+}
+
+int dab_cycler_run(dab_handle* h, int c0, int c1, double* out_analysis, double* out_traj) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready);
+  Cycler& c = h->cyc;
+  DAB_ARG(h, c.cfg.world == 1);
+  DAB_ARG(h, c0 >= 0 && c1 >= c0 && c1 <= c.cfg.n_cycles);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  const size_t slab = (size_t)c.cfg.ensemble_dim * c.n_loc;
+  for (int cy = c0; cy < c1; ++cy) {
+    int rc = dab_cycler_stats(h, cy);
+    if (rc) return rc;
+    rc = cycler_update(h, cy, out_analysis ? out_analysis + (size_t)(cy - c0) * slab : nullptr, nullptr,
+                       out_traj ? out_traj + (size_t)(cy - c0) * c.cfg.n_steps * slab : nullptr);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_out != nullptr && (which == 0 || which == 1));
+  static_assert(sizeof(cudaIpcMemHandle_t) == DAB_IPC_HANDLE_BYTES, "IPC handle size");
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  DAB_CUDA(h, cudaIpcGetMemHandle(&mh, h->cyc.xb[which]));
+  memcpy(handle_out, &mh, sizeof(mh));
+  return 0;
+}
+
+int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* handle_in) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_in != nullptr && (which == 0 || which == 1));
+  DAB_ARG(h, peer_rank >= 0 && peer_rank < h->cyc.cfg.world && peer_rank != h->cyc.cfg.rank);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle_in, sizeof(mh));
+  void* p = nullptr;
+  DAB_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->cyc.peer[peer_rank][which] = static_cast<const double*>(p);
+  h->cyc.peer_open[peer_rank][which] = true;
+  return 0;
+}
+
+int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                            const double* obs_values, const int64_t* system_index,
+                            const int64_t* padded_time_idx, double* out_analysis) {
+  DAB_ARG(h, h != nullptr && cfg != nullptr && x0 != nullptr);
+  DAB_ARG(h, cfg->world == 1);
+  int rc = dab_cycler_setup(h, cfg, obs_values, system_index, padded_time_idx);
+  if (rc) return rc;
+  // pin the output range if the caller did not, so the per-cycle D2H overlaps the next cycle
+  bool registered = false;
+  const size_t out_bytes = sizeof(double) * (size_t)cfg->n_cycles * cfg->ensemble_dim * cfg->system_dim;
+  if (out_analysis && out_bytes) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, out_analysis);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
+      if (cudaHostRegister(out_analysis, out_bytes, cudaHostRegisterDefault) == cudaSuccess) registered = true;
+      else cudaGetLastError();
+    }
+  }
+  rc = dab_cycler_set_state(h, x0, 1);
+  if (!rc) rc = dab_cycler_run(h, 0, cfg->n_cycles, out_analysis, nullptr);
+  if (!rc) rc = dab_sync(h);
+  if (registered) cudaHostUnregister(out_analysis);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// Internal launch interface between the engine (engine.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace dab {
+
+constexpr int kMaxRanks = 8;
+
+// K1  l96_forecast.cu
+int l96_max_steps_per_launch();
+cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
+                                int n_steps, double dt, double F, long long in_ld, long long out_ld,
+                                bool periodic, long long in_base, long long in_lo, long long in_hi,
+                                long long traj_stride, int sms, cudaStream_t st);
+
+// K2/K3  etkf_contract.cu
+int contract_k8(int k);
+int contract_grid(long long n_rows, int sms);
+size_t contract_partial_doubles(int k, int n_cta);
+cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
+                            const double* obs_val, const long long* seg, int n_seg,
+                            long long n_rows, double r_inv, double* partial, double* stats,
+                            int grid, cudaStream_t st);
+cudaError_t gather_launch(const double* X, long long ld, int k, const long long* idx,
+                          const unsigned char* mask, long long n_y, double* Yb, cudaStream_t st);
+cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
+                            long long n_y, int* loc, double* val, cudaStream_t st);
+
+// K4  etkf_eig.cu
+size_t eig_smem_bytes(int k);
+cudaError_t eig_transform_launch(const double* stats, int k, double rho, int empty_R, double* T,
+                                 double* lam_out, int* info_out, cudaStream_t st);
+
+// K5  etkf_transform.cu
+struct TransformArgs {
+  const double* T;                 // [k][k] row-major, Xa = Xb T
+  const double* src[kMaxRanks];    // Xb base pointer of every rank's slab (own + peer-mapped)
+  long long src_ld;                // member stride of the Xb slabs
+  double* dst;                     // extended-layout output rows
+  long long dst_ld, dst_base;      // member stride; column of slab position 0
+  long long n_loc, n_global, n0;   // slab length, ring size, first global column of this rank
+  int halo_l, halo_r, k, rank;
+};
+cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st);
+
+}  // namespace dab

@@ -1,0 +1,150 @@
+/* dab_b200.h -- C ABI of the B200-native ETKF cycling hot path for DataAssimBench.
+ *
+ * Drop-in boundary for ONE path of StevePny/DataAssimBench: `dabench.dacycler.ETKF.cycle()`
+ * on a Lorenz-96 ensemble (forecast -> observation gather -> ETKF analysis).  The reference is
+ * pure Python/JAX and has no FFI of its own, so each entry point below cites the reference
+ * *function* it replaces (file:line under the reference repo); INTEGRATION.md shows the ctypes
+ * stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; all floating data is FP64; ensembles are member-major [k][N]
+ *     (the `x[ensemble, index]` array of the reference's input Dataset);
+ *   - every function returns 0 on success, <0 for an argument error, >0 for a CUDA error code;
+ *     the message is available from dab_last_error(); no C++ exception crosses the boundary;
+ *   - "dev" pointers are device pointers owned by the caller (e.g. torch tensors); the library
+ *     never frees caller memory; "host" pointers are host memory (pinned for async overlap);
+ *   - work is enqueued on the stream passed in (or the handle's own stream for the cycler);
+ *     nothing synchronises implicitly except dab_destroy, dab_sync and the *_host entry points;
+ *   - one handle per host thread and per GPU; multi-GPU = one process (rank) per GPU, the
+ *     k*k+k statistics are all-reduced by the caller between dab_cycler_stats and
+ *     dab_cycler_update (NCCL through torch.distributed), halos travel by peer-mapped loads.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DAB_B200_H
+#define DAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DAB_API __attribute__((visibility("default")))
+#else
+#define DAB_API
+#endif
+
+typedef struct dab_handle dab_handle;
+
+#define DAB_MAX_ENSEMBLE 128   /* k <= 128: the eigensolver lives in one CTA's shared memory */
+#define DAB_MAX_RANKS 8
+#define DAB_IPC_HANDLE_BYTES 64
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+DAB_API int dab_version(void);
+DAB_API int dab_create(dab_handle** out, int device);
+DAB_API int dab_destroy(dab_handle* h);
+DAB_API int dab_sync(dab_handle* h);
+DAB_API const char* dab_last_error(const dab_handle* h);   /* h may be NULL: last create() error */
+
+/* ---- K1: Lorenz-96 RK4 ensemble forecast -----------------------------------------------
+ * Replaces ETKF._step_forecast (dabench/dacycler/_etkf.py:64-80) -> Model.forecast ->
+ * Data.generate (dabench/data/_data.py:86-211) -> integrate (dabench/data/_utils.py:16-57)
+ * with Lorenz96.rhs (dabench/data/_lorenz96.py:119-151), for all k members at once, with
+ * fixed-step classical RK4 (BASELINE.json north star) instead of adaptive Dormand-Prince.
+ *   x_in  [k][N] dev, x_out [k][N] dev (may NOT alias x_in)
+ *   traj  nullable dev [n_steps][k][N]: state after step 1..n_steps
+ *         (the reference's generate(n_steps+1) trajectory without its initial point) */
+DAB_API int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj,
+                         int64_t N, int k, int n_steps, double dt, double F, void* stream);
+
+/* ---- K2: observation operator as a gather ----------------------------------------------
+ * Replaces the dense one-hot H (DACycler._calc_default_H, dabench/dacycler/_dacycler.py:58-66),
+ * its masking (dabench/dacycler/_etkf.py:202-203) and ETKF._apply_obsop `H @ Xb`
+ * (dabench/dacycler/_etkf.py:82-92).  Also the device equivalent of the legacy
+ * ObsOp._index_state_vec (dabench/obsop/_obsop.py:43-58).  Bit-exact copy.
+ *   X [k][N] dev; idx [n_y] dev int64; mask nullable [n_y] dev uint8 (0 = row zeroed);
+ *   Yb [k][n_y] dev */
+DAB_API int dab_obs_gather_f64(dab_handle* h, const double* X, const int64_t* idx, const uint8_t* mask,
+                       double* Yb, int64_t N, int k, int64_t n_y, void* stream);
+
+/* ---- K3+K4: statistics and transform matrix (exposed for tests and for rank-parallel use) -
+ * stats = [C (k*k, row-major) | g (k)] with C = Yb'^T Rinv Yb', g = Yb'^T Rinv (y - ybar)
+ * (dabench/dacycler/_etkf.py:137-146,154) for R = obs_error_sd^2 I
+ * (DACycler._calc_default_R, dabench/dacycler/_dacycler.py:68-72). */
+DAB_API int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, const int64_t* idx,
+                       const uint8_t* mask, double obs_error_sd, int64_t N, int k, int64_t n_y,
+                       double* stats, void* stream);
+/* T [k][k] dev row-major with Xa[N,k] = Xb[N,k] T  (dabench/dacycler/_etkf.py:142-161);
+ * empty_R != 0 selects the reference's zero branch (:149-152).
+ * lam nullable dev [k]: eigenvalues of (k-1)/rho I + C; sweeps nullable dev int. */
+DAB_API int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, double rho,
+                                  int empty_R, double* T, double* lam, int* sweeps, void* stream);
+
+/* ---- single analysis --------------------------------------------------------------------
+ * Replaces ETKF._cycle_obsop + ETKF._compute_analysis (dabench/dacycler/_etkf.py:94-213) for
+ * the default operators (H = index gather, R = sd^2 I).
+ *   Xb [k][N] dev, Xa [k][N] dev (may not alias), y [n_y] dev, idx [n_y] dev int64,
+ *   mask nullable [n_y] dev uint8 (time mask AND location mask), rho = multiplicative inflation.
+ *   n_y == 0 reproduces the reference's empty-R branch. */
+DAB_API int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                          const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
+                          int64_t N, int k, int64_t n_y, void* stream);
+
+/* ---- the cycler: DACycler.cycle() for the ETKF -------------------------------------------
+ * Replaces DACycler.cycle / _cycle_and_forecast (dabench/dacycler/_dacycler.py:110-141,186-290):
+ * per cycle  analysis (K3,K4,K5)  then  forecast (K1), state resident in HBM throughout. */
+typedef struct dab_cycle_config {
+  int64_t system_dim;        /* N: global ring size */
+  int32_t ensemble_dim;      /* k */
+  int32_t n_steps;           /* model steps per window = steps_per_window - 1 (_dacycler.py:233) */
+  double model_dt;           /* the forecast model's own delta_t */
+  double forcing;            /* Lorenz-96 F */
+  double rho;                /* multiplicative_inflation (_etkf.py:54) */
+  double obs_error_sd;       /* R = sd^2 I */
+  int64_t n_obs_times;       /* observation Dataset: sizes time x observations */
+  int64_t n_obs;
+  int32_t stationary;        /* attrs['stationary_observers'] (_dacycler.py:262-268) */
+  int32_t n_cycles;
+  int32_t t_pad;             /* columns of the padded time-index table (_utils.py:97-119) */
+  int32_t rank, world;       /* grid sharding: rank owns columns [rank*N/world, (rank+1)*N/world) */
+} dab_cycle_config;
+
+/* obs_values [n_obs_times][n_obs] host (NaN = padded slot when not stationary),
+ * system_index [n_obs_times][n_obs] host int64 (dabench/observer/_observer.py:327-328),
+ * padded_time_idx [n_cycles][t_pad] host int64, 0 = masked, t+1 otherwise
+ * (`all_filtered_padded`, dabench/dacycler/_dacycler.py:259). */
+DAB_API int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                     const int64_t* system_index, const int64_t* padded_time_idx);
+/* local slab [k][N/world]; is_host selects the copy direction kind */
+DAB_API int dab_cycler_set_state(dab_handle* h, const double* x, int is_host);
+DAB_API int dab_cycler_get_state(dab_handle* h, double* x, int is_host);
+/* Run cycles [c0, c1) on one rank (world == 1).  out_analysis nullable host
+ * [c1-c0][k][N]: analysis of every cycle (`isel(cycle_timestep=0)`, _dacycler.py:290), copied
+ * device->host overlapped with the next cycle's compute.  out_traj nullable DEVICE
+ * [c1-c0][n_steps][k][N]: forecast steps 1..n_steps of every cycle (return_forecast=True). */
+DAB_API int dab_cycler_run(dab_handle* h, int c0, int c1, double* out_analysis, double* out_traj);
+/* Rank-parallel phases (world >= 1): stats -> [caller all-reduces dab_cycler_stats_ptr] -> update */
+DAB_API int dab_cycler_stats(dab_handle* h, int cycle);
+DAB_API double* dab_cycler_stats_ptr(dab_handle* h);            /* dev, k*k+k doubles */
+DAB_API int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev /* nullable [k][N/world] */);
+/* Peer plumbing for the fused halo exchange (CUDA IPC, one process per GPU):
+ * which = 0/1 selects the two background (Xb) buffers. */
+DAB_API int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out /* 64 bytes */);
+DAB_API int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* handle_in);
+DAB_API void* dab_cycler_stream(dab_handle* h);                  /* cudaStream_t the cycler enqueues on */
+/* device pointers of the current background / last analysis (extended layout) for tests */
+DAB_API double* dab_cycler_background_ptr(dab_handle* h);
+DAB_API int dab_cycler_kernel_launches(dab_handle* h);           /* kernels launched since setup */
+
+/* One call = DACycler.cycle() with HOST buffers (world == 1): setup, H2D of the ensemble and the
+ * observations, n_cycles cycles, D2H of every analysis.  x0 [k][N] host; out [n_cycles][k][N] host. */
+DAB_API int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                            const double* obs_values, const int64_t* system_index,
+                            const int64_t* padded_time_idx, double* out_analysis);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAB_B200_H */

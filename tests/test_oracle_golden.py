@@ -183,3 +183,12 @@ def test_metrics():
     assert metrics.mse(a, b) == pytest.approx((0.25 + 4) / 3)
     assert metrics.rmse(a, b) == pytest.approx(np.sqrt((0.25 + 4) / 3))
     assert metrics.mae(a, b) == pytest.approx(2.5 / 3)
+
+
+def test_get_all_times_keeps_reference_float_quirk():
+    """dabench/dacycler/_utils.py:32-36 builds the window centres with
+    arange(0, n*w, w); for e.g. n=12, w=0.1 that arange has 13 elements and the reference
+    fails on the broadcast.  The restatement keeps that behaviour on purpose."""
+    assert len(windows.get_all_times(0.0, 0.1, 10)) == 10
+    with pytest.raises(ValueError):
+        windows.get_all_times(0.0, 0.1, 12)
