@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- ETKF cycles/s on Lorenz-96 N=65,536, k=64 (BASELINE.json configs[2], "C3").
+
+One "step" = one ETKF cycle = analysis (gather + contraction + eigensolver + transform) followed
+by the S=20-step RK4 ensemble forecast.  Prints ONE JSON line (see the task contract):
+
+  value          cycles/s with everything resident in HBM (CUDA events on the launching stream)
+  e2e            cycles/s through the host-buffer C-ABI call `dab_etkf_cycle_host_f64`
+                 (H2D of ensemble + observations and D2H of every analysis inside the timed region)
+  roofline       the forecast kernel (FP64-pipe bound) against the FP64 peak measured in this run
+  kernels        time share and roofline of every kernel of the cycle
+  cpu_baseline   the NumPy oracle (a restatement of the reference, NOT JAX) on this box's host cores
+
+`--impl reference` times only the CPU oracle ("port": JAX/xarray are not installable here).
+
+The filter diverges after ~20 cycles at these shapes (k << N, no localisation), so
+the experiment is a 10-cycle run from a fresh ensemble, repeated; the reset (one 33.5 MB D2D copy
+per 10 cycles) stays INSIDE the timed region, and the final state is asserted finite.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, k, obs fraction, S, dt, sd, rho
+    "c3": dict(N=65536, k=64, obs_frac=0.3, S=20, dt=0.01, sd=1.0, rho=1.0,
+               label="Lorenz96 N=65536 k=64 ETKF, 30% random stationary obs, S=20 RK4 steps/cycle"),
+    "c4": dict(N=4194304, k=64, obs_frac=0.3, S=20, dt=0.01, sd=1.0, rho=1.0,
+               label="Lorenz96 N=4194304 k=64 ETKF, 30% random stationary obs, S=20"),
+    "c5": dict(N=1048576, k=128, obs_frac=1.0, S=20, dt=0.01, sd=1.0, rho=1.0,
+               label="Lorenz96 N=1048576 k=128 ETKF, 100% obs, S=20"),
+    "c1": dict(N=36, k=10, obs_frac=0.5, S=20, dt=0.01, sd=1.0, rho=1.0,
+               label="Lorenz96 N=36 k=10 ETKF, 50% stationary obs, S=20"),
+}
+BLOCK = 10          # cycles per experiment (fresh ensemble every BLOCK cycles)
+FLOPS_PER_POINT_STEP = 29.0
+
+
+def make_workload(name, seed=42):
+    """Synthetic experiment: truth spun up with RK4, ensemble = truth + N(0,1),
+    one observation time per window placed at the analysis time, stationary random locations
+    drawn like Observer does (default_rng.choice(N, n_obs, replace=False, shuffle=False))."""
+    from oracle import l96 as o_l96, windows as o_win
+    w = dict(WORKLOADS[name])
+    N, k, S, dt = w["N"], w["k"], w["S"], w["dt"]
+    rng = np.random.default_rng(seed)
+    truth = 8.0 + rng.standard_normal(N)
+    truth = o_l96.rk4_forecast(truth, 500, dt)
+    n_obs = int(round(w["obs_frac"] * N))
+    locs = np.sort(rng.choice(N, n_obs, replace=False, shuffle=False)) if n_obs == N else \
+        rng.choice(N, n_obs, replace=False, shuffle=False)
+    X0 = truth + rng.standard_normal((k, N))
+    vals = np.empty((BLOCK, n_obs))
+    x = truth
+    for c in range(BLOCK):
+        vals[c] = x[locs] + w["sd"] * rng.standard_normal(n_obs)
+        if c + 1 < BLOCK:
+            x = o_l96.rk4_forecast(x, S, dt)
+    obs_times = np.arange(BLOCK) * (S * dt)
+    times = o_win.get_all_times(0.0, S * dt, BLOCK)
+    padded = np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, obs_times, S * dt)))
+    w.update(n_obs=n_obs, X0=np.ascontiguousarray(X0), vals=np.ascontiguousarray(vals),
+             sysidx=np.ascontiguousarray(np.tile(locs, (BLOCK, 1)).astype(np.int64)), padded=padded,
+             name=name)
+    return w
+
+
+# ------------------------------------------------------------------------------ CPU oracle
+def oracle_cycles(w, n_cycles):
+    """Run n_cycles cycles of the ref-sparse oracle (analysis_sparse + vectorised RK4)."""
+    from oracle import l96 as o_l96, etkf as o_etkf
+    X = w["X0"].copy()
+    wts = np.full(w["n_obs"], 1.0 / w["sd"] ** 2)
+    for c in range(n_cycles):
+        cc = c % BLOCK
+        if cc == 0:
+            X = w["X0"].copy()
+        Xa = o_etkf.analysis_sparse(X, w["vals"][cc], w["sysidx"][cc], wts, w["rho"])
+        X = o_l96.rk4_forecast(Xa, w["S"], w["dt"])
+    return X
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return int(n)
+    except Exception:
+        return 1
+
+
+def time_oracle(w, steps, warmup, budget_s=60.0):
+    """(cycles/s, cycles timed).  Bounded: stops early once `budget_s` is spent."""
+    for _ in range(warmup):
+        oracle_cycles(w, 1)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        oracle_cycles(w, 1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """nvidia-smi's clocks line through NVML (same counters), every 20 ms."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples = []
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_sm = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                pw = nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0
+                self.samples.append((time.perf_counter(), sm, int(reasons), pw))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self, t0, t1):
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting",
+                 0x100: "display_clocks_setting"}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed"
+        if len(inside) < 3:
+            inside, window = self.samples, "whole-run"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        active = set()
+        for s in inside:
+            for bit, n in names.items():
+                if s[2] & bit:
+                    active.add(n)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(active), "samples": len(inside), "window": window,
+                "power_w_max": max(s[3] for s in inside)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload)
+    cps, done = time_oracle(w, args.steps, min(args.warmup, 1), budget_s=args.cpu_budget)
+    k, S = w["k"], w["S"]
+    line = {
+        "impl": "reference", "metric": "etkf_cycles_per_s", "value": cps, "unit": "cycles/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 / cps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "N": w["N"], "k": k, "n_obs": w["n_obs"], "S": S,
+                   "window": S * w["dt"], "integrator": "rk4"},
+        "member_steps_per_s": cps * k * S,
+        "cpu_baseline": {"value": cps, "unit": "cycles/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": "%d full cycles of the NumPy/SciPy oracle (gather + diagonal R + eigh + "
+                                   "vectorised RK4); JAX/xarray are absent, so this is a restatement of "
+                                   "the reference, not the reference" % done,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": cps, "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from dataassimbench_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
+                         % (args.gpus, world))
+
+    w = make_workload(args.workload)
+    N, k, S = w["N"], w["k"], w["S"]
+    H = _native.Handle(local_rank)
+    from dataassimbench_b200.sharded import ShardedCycler
+    cyc = ShardedCycler(H, w, BLOCK, rank, world)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(H.cycler_stream())
+    K, W = args.steps, args.warmup
+
+    def run_cycles(n):
+        done = 0
+        while done < n:
+            m = min(BLOCK, n - done)
+            cyc.reset()
+            cyc.run(0, m)
+            done += m
+
+    run_cycles(W)
+    H.sync()
+    barrier()
+    launches0 = H.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    run_cycles(K)
+    ev1.record(stream)
+    H.sync()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    launches = H.kernel_launches() - launches0
+    final = cyc.state_is_finite()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        f = torch.tensor([1.0 if final else 0.0], device="cuda")
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        final = bool(f.item() > 0.5)
+    cps = K / (ms * 1e-3)
+
+    # ---- per-kernel timing (separate pass: event records between kernels perturb the main timing)
+    H.set_profiling(True)
+    run_cycles(BLOCK)            # warm
+    H.read_profile()
+    run_cycles(max(BLOCK, min(K, 100)))
+    prof = H.read_profile()
+    H.set_profiling(False)
+    peaks = H.measure_fp64_peak()
+    sampler.stop_flag = True
+
+    # ---- e2e through the host-buffer C-ABI call (rank-local; N=1 only)
+    e2e = None
+    if world == 1:
+        x0 = torch.from_numpy(w["X0"]).pin_memory()
+        out = torch.empty((BLOCK, k, N), dtype=torch.float64).pin_memory()
+        cfg = cyc.config(n_cycles=BLOCK)
+        reps = max(1, min(K, 200) // BLOCK)
+        H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)      # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)
+        t1 = time.perf_counter()
+        assert bool(torch.isfinite(out).all())
+        h2d = (w["X0"].nbytes + w["vals"].nbytes + w["sysidx"].nbytes + w["padded"].nbytes) / BLOCK
+        e2e = {"value": reps * BLOCK / (t1 - t0), "unit": "cycles/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * N * 8),
+               "timer": "host wall clock around dab_etkf_cycle_host_f64 (setup, H2D, %d cycles, "
+                        "per-cycle D2H of the analysis, sync)" % BLOCK, "steps": reps * BLOCK}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline bookkeeping
+    measured = {}
+    try:
+        measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = measured.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in measured else "fallback"
+    fp64_peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
+    n_loc = N // world
+    n_y = w["n_obs"] / world
+    alg = {   # algorithmic flops / bytes per launch on one rank
+        "forecast": dict(flops=FLOPS_PER_POINT_STEP * n_loc * k * S, bytes=16.0 * n_loc * k),
+        "transform": dict(flops=2.0 * n_loc * k * k, bytes=16.0 * n_loc * k),
+        "contraction": dict(flops=2.0 * n_y * k * k + 4.0 * n_y * k, bytes=8.0 * k * n_y + 16.0 * n_y),
+        "reduction": dict(flops=0.0, bytes=0.0),
+        "eigensolver": dict(flops=0.0, bytes=0.0),
+    }
+    kernels = {}
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    for name, (tms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        us = 1e3 * tms / cnt
+        ent = {"us": round(us, 2), "share": round(tms / tot_ms, 4)}
+        a = alg[name]
+        if a["flops"]:
+            ent["tflops"] = round(a["flops"] / (us * 1e-6) / 1e12, 3)
+            ent["frac_fp64"] = round(ent["tflops"] / fp64_peak, 4)
+        if a["bytes"]:
+            ent["gbs"] = round(a["bytes"] / (us * 1e-6) / 1e9, 1)
+            ent["frac_hbm"] = round(ent["gbs"] / hbm_peak, 4)
+        kernels[name] = ent
+    fc = kernels.get("forecast", {})
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("forecast")
+    except Exception:
+        pass
+    roofline = {"kernel": "l96_rk4_window_kernel (forecast)", "bound": "fp64",
+                "achieved": fc.get("tflops"), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
+                "frac": fc.get("frac_fp64"), "traffic": traffic,
+                "peak_source": "DMMA.8x8x4 / DFMA chains measured in this run through "
+                               "dab_measure_fp64_peak (dfma %.2f, dmma %.2f TFLOP/s)"
+                               % (peaks["dfma_tflops"], peaks["dmma_tflops"]),
+                "flops_per_launch": alg["forecast"]["flops"],
+                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cps_cpu, done = time_oracle(w, 2, 0, budget_s=args.cpu_budget)
+        cpu = {"value": cps_cpu, "unit": "cycles/s", "cores": cpu_threads(), "kind": "port",
+               "sample": "%d full cycles of the NumPy/SciPy oracle on this box's host cores "
+                         "(restatement of the reference; JAX is not installable here)" % done,
+               "host_cpus": os.cpu_count()}
+
+    line = {
+        "metric": "etkf_cycles_per_s", "value": cps, "unit": "cycles/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "N": N, "k": k, "n_obs": w["n_obs"], "S": S,
+                   "window": S * w["dt"], "integrator": "rk4",
+                   "l2": "state (%.1f MB) is L2-resident; no flush: the cycle streams through all of it "
+                         "between reuses" % (N * k * 8 / 1e6),
+                   "experiment": "%d-cycle run from a fresh ensemble, repeated; reset copy inside the "
+                                 "timed region" % BLOCK,
+                   "parallelism": "grid-sharded x%d" % world if world > 1 else "single GPU"},
+        "member_steps_per_s": cps * k * S,
+        "point_steps_per_s": cps * k * S * N,
+        "all_finite": final,
+        "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": sampler.summary(t_wall0, t_wall1),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU oracle time")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "dab_cycler_stream": (_P, [_P]),
     "dab_cycler_background_ptr": (_P, [_P]),
     "dab_cycler_kernel_launches": (C.c_int, [_P]),
+    "dab_cycler_set_profiling": (C.c_int, [_P, C.c_int]),
+    "dab_cycler_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "dab_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dab_etkf_cycle_host_f64": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -200,6 +203,23 @@ class Handle:
 
     def kernel_launches(self):
         return self._lib.dab_cycler_kernel_launches(self._h)
+
+    PROFILE_KERNELS = ("contraction", "reduction", "eigensolver", "transform", "forecast")
+
+    def set_profiling(self, on):
+        self._check(self._lib.dab_cycler_set_profiling(self._h, int(on)))
+
+    def read_profile(self):
+        """{kernel: (total_ms, launches)} since profiling was switched on / last read."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int * 5)()
+        self._check(self._lib.dab_cycler_read_profile(self._h, ms, cnt))
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(self.PROFILE_KERNELS)}
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.dab_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value}
 
     def etkf_cycle_host(self, cfg, x0, obs_values, system_index, padded_time_idx, out_analysis):
         self._check(self._lib.dab_etkf_cycle_host_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),

@@ -58,7 +58,27 @@ struct dab_handle {
   long launches = 0;
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   Cycler cyc;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<int> prof_tags;
+  size_t prof_used = 0;
 };
+
+enum { PROF_START = -1, PROF_CONTRACT = 0, PROF_REDUCE = 1, PROF_EIG = 2, PROF_TRANSFORM = 3, PROF_FORECAST = 4 };
+
+static void prof_mark(dab_handle* h, int tag) {
+  if (!h->profiling) return;
+  if (h->prof_used == h->prof_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->prof_pool.push_back(e);
+  }
+  cudaEventRecord(h->prof_pool[h->prof_used], h->stream);
+  if (h->prof_tags.size() <= h->prof_used) h->prof_tags.resize(h->prof_used + 1);
+  h->prof_tags[h->prof_used] = tag;
+  h->prof_used++;
+}
 
 static std::string g_create_err;
 
@@ -139,6 +159,7 @@ int dab_destroy(dab_handle* h) {
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_seg.release();
   h->s_partial.release(); h->s_stats.release(); h->s_T.release();
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -223,8 +244,8 @@ static int stats_from_arrays(dab_handle* h, const double* X, const double* y, co
   const long long seg[3] = {0, n_y, 0};
   DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
   DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
-                              h->s_seg.as<long long>(), 1, n_y, 1.0 / (sd * sd),
-                              h->s_partial.as<double>(), stats, grid, st));
+                              h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, st));
+  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, 1.0 / (sd * sd), stats, st));
   h->launches += (n_y > 0 ? 1 : 0) + 2;
   return 0;
 }
@@ -416,10 +437,15 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
   const long long rows = c.n_rows[(size_t)cycle];
   const int grid = contract_grid(rows, h->sms);
   const int ns = c.n_seg[(size_t)cycle] > 0 ? c.n_seg[(size_t)cycle] : 1;
+  prof_mark(h, PROF_START);
   DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
                               c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
-                              1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd),
-                              c.partial.as<double>(), c.stats.as<double>(), grid, h->stream));
+                              c.partial.as<double>(), grid, h->stream));
+  prof_mark(h, PROF_CONTRACT);
+  DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k,
+                                  1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd),
+                                  c.stats.as<double>(), h->stream));
+  prof_mark(h, PROF_REDUCE);
   h->launches += 2;
   return 0;
 }
@@ -435,8 +461,10 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   Cycler& c = h->cyc;
   const int k = c.cfg.ensemble_dim;
   const int eb = cycle & 1;
+  prof_mark(h, PROF_START);
   DAB_CUDA(h, eig_transform_launch(c.stats.as<double>(), k, c.cfg.rho, c.empty_R, c.T.as<double>(),
                                    c.lam.as<double>(), c.info.as<int>(), h->stream));
+  prof_mark(h, PROF_EIG);
   if (c.copied_pending[eb]) {                 // the D2H of cycle-2's analysis still reads ext[eb]
     DAB_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_copied[eb], 0));
     c.copied_pending[eb] = false;
@@ -455,6 +483,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   a.n_loc = c.n_loc; a.n_global = c.cfg.system_dim; a.n0 = c.n0;
   a.halo_l = c.halo_l; a.halo_r = c.halo_r; a.k = k; a.rank = c.cfg.rank;
   DAB_CUDA(h, transform_launch(a, h->sms, h->stream));
+  prof_mark(h, PROF_TRANSFORM);
   h->launches += 2;
   const double* xa = c.ext[eb].as<double>() + c.halo_l;
   if (out_host) {
@@ -470,6 +499,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
                                   sizeof(double) * c.n_loc, k, cudaMemcpyDeviceToDevice, h->stream));
   }
   // forecast: ext[eb] -> xb[cur ^ 1]
+  prof_mark(h, PROF_START);
   const int S = c.cfg.n_steps;
   double* nxt = c.xb[c.cur ^ 1];
   const long long traj_stride = (long long)k * c.n_loc;
@@ -507,6 +537,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
       done += s;
     }
   }
+  prof_mark(h, PROF_FORECAST);
   c.cur ^= 1;
   return 0;
 }
@@ -555,6 +586,37 @@ int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* h
   DAB_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
   h->cyc.peer[peer_rank][which] = static_cast<const double*>(p);
   h->cyc.peer_open[peer_rank][which] = true;
+  return 0;
+}
+
+int dab_cycler_set_profiling(dab_handle* h, int on) {
+  DAB_ARG(h, h != nullptr);
+  h->profiling = on != 0;
+  h->prof_used = 0;
+  return 0;
+}
+
+int dab_cycler_read_profile(dab_handle* h, double* ms_out, int* count_out) {
+  DAB_ARG(h, h != nullptr && ms_out != nullptr && count_out != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 5; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (size_t i = 1; i < h->prof_used; ++i) {
+    const int tag = h->prof_tags[i];
+    if (tag < 0) continue;
+    float ms = 0.f;
+    DAB_CUDA(h, cudaEventElapsedTime(&ms, h->prof_pool[i - 1], h->prof_pool[i]));
+    ms_out[tag] += ms;
+    count_out[tag] += 1;
+  }
+  h->prof_used = 0;
+  return 0;
+}
+
+int dab_measure_fp64_peak(dab_handle* h, double* dfma_tflops, double* dmma_tflops) {
+  DAB_ARG(h, h != nullptr && dfma_tflops != nullptr && dmma_tflops != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, fp64_peak_measure(h->sms, dfma_tflops, dmma_tflops, h->stream));
   return 0;
 }
 

@@ -155,8 +155,7 @@ int contract_grid(long long n_rows, int sms) {
 
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
                             const double* obs_val, const long long* seg, int n_seg,
-                            long long n_rows, double r_inv, double* partial, double* stats,
-                            int grid, cudaStream_t st) {
+                            long long n_rows, double* partial, int grid, cudaStream_t st) {
   const int k8 = contract_k8(k);
   switch (k8) {
     case 2: contract_kernel<2><<<grid, 64, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
@@ -164,10 +163,13 @@ cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs
     case 8: contract_kernel<8><<<grid, 256, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
     default: contract_kernel<16><<<grid, 512, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
+                                cudaStream_t st) {
   const int n_el = k * k + k;
-  stats_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partial, grid, 8 * k8, k, r_inv, stats);
+  stats_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats);
   return cudaGetLastError();
 }
 

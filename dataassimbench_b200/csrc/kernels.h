@@ -21,8 +21,9 @@ int contract_grid(long long n_rows, int sms);
 size_t contract_partial_doubles(int k, int n_cta);
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
                             const double* obs_val, const long long* seg, int n_seg,
-                            long long n_rows, double r_inv, double* partial, double* stats,
-                            int grid, cudaStream_t st);
+                            long long n_rows, double* partial, int grid, cudaStream_t st);
+cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
+                                cudaStream_t st);
 cudaError_t gather_launch(const double* X, long long ld, int k, const long long* idx,
                           const unsigned char* mask, long long n_y, double* Yb, cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
@@ -44,5 +45,8 @@ struct TransformArgs {
   int halo_l, halo_r, k, rank;
 };
 cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st);
+
+// fp64_peak.cu: measured FP64 roofline denominators (TFLOP/s)
+cudaError_t fp64_peak_measure(int sms, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 
 }  // namespace dab

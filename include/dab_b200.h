@@ -138,6 +138,14 @@ DAB_API void* dab_cycler_stream(dab_handle* h);                  /* cudaStream_t
 DAB_API double* dab_cycler_background_ptr(dab_handle* h);
 DAB_API int dab_cycler_kernel_launches(dab_handle* h);           /* kernels launched since setup */
 
+/* Measurement aids (bench.py): per-kernel CUDA-event timing on the cycler's stream.
+ * ms_out[5]/count_out[5]: contraction, reduction, eigensolver, transform, forecast. */
+DAB_API int dab_cycler_set_profiling(dab_handle* h, int on);
+DAB_API int dab_cycler_read_profile(dab_handle* h, double* ms_out, int* count_out);
+/* FP64 roofline denominators measured on this device: independent DFMA chains and
+ * DMMA.8x8x4 (TFLOP/s).  MEASURED_PEAKS.json carries no FP64 entry. */
+DAB_API int dab_measure_fp64_peak(dab_handle* h, double* dfma_tflops, double* dmma_tflops);
+
 /* One call = DACycler.cycle() with HOST buffers (world == 1): setup, H2D of the ensemble and the
  * observations, n_cycles cycles, D2H of every analysis.  x0 [k][N] host; out [n_cycles][k][N] host. */
 DAB_API int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
