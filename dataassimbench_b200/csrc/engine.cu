@@ -36,6 +36,7 @@ struct Cycler {
   int empty_R = 0;
   int cur = 0;                             // which Xb buffer holds the current background
   double* xb[2] = {nullptr, nullptr};      // plain [k][n_loc], separately cudaMalloc'ed (IPC-exportable)
+  size_t xb_bytes = 0;
   DevBuf ext[2];                           // extended-layout analysis buffers
   DevBuf obs_loc, obs_val, seg, partial, stats, T, lam, info;
   std::vector<long long> csr_off;          // [n_obs_times + 1]
@@ -99,11 +100,18 @@ static int fail(dab_handle* h, int code, const char* fmt, ...) {
 #define DAB_ARG(h, cond)                                                                     \
   do { if (!(cond)) return fail((h), -1, "invalid argument: %s", #cond); } while (0)
 
-static void cycler_free(dab_handle* h) {
+static void cycler_close_peers(dab_handle* h) {
   Cycler& c = h->cyc;
   for (int r = 0; r < kMaxRanks; ++r)
     for (int w = 0; w < 2; ++w)
       if (c.peer_open[r][w]) { cudaIpcCloseMemHandle(const_cast<double*>(c.peer[r][w])); c.peer_open[r][w] = false; }
+}
+
+// Workspaces are grow-only and survive dab_cycler_setup calls (cudaMalloc/cudaFree cost
+// milliseconds and synchronise the device); everything is released in dab_destroy.
+static void cycler_free(dab_handle* h) {
+  Cycler& c = h->cyc;
+  cycler_close_peers(h);
   for (int w = 0; w < 2; ++w) {
     if (c.xb[w]) cudaFree(c.xb[w]);
     c.xb[w] = nullptr;
@@ -113,6 +121,7 @@ static void cycler_free(dab_handle* h) {
     c.ev_xa[w] = c.ev_copied[w] = nullptr;
     c.copied_pending[w] = false;
   }
+  c.xb_bytes = 0;
   c.obs_loc.release(); c.obs_val.release(); c.seg.release(); c.partial.release();
   c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
   c.ready = false;
@@ -321,8 +330,10 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   DAB_CUDA(h, cudaSetDevice(h->device));
   DAB_CUDA(h, cudaStreamSynchronize(h->stream));
   DAB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
-  cycler_free(h);
   Cycler& c = h->cyc;
+  c.ready = false;
+  cycler_close_peers(h);
+  c.copied_pending[0] = c.copied_pending[1] = false;
   c.cfg = *cfg;
   const int k = cfg->ensemble_dim;
   c.n_loc = cfg->system_dim / cfg->world;
@@ -336,12 +347,19 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   c.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
   c.cur = 0;
   const size_t slab = sizeof(double) * (size_t)k * c.n_loc;
+  if (slab > c.xb_bytes) {
+    for (int w = 0; w < 2; ++w) {
+      if (c.xb[w]) cudaFree(c.xb[w]);
+      c.xb[w] = nullptr;
+    }
+    c.xb_bytes = 0;
+    for (int w = 0; w < 2; ++w) DAB_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&c.xb[w]), slab));
+    c.xb_bytes = slab;
+  }
   for (int w = 0; w < 2; ++w) {
-    DAB_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&c.xb[w]), slab));
     DAB_CUDA(h, c.ext[w].reserve(sizeof(double) * (size_t)k * c.ld_e));
-    DAB_CUDA(h, cudaMemsetAsync(c.ext[w].p, 0, c.ext[w].bytes, h->stream));
-    DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_xa[w], cudaEventDisableTiming));
-    DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_copied[w], cudaEventDisableTiming));
+    if (!c.ev_xa[w]) DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_xa[w], cudaEventDisableTiming));
+    if (!c.ev_copied[w]) DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_copied[w], cudaEventDisableTiming));
   }
   // ---- observations: CSR over observation times, rows owned by this rank, masked rows dropped
   const long long nt = cfg->n_obs_times, no = cfg->n_obs;

@@ -9,172 +9,114 @@
 // by the single matrix  T = U + (I-U)(wa 1^T + Wa),  U = 11^T/k,  so that Xa = Xb T  (K5).
 //
 // Method: A = (k-1)/rho I + C is symmetric positive definite.  One-sided (Hestenes) cyclic
-// Jacobi applied to the columns of G := A: plane rotations from the right until the columns
-// are mutually orthogonal; then G = A V = V L, i.e. column c has norm lambda_c and direction
-// v_c.  No separate V accumulator is needed (backward stable: V L V^T = A + O(eps |A|)), so the
-// whole state is one k x k matrix: 32 KB at k = 64, 128 KB at k = 128 -- one CTA's shared memory.
-// Parallel ordering: round-robin tournament, k/2 disjoint pairs per round, one warp per pair;
-// the three inner products are warp-shuffle reductions.
+// Jacobi on the columns of G := A: plane rotations from the right until the columns are
+// mutually orthogonal; then G = A V = V L, i.e. column c has norm lambda_c and direction v_c.
+// No separate V accumulator is needed (backward stable: V L V^T = A + O(eps |A|)), so the whole
+// state is one k x k matrix: 36 KB at k = 64, 139 KB at k = 128 -- one CTA's shared memory.
+//
+// Mapping (latency- and issue-bound, so every instruction counts):
+//   * round-robin tournament, k/2 disjoint pairs per round, one __syncthreads per round;
+//   * a pair is owned by LPP lanes holding 8 rows each (LPP = 8 at k = 64: four pairs per warp),
+//     so the three inner products cost 3*log2(LPP) shuffles and one 8-deep FMA chain;
+//   * thresholds are tested as gamma^2 > tol^2 alpha beta (no sqrt/div), and the rotation is
+//     r = rsqrt(tau^2 + 4 gamma^2), x = (1 + |tau| r)/2, c = x rsqrt(x), s = sgn(tau) gamma r rsqrt(x)
+//     -- two rsqrt instead of two divisions and two square roots;
+//   * sweeps stop when nothing rotated, or one sweep early once every |gamma|/sqrt(alpha beta)
+//     seen in a sweep was below 1e-8 (quadratic convergence finishes the job within that sweep);
+//   * Wa = V diag(sqrt((k-1)/lambda)) V^T runs on the FP64 tensor core (DMMA.8x8x4).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace dab {
 
-__device__ __forceinline__ double warp_sum(double v) {
+template <int LPP>
+__device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// stats: [k*k] C row-major, then [k] g.  Tout: [k][k] row-major, T[m][j].
-// lam_out (nullable): k eigenvalues of A (unsorted); info_out (nullable): sweeps used.
-template <int RPL>   // rows per lane: ceil(k/32)
-__global__ void __launch_bounds__(1024)
-eig_transform_kernel(const double* __restrict__ stats, int k, double rho, int empty_R,
-                     double* __restrict__ Tout, double* __restrict__ lam_out, int* __restrict__ info_out) {
-  extern __shared__ __align__(16) double sm[];
-  const int kj = (k + 1) & ~1;                 // even number of Jacobi columns (last may be a zero column)
-  const int ld = k;                            // column-major, column c at sm + c*ld
-  double* G = sm;                              // kj * ld
-  double* lam = G + kj * ld;                   // kj
-  double* dw = lam + kj;                       // kj   sqrt((k-1)/lambda)
-  double* da = dw + kj;                        // kj   1/lambda (0 below the pinv cutoff)
-  double* wa = da + kj;                        // k
-  double* proj = wa + kj;                      // kj   v_c . g
-  double* cmean = proj + kj;                   // k
-  __shared__ int s_rot;
+// After convergence: column c of G has norm lambda_c and direction v_c.  Builds T in Tout.
+// G: [ncol][LD] column-major in shared memory with ROWS >= 8*ceil(k/8) zero-padded rows;
+// aux: 6*ncol doubles of shared memory.
+template <int LD, int ROWS>
+__device__ __forceinline__ void build_transform(double* G, double* aux, int ncol, const double* __restrict__ stats,
+                                                int k, double* __restrict__ Tout, double* __restrict__ lam_out,
+                                                int* __restrict__ info_out, int sweeps) {
+  double* lam = aux;                           // ncol
+  double* dw = lam + ncol;                     // ncol  sqrt((k-1)/lambda), 0 beyond k
+  double* da = dw + ncol;                      // ncol  1/lambda (0 below the pinv cutoff)
+  double* wa = da + ncol;                      // ncol
+  double* proj = wa + ncol;                    // ncol  v_c . g
+  double* cmean = proj + ncol;                 // ncol
   __shared__ double s_red[32];
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const double inv_k = 1.0 / (double)k;
-
-  if (empty_R) {                               // reference zero branch: T = U
-    for (int e = tid; e < k * k; e += blockDim.x) Tout[e] = inv_k;
-    if (info_out && tid == 0) *info_out = 0;
-    return;
-  }
-
-  const double shift = (double)(k - 1) / rho;
-  for (int e = tid; e < kj * ld; e += blockDim.x) {
-    const int c = e / ld, r = e - c * ld;
-    double v = 0.0;
-    if (c < k) v = stats[r * k + c] + (r == c ? shift : 0.0);
-    G[e] = v;
-  }
-  __syncthreads();
-
-  const int npairs = kj / 2;
-  const int m = kj - 1;                        // round-robin modulus
-  const double tol = 1.1e-16 * sqrt((double)k) * 4.0;
-  int sweeps = 0;
-  for (; sweeps < 40; ++sweeps) {
-    if (tid == 0) s_rot = 0;
-    __syncthreads();
-    int rotated = 0;
-    for (int rnd = 0; rnd < m; ++rnd) {
-      for (int pr = warp; pr < npairs; pr += nwarp) {
-        int p, q;
-        if (pr == 0) { p = m; q = rnd; }
-        else { p = (rnd + pr) % m; q = (rnd - pr + m) % m; }
-        if (p > q) { const int t_ = p; p = q; q = t_; }
-        double* gp = G + p * ld;
-        double* gq = G + q * ld;
-        double xp[RPL], xq[RPL];
-        double al = 0.0, be = 0.0, ga = 0.0;
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) {
-          const int r = lane + 32 * i;
-          xp[i] = r < k ? gp[r] : 0.0;
-          xq[i] = r < k ? gq[r] : 0.0;
-          al = fma(xp[i], xp[i], al);
-          be = fma(xq[i], xq[i], be);
-          ga = fma(xp[i], xq[i], ga);
-        }
-        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-        if (fabs(ga) > tol * sqrt(al * be)) {   // warp-uniform
-          rotated = 1;
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t_ = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-          const double c_ = rsqrt(fma(t_, t_, 1.0));
-          const double s_ = c_ * t_;
-#pragma unroll
-          for (int i = 0; i < RPL; ++i) {
-            const int r = lane + 32 * i;
-            if (r < k) {
-              gp[r] = c_ * xp[i] - s_ * xq[i];
-              gq[r] = s_ * xp[i] + c_ * xq[i];
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (rotated && lane == 0) s_rot = 1;       // benign race: all writers store 1
-    __syncthreads();
-    const int any = s_rot;
-    __syncthreads();
-    if (!any) break;
-  }
-
-  // eigenvalues = column norms; normalise columns to eigenvectors
+  const int k8 = (k + 7) >> 3;
+  // eigenvalues = column norms; normalise columns to eigenvectors; proj = V^T g
+  const double* gvec = stats + k * k;
   for (int c = warp; c < k; c += nwarp) {
-    double* gc = G + c * ld;
-    double ss = 0.0, pg = 0.0;
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      const int r = lane + 32 * i;
-      const double v = r < k ? gc[r] : 0.0;
-      ss = fma(v, v, ss);
-    }
-    ss = warp_sum(ss);
+    double* gc = G + c * LD;
+    double ss = 0.0;
+    for (int r = lane; r < ROWS; r += 32) ss = fma(gc[r], gc[r], ss);
+    ss = group_sum<32>(ss);
     const double l = sqrt(ss);
     const double il = l > 0.0 ? 1.0 / l : 0.0;
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      const int r = lane + 32 * i;
-      if (r < k) {
-        const double v = gc[r] * il;
-        gc[r] = v;
-        pg = fma(v, stats[k * k + r], pg);
-      }
+    double pg = 0.0;
+    for (int r = lane; r < ROWS; r += 32) {
+      const double v = gc[r] * il;
+      gc[r] = v;
+      if (r < k) pg = fma(v, gvec[r], pg);
     }
-    pg = warp_sum(pg);
+    pg = group_sum<32>(pg);
     if (lane == 0) { lam[c] = l; proj[c] = pg; }
   }
   __syncthreads();
   // pinv cutoff: 1e-15 * largest eigenvalue (rtol semantics of jnp.linalg.pinv)
   double lmax = 0.0;
   for (int c = tid; c < k; c += blockDim.x) lmax = fmax(lmax, lam[c]);
-  lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, 16));
-  lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, 8));
-  lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, 4));
-  lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, 2));
-  lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, 1));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if (lane == 0) s_red[warp] = lmax;
   __syncthreads();
   lmax = 0.0;
   for (int w = 0; w < nwarp; ++w) lmax = fmax(lmax, s_red[w]);
-  for (int c = tid; c < k; c += blockDim.x) {
-    const double l = lam[c];
-    const double inv = l > 1e-15 * lmax ? 1.0 / l : 0.0;
+  for (int c = tid; c < ncol; c += blockDim.x) {
+    double inv = 0.0, l = 0.0;
+    if (c < k) {
+      l = lam[c];
+      inv = l > 1e-15 * lmax ? 1.0 / l : 0.0;
+      if (lam_out) lam_out[c] = l;
+    }
     da[c] = inv;
     dw[c] = sqrt((double)(k - 1) * inv);
-    if (lam_out) lam_out[c] = l;
   }
   __syncthreads();
   // wa = V diag(da) V^T g
   for (int r = tid; r < k; r += blockDim.x) {
     double s = 0.0;
-    for (int c = 0; c < k; ++c) s = fma(G[c * ld + r] * da[c], proj[c], s);
+    for (int c = 0; c < k; ++c) s = fma(G[c * LD + r] * da[c], proj[c], s);
     wa[r] = s;
   }
-  // Wa = V diag(dw) V^T  -> Tout (raw), row-major
-  for (int e = tid; e < k * k; e += blockDim.x) {
-    const int j = e / k, mm = e - j * k;       // consecutive threads: consecutive mm (conflict-free), j broadcast
-    double s = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < k; ++c) s = fma(G[c * ld + mm] * dw[c], G[c * ld + j], s);
-    Tout[mm * k + j] = s;
+  // Wa = (V diag(dw)) V^T on the tensor core -> Tout (raw).  Strip `st` = rows 8*st..8*st+7.
+  {
+    const int fm = lane >> 2, fr = lane & 3;
+    for (int st = warp; st < k8; st += nwarp) {
+      for (int tj = 0; tj < k8; ++tj) {
+        double c0 = 0.0, c1 = 0.0;
+        for (int ks = 0; ks < 2 * k8; ++ks) {
+          const int c = 4 * ks + fr;
+          const double a = G[c * LD + 8 * st + fm] * dw[c];
+          const double b = G[c * LD + 8 * tj + fm];
+          dmma884(c0, c1, a, b);
+        }
+        const int row = 8 * st + fm, col = 8 * tj + 2 * fr;
+        if (row < k) {
+          if (col < k) Tout[row * k + col] = c0;
+          if (col + 1 < k) Tout[row * k + col + 1] = c1;
+        }
+      }
+    }
   }
   __syncthreads();
   // column means of Wa and mean of wa
@@ -195,27 +137,302 @@ eig_transform_kernel(const double* __restrict__ stats, int k, double rho, int em
   if (info_out && tid == 0) *info_out = sweeps;
 }
 
+// stats: [k*k] C row-major, then [k] g.  Tout: [k][k] row-major, T[m][j].
+// lam_out (nullable): k eigenvalues of A (unsorted); info_out (nullable): sweeps used.
+template <int LPP>
+__global__ void __launch_bounds__(1024)
+eig_transform_kernel(const double* __restrict__ stats, int k, double rho, int empty_R,
+                     double* __restrict__ Tout, double* __restrict__ lam_out, int* __restrict__ info_out) {
+  constexpr int RPL = 8;                       // rows per lane
+  constexpr int ROWS = RPL * LPP;              // padded row count (>= k)
+  constexpr int LD = ROWS + 8;                 // column stride: keeps the 4 pairs of a warp 2-way at worst
+  constexpr int PPW = 32 / LPP;                // pairs per warp
+  extern __shared__ __align__(16) double sm[];
+  const int kj = (k + 1) & ~1;                 // even number of Jacobi columns (last may be a zero column)
+  const int k8 = (k + 7) >> 3;
+  const int ncol = kj > 8 * k8 ? kj : 8 * k8;  // columns kept (zero beyond k) so DMMA tiles need no guards
+  double* G = sm;                              // ncol * LD, column-major
+  double* aux = G + ncol * LD;                 // 6 * ncol
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const double inv_k = 1.0 / (double)k;
+
+  if (empty_R) {                               // reference zero branch: T = U
+    for (int e = tid; e < k * k; e += blockDim.x) Tout[e] = inv_k;
+    if (info_out && tid == 0) *info_out = 0;
+    return;
+  }
+
+  const double shift = (double)(k - 1) / rho;
+  for (int e = tid; e < ncol * LD; e += blockDim.x) {
+    const int c = e / LD, r = e - c * LD;
+    double v = 0.0;
+    if (c < k && r < k) v = stats[r * k + c] + (r == c ? shift : 0.0);
+    G[e] = v;
+  }
+  __syncthreads();
+
+  const int npairs = kj / 2;
+  const int m = kj - 1;                        // round-robin modulus
+  const int sub = lane % LPP;
+  const int pr = warp * PPW + lane / LPP;      // pair slot of this lane group
+  const bool active = pr < npairs;
+  const double tol = 1.1e-16 * sqrt((double)k) * 4.0;
+  const double tol2 = tol * tol;
+  const double quad2 = 1e-16;                  // (1e-8)^2
+  int sweeps = 0;
+  for (; sweeps < 40; ++sweeps) {
+    int rotated = 0, big = 0;
+    for (int rnd = 0; rnd < m; ++rnd) {
+      {
+        // every lane runs the loads and shuffles (full-mask shuffles need the whole warp);
+        // lane groups without a pair work on columns (0,1) and discard the result.
+        int p = 0, q = 1;
+        if (active) {
+          if (pr == 0) { p = m; q = rnd; }
+          else {
+            p = rnd + pr; if (p >= m) p -= m;
+            q = rnd - pr; if (q < 0) q += m;
+          }
+          if (p > q) { const int t_ = p; p = q; q = t_; }
+        }
+        double* gp = G + p * LD + sub;
+        double* gq = G + q * LD + sub;
+        double xp[RPL], xq[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) { xp[i] = gp[LPP * i]; xq[i] = gq[LPP * i]; }
+        double al0 = xp[0] * xp[0], be0 = xq[0] * xq[0], ga0 = xp[0] * xq[0];
+        double al1 = xp[1] * xp[1], be1 = xq[1] * xq[1], ga1 = xp[1] * xq[1];
+#pragma unroll
+        for (int i = 2; i < RPL; i += 2) {
+          al0 = fma(xp[i], xp[i], al0); be0 = fma(xq[i], xq[i], be0); ga0 = fma(xp[i], xq[i], ga0);
+          al1 = fma(xp[i + 1], xp[i + 1], al1); be1 = fma(xq[i + 1], xq[i + 1], be1);
+          ga1 = fma(xp[i + 1], xq[i + 1], ga1);
+        }
+        const double al = group_sum<LPP>(al0 + al1);
+        const double be = group_sum<LPP>(be0 + be1);
+        const double ga = group_sum<LPP>(ga0 + ga1);
+        const double g2 = ga * ga, ab = al * be;
+        if (active && g2 > tol2 * ab) {        // uniform within the lane group
+          rotated = 1;
+          if (g2 > quad2 * ab) big = 1;
+          const double tau = be - al;
+          const double r = rsqrt(fma(tau, tau, 4.0 * g2));
+          const double x = fma(0.5 * fabs(tau), r, 0.5);
+          const double ic = rsqrt(x);
+          const double c_ = x * ic;
+          const double s_ = copysign(ga * r * ic, tau >= 0.0 ? ga : -ga);
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) {
+            gp[LPP * i] = fma(c_, xp[i], -s_ * xq[i]);
+            gq[LPP * i] = fma(s_, xp[i], c_ * xq[i]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int any_rot = __syncthreads_or(rotated);
+    const int any_big = __syncthreads_or(big);
+    if (!any_rot) break;
+    if (!any_big) { ++sweeps; break; }
+  }
+
+  build_transform<LD, ROWS>(G, aux, ncol, stats, k, Tout, lam_out, info_out, sweeps);
+}
+
+// ---- warp-local block Jacobi (32 < k <= 128) ------------------------------------------------
+// Columns are grouped in blocks of 4; a warp keeps a PAIR of blocks (8 columns, 8 lanes x RPL rows
+// per column pair) in registers for a whole block-round and rotates the 16 cross pairs in four
+// sub-rounds, passing the second block's columns from lane group to lane group with shuffles.
+// Shared memory is touched, and the CTA synchronised, once per block-round (15 per sweep at
+// k = 64) instead of once per rotation round (63); the three rounds of within-block pairs go
+// through shared memory.  Column norms ride along with the columns (updated by the rotation,
+// recomputed at every load), so a sub-round needs one inner product instead of three.
+template <int RPL>
+__global__ void __launch_bounds__(512)
+eig_block_kernel(const double* __restrict__ stats, int k, double rho,
+                 double* __restrict__ Tout, double* __restrict__ lam_out, int* __restrict__ info_out) {
+  constexpr int LPP = 8;
+  constexpr int ROWS = RPL * LPP;
+  constexpr int LD = ROWS + 8;
+  extern __shared__ __align__(16) double sm[];
+  const int ncol = (k + 7) & ~7;               // 4-column blocks, even number of blocks
+  const int nb = ncol >> 2;
+  double* G = sm;
+  double* aux = G + ncol * LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7, grp = lane >> 3;
+
+  const double shift = (double)(k - 1) / rho;
+  for (int e = tid; e < ncol * LD; e += blockDim.x) {
+    const int c = e / LD, r = e - c * LD;
+    double v = 0.0;
+    if (c < k && r < k) v = stats[r * k + c] + (r == c ? shift : 0.0);
+    G[e] = v;
+  }
+  __syncthreads();
+
+  const double tol = 1.1e-16 * sqrt((double)k) * 4.0;
+  const double tol2 = tol * tol;
+  const double quad2 = 1e-16;
+  const int m = nb - 1;
+  int sweeps = 0;
+  for (; sweeps < 40; ++sweeps) {
+    int rotated = 0, big = 0;
+    // ---- phase A: the 6 pairs inside every block, 3 rounds through shared memory
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+      const int gid = warp * 4 + grp;           // 2 lane groups per block
+      const int blk = gid >> 1, wh = gid & 1;
+      int p, q;
+      if (t == 0) { p = 2 * wh; q = 2 * wh + 1; }
+      else if (t == 1) { p = wh; q = wh + 2; }
+      else { p = wh; q = 3 - wh; }
+      double* gp = G + (4 * blk + p) * LD + sub;
+      double* gq = G + (4 * blk + q) * LD + sub;
+      double xp[RPL], xq[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) { xp[i] = gp[LPP * i]; xq[i] = gq[LPP * i]; }
+      double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        al = fma(xp[i], xp[i], al); be = fma(xq[i], xq[i], be); ga = fma(xp[i], xq[i], ga);
+      }
+      al = group_sum<LPP>(al); be = group_sum<LPP>(be); ga = group_sum<LPP>(ga);
+      const double g2 = ga * ga, ab = al * be;
+      if (g2 > tol2 * ab) {
+        rotated = 1;
+        if (g2 > quad2 * ab) big = 1;
+        const double tau = be - al;
+        const double r = rsqrt(fma(tau, tau, 4.0 * g2));
+        const double x = fma(0.5 * fabs(tau), r, 0.5);
+        const double ic = rsqrt(x);
+        const double c_ = x * ic;
+        const double s_ = copysign(ga * r * ic, tau >= 0.0 ? ga : -ga);
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          gp[LPP * i] = fma(c_, xp[i], -s_ * xq[i]);
+          gq[LPP * i] = fma(s_, xp[i], c_ * xq[i]);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase B: block round-robin, 16 cross pairs per block pair in registers
+#pragma unroll 1
+    for (int R = 0; R < m; ++R) {
+      int I, J;
+      if (warp == 0) { I = m; J = R; }
+      else {
+        I = R + warp; if (I >= m) I -= m;
+        J = R - warp; if (J < 0) J += m;
+      }
+      double* ga_ptr = G + (4 * I + grp) * LD + sub;
+      double xa[RPL], xb[RPL];
+      double na = 0.0, nbn = 0.0;
+      {
+        const double* gb_ptr = G + (4 * J + grp) * LD + sub;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) { xa[i] = ga_ptr[LPP * i]; xb[i] = gb_ptr[LPP * i]; }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) { na = fma(xa[i], xa[i], na); nbn = fma(xb[i], xb[i], nbn); }
+        na = group_sum<LPP>(na); nbn = group_sum<LPP>(nbn);
+      }
+#pragma unroll
+      for (int sr = 0; sr < 4; ++sr) {
+        double g0 = xa[0] * xb[0], g1 = xa[1] * xb[1];
+#pragma unroll
+        for (int i = 2; i < RPL; i += 2) { g0 = fma(xa[i], xb[i], g0); g1 = fma(xa[i + 1], xb[i + 1], g1); }
+        const double ga = group_sum<LPP>(g0 + g1);
+        const double g2 = ga * ga, ab = na * nbn;
+        if (g2 > tol2 * ab) {
+          rotated = 1;
+          if (g2 > quad2 * ab) big = 1;
+          const double tau = nbn - na;
+          const double r = rsqrt(fma(tau, tau, 4.0 * g2));
+          const double x = fma(0.5 * fabs(tau), r, 0.5);
+          const double ic = rsqrt(x);
+          const double c_ = x * ic;
+          const double s_ = copysign(ga * r * ic, tau >= 0.0 ? ga : -ga);
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) {
+            const double a_ = xa[i], b_ = xb[i];
+            xa[i] = fma(c_, a_, -s_ * b_);
+            xb[i] = fma(s_, a_, c_ * b_);
+          }
+          // |a'|^2 = c^2 a + s^2 b - 2cs g ; |b'|^2 = s^2 a + c^2 b + 2cs g
+          const double cc = c_ * c_, ss = s_ * s_, cs2 = 2.0 * c_ * s_ * ga;
+          const double na2 = fma(cc, na, fma(ss, nbn, -cs2));
+          const double nb2 = fma(ss, na, fma(cc, nbn, cs2));
+          na = na2; nbn = nb2;
+        }
+        if (sr < 3) {                           // pass the b columns to the previous lane group
+          const int src = (lane + 8) & 31;
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) xb[i] = __shfl_sync(0xffffffffu, xb[i], src);
+          nbn = __shfl_sync(0xffffffffu, nbn, src);
+        }
+      }
+      double* gb_out = G + (4 * J + ((grp + 3) & 3)) * LD + sub;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) { ga_ptr[LPP * i] = xa[i]; gb_out[LPP * i] = xb[i]; }
+      __syncthreads();
+    }
+    const int any_rot = __syncthreads_or(rotated);
+    const int any_big = __syncthreads_or(big);
+    if (!any_rot) break;
+    if (!any_big) { ++sweeps; break; }
+  }
+  build_transform<LD, ROWS>(G, aux, ncol, stats, k, Tout, lam_out, info_out, sweeps);
+}
+
+static int eig_lpp(int k) { return k <= 8 ? 1 : (k <= 16 ? 2 : (k <= 32 ? 4 : (k <= 64 ? 8 : 16))); }
+
 size_t eig_smem_bytes(int k) {
-  const int kj = (k + 1) & ~1;
-  return ((size_t)kj * k + 7 * (size_t)kj + 8) * sizeof(double);
+  if (k > 32) {
+    const int rows = k <= 64 ? 64 : 128;
+    const int ncol = (k + 7) & ~7;
+    return ((size_t)ncol * (rows + 8) + 6 * (size_t)ncol + 8) * sizeof(double);
+  }
+  const int lpp = eig_lpp(k);
+  const int ld = 8 * lpp + 8;
+  const int kj = (k + 1) & ~1, k8 = (k + 7) >> 3;
+  const int ncol = kj > 8 * k8 ? kj : 8 * k8;
+  return ((size_t)ncol * ld + 6 * (size_t)ncol + 8) * sizeof(double);
 }
 
 cudaError_t eig_transform_launch(const double* stats, int k, double rho, int empty_R, double* T,
                                  double* lam_out, int* info_out, cudaStream_t st) {
   const size_t smem = eig_smem_bytes(k);
-  const int npairs = ((k + 1) & ~1) / 2;
-  int warps = npairs < 32 ? npairs : 32;
-  if (warps < 1) warps = 1;
-  const int threads = 32 * warps;
-#define DAB_EIG_CASE(R)                                                                              \
-  {                                                                                                  \
-    cudaFuncSetAttribute(eig_transform_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    eig_transform_kernel<R><<<1, threads, smem, st>>>(stats, k, rho, empty_R, T, lam_out, info_out);   \
+  if (k > 32 && !empty_R) {
+    const int threads = 32 * (((k + 7) & ~7) / 8);
+    if (k <= 64) {
+      cudaFuncSetAttribute(eig_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      eig_block_kernel<8><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out);
+    } else {
+      cudaFuncSetAttribute(eig_block_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      eig_block_kernel<16><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out);
+    }
+    return cudaGetLastError();
   }
-  if (k <= 32) DAB_EIG_CASE(1)
-  else if (k <= 64) DAB_EIG_CASE(2)
-  else if (k <= 96) DAB_EIG_CASE(3)
-  else DAB_EIG_CASE(4)
+  const int lpp = eig_lpp(k);
+  const int npairs = ((k + 1) & ~1) / 2;
+  const int ppw = 32 / lpp;
+  int warps = (npairs + ppw - 1) / ppw;
+  if (warps < 1) warps = 1;
+  if (warps > 32) warps = 32;
+  const int threads = 32 * warps;
+#define DAB_EIG_CASE(L)                                                                              \
+  {                                                                                                  \
+    cudaFuncSetAttribute(eig_transform_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    eig_transform_kernel<L><<<1, threads, smem, st>>>(stats, k, rho, empty_R, T, lam_out, info_out);   \
+  }
+  switch (lpp) {
+    case 1: DAB_EIG_CASE(1) break;
+    case 2: DAB_EIG_CASE(2) break;
+    case 4: DAB_EIG_CASE(4) break;
+    case 8: DAB_EIG_CASE(8) break;
+    default: DAB_EIG_CASE(16) break;
+  }
 #undef DAB_EIG_CASE
   return cudaGetLastError();
 }

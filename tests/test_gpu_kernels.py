@@ -277,7 +277,7 @@ def run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, stationary, return_traj=Fal
     (40, 20, 20, 20, 20, False, None),
     (40, 20, 40, 40, 5, True, None),          # converged regime
     (256, 8, 64, 10, 10, False, 5),           # two obs times per window (T_pad = 2)
-    (2048, 64, 600, 6, 20, True, None),
+    (2048, 64, 600, 5, 20, True, None),
 ])
 def test_cycler_matches_oracle_rk4(H, N, k, n_obs, n_cycles, S, stationary, obs_every):
     sd, rho = 1.0, 1.05
