@@ -5,3 +5,5 @@ Same Python surface as the reference for this one path (`dacycler.ETKF.cycle()`,
 sm_100a CUDA kernels behind the C ABI of include/dab_b200.h.  No CPU fallback.
 """
 __version__ = "0.1.0"
+
+from . import data, model, dacycler, observer, obsop, vector, metrics  # noqa: E402,F401

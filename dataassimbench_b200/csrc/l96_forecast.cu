@@ -19,6 +19,8 @@
 //     they go through a double-buffered shared-memory edge array, one __syncthreads per stage;
 //   * loads/stores are staged through padded shared memory so HBM sees fully coalesced 8-byte
 //     accesses while each thread ends up with P consecutive points.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -46,7 +48,6 @@ l96_rk4_window_kernel(const L96Args a) {
   extern __shared__ __align__(16) double smem[];
   const int T = blockDim.x;
   const int t = threadIdx.x;
-  const int W = T * P;
   double2* e_last2 = reinterpret_cast<double2*>(smem);  // [2][T] (s_{P-2}, s_{P-1}) of every thread
   double* e_first = smem + 4 * T;                       // [2][T] s_0 of every thread
   double* stage = e_first + 2 * T;                      // phys(W) doubles, load/store staging
@@ -185,7 +186,12 @@ static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per
                      int* T_out, int* useful_out, int* tiles_out) {
   const int halo = 12 * steps;
   double best = 1e300;
-  for (int T = 64; T <= 512; T += 32) {
+  int t_lo = 64, t_hi = 512;
+  if (const char* ev = getenv("DAB_L96_T")) {            // experiment knob: force the CTA width
+    const int t = atoi(ev);
+    if (t >= 32 && t <= 512 && t % 32 == 0 && t * P >= halo + 16) { t_lo = t; t_hi = t; }
+  }
+  for (int T = t_lo; T <= t_hi; T += 32) {
     const int W = T * P;
     if (W < halo + 16) continue;
     const int useful_max = W - halo;

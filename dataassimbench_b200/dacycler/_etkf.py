@@ -1,0 +1,98 @@
+"""ETKF cycler with the reference's constructor and `cycle()` signature.
+
+Mirrors `dabench.dacycler.ETKF` (dabench/dacycler/_etkf.py:19-62) and `DACycler.cycle`
+(dabench/dacycler/_dacycler.py:186-290).  The accelerated contract: the forecast
+model is the native `Lorenz96Model`, H is the default index gather and R the default
+`obs_error_sd**2 * I`.  Anything else (user-supplied dense H/R/B, callable h, other models)
+raises `NotImplementedError` -- there is deliberately no CPU fallback.
+"""
+import numpy as np
+
+from .. import _xr, _native
+from ._dacycler import DACycler
+
+
+class ETKF(DACycler):
+    _in_4d = False
+    _uses_ensemble = True
+
+    def __init__(self, system_dim, delta_t, model_obj, B=None, R=None, H=None, h=None,
+                 ensemble_dim=4, multiplicative_inflation=1.0):
+        self.ensemble_dim = ensemble_dim
+        self.multiplicative_inflation = multiplicative_inflation
+        super().__init__(system_dim=system_dim, delta_t=delta_t, model_obj=model_obj,
+                         B=B, R=R, H=H, h=h)
+
+    # ------------------------------------------------------------------ marshalling (CPU-testable)
+    def _plan(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
+              analysis_window=0.2, analysis_time_in_window=None):
+        """Everything `dab_cycler_setup` needs, as plain arrays."""
+        from ..model import Lorenz96Model
+        if self.h is not None and self.H is None:
+            # dabench/dacycler/_dacycler.py:103-104
+            raise ValueError('Only linear obs operators (H) are supported right now.')
+        if self.H is not None or self.R is not None or self.B is not None:
+            raise NotImplementedError('user-supplied H / R / B matrices are outside the accelerated path '
+                                      '(default index-gather H and obs_error_sd**2 * I only)')
+        if not isinstance(self.model_obj, Lorenz96Model):
+            raise NotImplementedError('the accelerated ETKF.cycle() needs model_obj to be a '
+                                      'dataassimbench_b200.model.Lorenz96Model')
+        w = self._prepare_cycle(input_state, start_time, obs_vector, n_cycles, obs_error_sd,
+                                analysis_window, analysis_time_in_window)
+        if self._data_vars != ['x'] or self._observed_vars != ['x']:
+            raise NotImplementedError("single-variable states named 'x' only (as the reference's ETKF, "
+                                      "dabench/dacycler/_etkf.py:213)")
+        if np.ndim(self.obs_error_sd) != 0:
+            raise NotImplementedError('scalar obs_error_sd only')
+        X0 = np.ascontiguousarray(_xr.var_array(input_state, 'x'), dtype=np.float64)
+        if X0.ndim != 2:
+            raise ValueError("input_state['x'] must have dims ('ensemble', <state>)")
+        n_ens, n_sys = X0.shape
+        # dabench/dacycler/_etkf.py:196-199
+        assert n_ens == self.ensemble_dim, (
+            'cycle:: model_forecast must have dimension {}x{}').format(self.ensemble_dim, self.system_dim)
+        vals = np.asarray(_xr.var_array(obs_vector, 'x'), dtype=np.float64)
+        vals = np.ascontiguousarray(vals.reshape(len(w['obs_times']), -1))
+        sysidx = np.asarray(_xr.var_array(obs_vector, 'system_index'))
+        sysidx = np.ascontiguousarray(sysidx.reshape(vals.shape), dtype=np.int64)
+        gen = self.model_obj.model_obj
+        cfg = _native.CycleConfig(
+            system_dim=n_sys, ensemble_dim=n_ens, n_steps=self.steps_per_window - 1,
+            model_dt=float(gen.delta_t), forcing=float(gen.forcing_term),
+            rho=float(self.multiplicative_inflation), obs_error_sd=float(self.obs_error_sd),
+            n_obs_times=vals.shape[0], n_obs=vals.shape[1], stationary=int(w['stationary']),
+            n_cycles=int(n_cycles), t_pad=w['padded'].shape[1], rank=0, world=1)
+        state_dim = [d for d in _xr.var_dims(input_state, 'x') if d != 'ensemble']
+        return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx,
+                    padded=np.ascontiguousarray(w['padded']), state_dim=state_dim[0] if state_dim else 'index')
+
+    # ------------------------------------------------------------------ the call
+    def cycle(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
+              analysis_window=0.2, analysis_time_in_window=None, return_forecast=False):
+        """Analysis + forecast, `n_cycles` times (dabench/dacycler/_dacycler.py:186-290).
+
+        Returns a Dataset `x[cycle, ensemble, index]` (analyses) or, with return_forecast=True,
+        `x[cycle, ensemble, cycle_timestep, index]` where cycle_timestep 0 is the analysis and the
+        last forecast point (the next background) is dropped, as in the reference (:281-290)."""
+        import torch
+        from .._runtime import handle
+        p = self._plan(input_state, start_time, obs_vector, n_cycles, obs_error_sd,
+                       analysis_window, analysis_time_in_window)
+        cfg = p['cfg']
+        k, N, S = cfg.ensemble_dim, cfg.system_dim, cfg.n_steps
+        H = handle()
+        out = torch.empty((n_cycles, k, N), dtype=torch.float64).pin_memory()
+        dim = p['state_dim']
+        if not return_forecast:
+            H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out)
+            return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy().copy())})
+        H.cycler_setup(cfg, p['vals'], p['sysidx'], p['padded'])
+        H.cycler_set_state(p['X0'], True)
+        traj = torch.empty((n_cycles, max(S, 1), k, N), dtype=torch.float64, device='cuda')
+        H.cycler_run(0, n_cycles, out, traj if S > 0 else None)
+        H.sync()
+        full = np.empty((n_cycles, k, max(S, 1), N))
+        full[:, :, 0, :] = out.numpy()
+        if S > 1:
+            full[:, :, 1:, :] = traj[:, :S - 1].permute(0, 2, 1, 3).cpu().numpy()
+        return _xr.new_dataset({'x': (('cycle', 'ensemble', 'cycle_timestep', dim), full)})

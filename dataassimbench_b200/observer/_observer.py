@@ -1,0 +1,102 @@
+"""Observation sampling: the input contract of `ETKF.cycle()`.
+
+Mirrors `dabench.observer.Observer` (dabench/observer/_observer.py:89-366) for single-variable
+1-D states (Lorenz-96).  Index sets must be bit-compatible with the reference, so the one
+`numpy.random.default_rng(random_seed)` stream is consumed in the reference's order: times
+(:192-207), then locations (:209-271), then ONE normal draw covering every slot (:346-348).
+Host-side NumPy; the sampled arrays feed the device through `dab_cycler_setup`.
+"""
+import numpy as np
+
+from .. import _xr
+
+
+class Observer:
+    def __init__(self, state_vec, random_time_density=1., random_location_density=1.,
+                 random_time_count=None, random_location_count=None, times=None, locations=None,
+                 stationary_observers=True, error_bias=0., error_sd=0., error_positive_only=False,
+                 random_seed=99, store_as_jax=False):
+        self.state_vec = state_vec
+        self.random_time_density = random_time_density
+        self.random_location_density = random_location_density
+        self.random_time_count = random_time_count
+        self.random_location_count = random_location_count
+        self.times = None if times is None else np.array(times)
+        self.locations = locations
+        self.stationary_observers = stationary_observers
+        self.error_bias = error_bias
+        self.error_sd = error_sd
+        self.error_positive_only = error_positive_only
+        self.random_seed = random_seed
+        self.store_as_jax = store_as_jax
+        if np.ndim(error_bias) != 0 or np.ndim(error_sd) != 0:
+            raise NotImplementedError('per-location error_bias / error_sd lists are outside the ETKF path')
+
+    def _draw_count(self, rng, n):
+        if self.random_location_count is not None:
+            return int(self.random_location_count)
+        return int(np.sum(rng.binomial(1, p=self.random_location_density, size=n)))
+
+    def observe(self):
+        traj = _xr.var_array(self.state_vec, 'x')
+        traj_t = _xr.var_array(self.state_vec, 'time')
+        n_t, n_sys = traj.shape
+        index = np.arange(n_sys)
+        rng = np.random.default_rng(self.random_seed)
+
+        if self.times is None:
+            if self.random_time_count is not None:
+                self.times = np.sort(rng.choice(traj_t, size=self.random_time_count,
+                                                replace=False, shuffle=False))
+            else:
+                keep = rng.binomial(1, p=self.random_time_density, size=n_t).astype(bool)
+                self.times = traj_t[np.where(keep)[0]]
+        self.time_dim = self.times.shape[0]
+        pos = np.searchsorted(traj_t, self.times)
+        if np.any(pos >= n_t) or np.any(traj_t[np.minimum(pos, n_t - 1)] != self.times):
+            raise KeyError('observation times must be times of the trajectory')
+
+        if self.stationary_observers:
+            if self.locations is None:
+                count = self._draw_count(rng, n_sys)
+                locs = rng.choice(index, size=count, replace=False, shuffle=False)
+            else:
+                locs = np.asarray(_loc_array(self.locations), dtype=np.int64)
+            self.location_dim = len(locs)
+            sysidx = np.tile(locs, (self.time_dim, 1)).astype(np.int64)
+            clean = traj[pos][:, locs]
+        else:
+            if self.locations is None:
+                if self.random_location_count is not None:
+                    counts = [int(self.random_location_count)] * self.time_dim
+                else:       # every count first, then every location draw (:246-268)
+                    counts = [self._draw_count(rng, n_sys) for _ in range(self.time_dim)]
+                per_time = [rng.choice(index, size=c, replace=False, shuffle=False) for c in counts]
+            else:
+                per_time = [np.asarray(_loc_array(l), dtype=np.int64) for l in self.locations]
+                counts = [len(l) for l in per_time]
+            self._location_counts = counts
+            self.location_dim = int(np.max(counts)) if len(counts) else 0
+            sysidx = np.zeros((self.time_dim, self.location_dim), dtype=np.int64)
+            clean = np.full((self.time_dim, self.location_dim), np.nan)
+            for i, l in enumerate(per_time):
+                sysidx[i, :len(l)] = l
+                clean[i, :len(l)] = traj[pos[i], l]
+
+        errors = rng.normal(loc=self.error_bias, scale=self.error_sd,
+                            size=(1, self.time_dim, self.location_dim))
+        if self.error_positive_only:
+            errors[errors < 0.] = 0.
+        return _xr.new_dataset(
+            {'x': (('time', 'observations'), clean + errors[0]),
+             'system_index': (('variable', 'time', 'observations'), sysidx[None]),
+             'errors': (('variable', 'time', 'observations'), errors)},
+            coords={'time': self.times, 'variable': np.array(['x'])},
+            attrs={'stationary_observers': self.stationary_observers, 'error_sd': self.error_sd})
+
+
+def _loc_array(locations):
+    """Accepts an index array, or the reference's {'index': DataArray} mapping."""
+    if isinstance(locations, dict):
+        locations = next(iter(locations.values()))
+    return np.asarray(locations.values if hasattr(locations, 'values') else locations)

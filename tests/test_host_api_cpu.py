@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference interface, on CPU: window tables against the oracle's literal
+restatement, Observer against the reference's known answers, error behaviour, and the arrays
+`ETKF.cycle()` hands to the C ABI.  No compute kernels run here."""
+import numpy as np
+import pytest
+import scipy.integrate
+
+import dataassimbench_b200 as dab
+from dataassimbench_b200 import _xr
+from dataassimbench_b200.dacycler import _windows
+from oracle import windows as o_win, l96 as o_l96, observer as o_obs
+
+
+@pytest.mark.parametrize("start,w,n,obs_dt,n_obs_t", [
+    (0.1, 0.1, 10, 0.05, 25), (0.0, 0.2, 20, 0.2, 21), (0.5, 0.2, 7, 0.01, 200), (0.0, 0.05, 40, 0.05, 41),
+    (1.0, 0.3, 5, 0.07, 40)])
+def test_window_tables_equal_reference_restatement(start, w, n, obs_dt, n_obs_t):
+    obs_t = np.arange(n_obs_t) * obs_dt
+    centres = _windows.window_centres(start, w, n)
+    assert np.array_equal(centres, o_win.get_all_times(start, w, n))
+    ref = o_win.pad_time_indices(o_win.get_obs_indices(centres, obs_t, w))
+    got = _windows.padded_time_table(obs_t, centres, w)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+
+
+def test_window_centres_keeps_reference_arange_quirk():
+    with pytest.raises(ValueError):
+        _windows.window_centres(0.0, 0.1, 12)
+
+
+def test_window_table_without_any_observation():
+    t = _windows.padded_time_table(np.array([5.0]), _windows.window_centres(0.0, 0.2, 4), 0.2)
+    assert t.shape == (4, 0)
+
+
+def _nature(N, dt, n):
+    x0 = o_l96.default_x0(N, dt)
+    t = o_l96.time_grid(n, dt)
+    y = scipy.integrate.odeint(lambda x, _t: o_l96.rhs(x), x0, t)
+    return _xr.new_dataset({'x': (('time', 'index'), y)}, coords={'time': t, 'index': np.arange(N)},
+                           attrs={'system_dim': N, 'delta_t': dt})
+
+
+def test_observer_reference_goldens():
+    """/root/reference/tests/observer_base_test.py:133-180 through the API class."""
+    ds = _nature(36, 0.05, 10)
+    ov = dab.observer.Observer(ds, random_time_density=0.4, random_location_density=0.2,
+                               error_sd=0.7).observe()
+    assert ov['x'].shape == (3, 4)
+    assert np.array_equal(ov['system_index'].values, np.tile([16, 9, 31, 32], 3).reshape((1, 3, 4)))
+    assert np.allclose(ov['errors'].values[0, 0], [0.5913821, -0.22663247, 0.00787655, -0.29022197])
+    assert np.allclose(ov['time'].values, [0.15, 0.2, 0.45])
+    assert ov.error_sd == 0.7 and ov.stationary_observers is True
+    mv = dab.observer.Observer(ds, random_time_density=0.4, random_location_density=0.3, error_sd=1.2,
+                               stationary_observers=False).observe()
+    assert mv['x'].shape == (3, 12)
+    assert mv['system_index'].values[0, 2, -1] == 32
+    assert mv['errors'].values[0, 1, 4] == pytest.approx(-0.7470301078422978)
+    assert mv['x'].values[2, 5] == pytest.approx(0.010236507277464613)
+
+
+def test_observer_matches_oracle_bit_for_bit():
+    ds = _nature(36, 0.01, 40)
+    for stat in (True, False):
+        a = dab.observer.Observer(ds, random_time_count=6, random_location_density=0.4, error_sd=0.3,
+                                  error_bias=0.1, stationary_observers=stat, random_seed=7).observe()
+        b = o_obs.observe(ds['x'].values, ds['time'].values, random_time_count=6,
+                          random_location_density=0.4, error_sd=0.3, error_bias=0.1,
+                          stationary_observers=stat, random_seed=7)
+        assert np.array_equal(a['system_index'].values[0], b['system_index'])
+        assert np.array_equal(a['x'].values, b['values'], equal_nan=True)
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError):                       # dabench/data/_lorenz96.py:57-59
+        dab.data.Lorenz96(system_dim=3)
+    with pytest.raises(TypeError):                        # dabench/data/_data.py:127-128
+        dab.data.Lorenz96(system_dim=5).generate()
+
+    class NoForecast(dab.model.Model):
+        forecast = None
+    with pytest.raises(ValueError):                       # dabench/model/_model.py:28-32
+        NoForecast()
+    assert np.allclose(dab.data.Lorenz96(system_dim=5, delta_t=0.01).x0,
+                       [1.7660924, 0.29829425, 0.3133399, 4.521974, 8.680367])
+    assert np.array_equal(dab.data.Lorenz96(system_dim=40).x0, np.r_[0.01, np.zeros(39)])
+    l = dab.data.Lorenz96(system_dim=6)
+    assert np.array_equal(l.rhs(np.arange(6.0)), o_l96.rhs(np.arange(6.0)))
+
+
+def _experiment(N=8, k=4, n_cycles=5, S=10):
+    ds = _nature(N, 0.01, n_cycles * S + 1)
+    obs = dab.observer.Observer(ds, times=ds['time'].values[::S], random_location_count=3,
+                                error_sd=0.5, random_seed=3).observe()
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.01))
+    X0 = ds['x'].values[0] + np.random.default_rng(0).standard_normal((k, N))
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), X0)}, coords={'index': np.arange(N)})
+    return ds, obs, model, init
+
+
+def test_cycle_plan_marshalling():
+    N, k, n_cycles, S = 8, 4, 5, 10
+    ds, obs, model, init = _experiment(N, k, n_cycles, S)
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, model_obj=model, ensemble_dim=k,
+                           multiplicative_inflation=1.1)
+    p = dc._plan(init, 0.0, obs, n_cycles, analysis_window=0.1)
+    cfg = p['cfg']
+    assert (cfg.system_dim, cfg.ensemble_dim, cfg.n_steps, cfg.n_cycles) == (N, k, S, n_cycles)
+    assert cfg.rho == 1.1 and cfg.obs_error_sd == 0.5 and cfg.model_dt == 0.01 and cfg.stationary == 1
+    assert p['vals'].shape == (n_cycles + 1, 3) and p['sysidx'].dtype == np.int64
+    assert np.array_equal(p['padded'], np.arange(1, n_cycles + 1)[:, None])
+    assert dc.steps_per_window == S + 1
+
+
+def test_cycle_rejects_what_it_does_not_accelerate():
+    N, k = 8, 4
+    ds, obs, model, init = _experiment(N, k)
+    with pytest.raises(AssertionError):                   # dabench/dacycler/_etkf.py:196-199
+        dab.dacycler.ETKF(N, 0.01, model, ensemble_dim=k + 1)._plan(init, 0.0, obs, 5, analysis_window=0.1)
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.ETKF(N, 0.01, model, ensemble_dim=k, H=np.eye(N))._plan(init, 0.0, obs, 5, analysis_window=0.1)
+    with pytest.raises(ValueError):                       # dabench/dacycler/_dacycler.py:103-104
+        dab.dacycler.ETKF(N, 0.01, model, ensemble_dim=k, h=lambda x: x)._plan(init, 0.0, obs, 5, analysis_window=0.1)
+
+    class Other(dab.model.Model):
+        def forecast(self, s, n_steps):
+            return s, s
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.ETKF(N, 0.01, Other(), ensemble_dim=k)._plan(init, 0.0, obs, 5, analysis_window=0.1)
+
+
+def test_mini_dataset_surface():
+    ds = _xr.MiniDataset({'x': (('time', 'index'), np.arange(12.0).reshape(3, 4))},
+                         coords={'time': np.array([0.0, 0.1, 0.2]), 'index': np.arange(4)}, attrs={'a': 1})
+    assert ds.sizes == {'time': 3, 'index': 4} and ds.a == 1
+    last = ds.isel(time=-1)
+    assert last['x'].dims == ('index',) and np.array_equal(last['x'].values, [8, 9, 10, 11])
+    assert float(last['time'].data) == 0.2
+    e = ds.assign(x=(('ensemble', 'index'), np.ones((2, 4))))
+    assert e['x'].shape == (2, 4) and ds['x'].shape == (3, 4)
+    assert np.array_equal(ds.mean(dim='time')['x'].values, [4, 5, 6, 7])
+    s = _xr.MiniDataset({'x': (('cycle', 'ensemble', 'cycle_timestep', 'index'), np.zeros((2, 3, 5, 4)))})
+    st = s.stack(time=['cycle', 'cycle_timestep']).transpose('time', ...)
+    assert st['x'].shape == (10, 3, 4)
