@@ -67,6 +67,8 @@ _SIGNATURES = {
     "dab_cycler_update": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_export": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "dab_cycler_buffer_ptr": (_P, [_P, C.c_int]),
+    "dab_cycler_set_peer": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dab_cycler_stream": (_P, [_P]),
     "dab_cycler_background_ptr": (_P, [_P]),
     "dab_cycler_kernel_launches": (C.c_int, [_P]),
@@ -194,6 +196,12 @@ class Handle:
     def cycler_ipc_import(self, peer_rank, which, handle_bytes):
         buf = C.create_string_buffer(bytes(handle_bytes), IPC_HANDLE_BYTES)
         self._check(self._lib.dab_cycler_ipc_import(self._h, peer_rank, which, buf))
+
+    def cycler_buffer_ptr(self, which):
+        return self._lib.dab_cycler_buffer_ptr(self._h, which)
+
+    def cycler_set_peer(self, peer_rank, which, ptr):
+        self._check(self._lib.dab_cycler_set_peer(self._h, peer_rank, which, _ptr(ptr)))
 
     def cycler_stream(self):
         return self._lib.dab_cycler_stream(self._h)

@@ -43,6 +43,7 @@ struct Cycler {
   std::vector<int> n_seg;                  // per cycle
   std::vector<long long> n_rows;           // per cycle
   int max_grid = 1;
+  int l96_T = 0;                           // autotuned CTA width of the forecast kernel (0 = heuristic)
   const double* peer[kMaxRanks][2];        // peer-mapped Xb buffers
   bool peer_open[kMaxRanks][2];
   cudaEvent_t ev_xa[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -60,6 +61,9 @@ struct dab_handle {
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   Cycler cyc;
   // optional per-kernel timing (CUDA events on the launching stream)
+  // forecast autotune cache: (n_loc, k, steps) -> CTA width
+  std::vector<long long> tune_key;
+  std::vector<int> tune_T;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_pool;
   std::vector<int> prof_tags;
@@ -103,8 +107,10 @@ static int fail(dab_handle* h, int code, const char* fmt, ...) {
 static void cycler_close_peers(dab_handle* h) {
   Cycler& c = h->cyc;
   for (int r = 0; r < kMaxRanks; ++r)
-    for (int w = 0; w < 2; ++w)
+    for (int w = 0; w < 2; ++w) {
       if (c.peer_open[r][w]) { cudaIpcCloseMemHandle(const_cast<double*>(c.peer[r][w])); c.peer_open[r][w] = false; }
+      c.peer[r][w] = nullptr;
+    }
 }
 
 // Workspaces are grow-only and survive dab_cycler_setup calls (cudaMalloc/cudaFree cost
@@ -203,7 +209,7 @@ static int forecast_plain(dab_handle* h, const double* x_in, double* x_out, doub
     // ping-pong so that the last chunk lands in x_out
     double* dst = ((n_chunks - 1 - c) % 2 == 0) ? x_out : tmp;
     DAB_CUDA(h, l96_forecast_launch(src, dst, traj ? traj + (long long)done * traj_stride : nullptr, N, k, s,
-                                    dt, F, N, N, true, 0, 0, 0, traj_stride, h->sms, st));
+                                    dt, F, N, N, true, 0, 0, 0, traj_stride, h->sms, 0, st));
     h->launches++;
     src = dst;
     done += s;
@@ -420,6 +426,38 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   DAB_CUDA(h, c.lam.reserve(sizeof(double) * (size_t)k));
   DAB_CUDA(h, c.info.reserve(sizeof(int) * 4));
   DAB_CUDA(h, cudaStreamSynchronize(h->stream));               // host vectors go out of scope
+  // ---- measure, don't guess: pick the forecast kernel's CTA width for this shape with CUDA events
+  c.l96_T = 0;
+  const long long tkey = (c.n_loc * 256 + k) * 64 + c.first_steps;
+  for (size_t i = 0; i < h->tune_key.size(); ++i)
+    if (h->tune_key[i] == tkey) c.l96_T = h->tune_T[i];
+  if (c.l96_T == 0 && c.first_steps > 0 && (long long)k * c.n_loc >= (1ll << 20)) {
+    DAB_CUDA(h, cudaMemsetAsync(c.ext[0].p, 0, c.ext[0].bytes, h->stream));
+    cudaEvent_t e0, e1;
+    DAB_CUDA(h, cudaEventCreate(&e0));
+    DAB_CUDA(h, cudaEventCreate(&e1));
+    const int cand[6] = {128, 192, 256, 320, 384, 512};
+    float best_ms = 1e30f;
+    for (int ci = 0; ci < 6; ++ci) {
+      if (cand[ci] * 8 < 12 * c.first_steps + 16) continue;
+      float ms = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {
+        DAB_CUDA(h, cudaEventRecord(e0, h->stream));
+        DAB_CUDA(h, l96_forecast_launch(c.ext[0].as<double>(), c.xb[1], nullptr, c.n_loc, k, c.first_steps,
+                                        cfg->model_dt, cfg->forcing, c.ld_e, c.n_loc, false, c.halo_l,
+                                        -(long long)c.halo_l, c.n_loc + c.halo_r, 0, h->sms, cand[ci], h->stream));
+        DAB_CUDA(h, cudaEventRecord(e1, h->stream));
+        DAB_CUDA(h, cudaEventSynchronize(e1));
+        float t = 0.f;
+        DAB_CUDA(h, cudaEventElapsedTime(&t, e0, e1));
+        if (rep > 0 && t < ms) ms = t;
+      }
+      if (ms < best_ms) { best_ms = ms; c.l96_T = cand[ci]; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->tune_key.push_back(tkey);
+    h->tune_T.push_back(c.l96_T);
+  }
   h->launches = 0;
   c.ready = true;
   return 0;
@@ -492,7 +530,8 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   for (int r = 0; r < c.cfg.world; ++r) {
     if (r == c.cfg.rank) a.src[r] = c.xb[c.cur];
     else {
-      if (!c.peer_open[r][c.cur]) return fail(h, -3, "peer buffer of rank %d not imported (dab_cycler_ipc_import)", r);
+      if (c.peer[r][c.cur] == nullptr)
+        return fail(h, -3, "peer buffer of rank %d not registered (dab_cycler_ipc_import / dab_cycler_set_peer)", r);
       a.src[r] = c.peer[r][c.cur];
     }
   }
@@ -527,7 +566,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   } else if (S <= c.first_steps) {
     DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), nxt, out_traj, c.n_loc, k, S, c.cfg.model_dt,
                                     c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l, -(long long)c.halo_l,
-                                    c.n_loc + c.halo_r, traj_stride, h->sms, h->stream));
+                                    c.n_loc + c.halo_r, traj_stride, h->sms, c.l96_T, h->stream));
     h->launches++;
   } else {
     // long window on one rank: first chunk from the extended buffer, the rest periodic.
@@ -540,7 +579,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
     double* first_dst = (rest_chunks % 2 == 0) ? nxt : tmp;
     DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), first_dst, out_traj, c.n_loc, k, c.first_steps,
                                     c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l,
-                                    -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms, h->stream));
+                                    -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms, c.l96_T, h->stream));
     h->launches++;
     const double* src = first_dst;
     int done = c.first_steps;
@@ -549,7 +588,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
       double* dst = (src == tmp) ? nxt : tmp;
       DAB_CUDA(h, l96_forecast_launch(src, dst, out_traj ? out_traj + (long long)done * traj_stride : nullptr,
                                       c.n_loc, k, s, c.cfg.model_dt, c.cfg.forcing, c.n_loc, c.n_loc, true,
-                                      0, 0, 0, traj_stride, h->sms, h->stream));
+                                      0, 0, 0, traj_stride, h->sms, 0, h->stream));
       h->launches++;
       src = dst;
       done += s;
@@ -604,6 +643,20 @@ int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* h
   DAB_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
   h->cyc.peer[peer_rank][which] = static_cast<const double*>(p);
   h->cyc.peer_open[peer_rank][which] = true;
+  return 0;
+}
+
+double* dab_cycler_buffer_ptr(dab_handle* h, int which) {
+  if (!h || !h->cyc.ready || (which != 0 && which != 1)) return nullptr;
+  return h->cyc.xb[which];
+}
+
+int dab_cycler_set_peer(dab_handle* h, int peer_rank, int which, const double* ptr) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready && ptr != nullptr && (which == 0 || which == 1));
+  DAB_ARG(h, peer_rank >= 0 && peer_rank < h->cyc.cfg.world && peer_rank != h->cyc.cfg.rank);
+  Cycler& c = h->cyc;
+  if (c.peer_open[peer_rank][which]) return fail(h, -1, "peer %d buffer %d already imported through IPC", peer_rank, which);
+  c.peer[peer_rank][which] = ptr;
   return 0;
 }
 

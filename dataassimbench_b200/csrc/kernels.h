@@ -13,7 +13,8 @@ int l96_max_steps_per_launch();
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
-                                long long traj_stride, int sms, cudaStream_t st);
+                                long long traj_stride, int sms, int forced_T /* 0 = heuristic */,
+                                cudaStream_t st);
 
 // K2/K3  etkf_contract.cu
 int contract_k8(int k);

@@ -182,14 +182,17 @@ static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, cudaS
 // `sms` SMs.  The kernel is FP64-pipe bound, so its time is proportional to
 //   waves * (points computed per SM per wave) = ceil(ctas / (sms*occ)) * occ * W,
 // halo recomputation and wave quantisation included; ties go to more resident threads.
-static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per_thread,
+static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per_thread, int forced_T,
                      int* T_out, int* useful_out, int* tiles_out) {
   const int halo = 12 * steps;
   double best = 1e300;
   int t_lo = 64, t_hi = 512;
   if (const char* ev = getenv("DAB_L96_T")) {            // experiment knob: force the CTA width
     const int t = atoi(ev);
-    if (t >= 32 && t <= 512 && t % 32 == 0 && t * P >= halo + 16) { t_lo = t; t_hi = t; }
+    if (t >= 32 && t <= 512 && t % 32 == 0) forced_T = t;
+  }
+  if (forced_T >= 32 && forced_T <= 512 && forced_T % 32 == 0 && forced_T * P >= halo + 16) {
+    t_lo = forced_T; t_hi = forced_T;
   }
   for (int T = t_lo; T <= t_hi; T += 32) {
     const int W = T * P;
@@ -217,16 +220,18 @@ static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
-                                long long traj_stride, int sms, cudaStream_t st) {
-  const int P = 8;
+                                long long traj_stride, int sms, int forced_T, cudaStream_t st) {
+  int P = 8;
+  if (const char* ev = getenv("DAB_L96_P")) { if (atoi(ev) == 4) P = 4; }   // experiment knob
   int T = 256, useful = 0, tiles = 0;
-  l96_plan(n, k, n_steps, sms, P, 88, &T, &useful, &tiles);
+  l96_plan(n, k, n_steps, sms, P, P == 8 ? 88 : 72, forced_T, &T, &useful, &tiles);
   L96Args a;
   a.in = in; a.out = out; a.traj = traj;
   a.in_ld = in_ld; a.out_ld = out_ld; a.in_base = in_base; a.in_lo = in_lo; a.in_hi = in_hi;
   a.n = n; a.traj_stride = traj_stride;
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
   a.dt = dt; a.F = F;
+  if (P == 4) return launch_p<4>(a, k, T, periodic, st);
   return launch_p<8>(a, k, T, periodic, st);
 }
 

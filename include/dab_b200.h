@@ -133,6 +133,10 @@ DAB_API int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev
  * which = 0/1 selects the two background (Xb) buffers. */
 DAB_API int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out /* 64 bytes */);
 DAB_API int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* handle_in);
+/* Same-process alternative (several handles in one process, e.g. one per peer-enabled GPU, or
+ * emulated ranks on one GPU in tests): register a peer's background buffer pointer directly. */
+DAB_API double* dab_cycler_buffer_ptr(dab_handle* h, int which);
+DAB_API int dab_cycler_set_peer(dab_handle* h, int peer_rank, int which, const double* ptr);
 DAB_API void* dab_cycler_stream(dab_handle* h);                  /* cudaStream_t the cycler enqueues on */
 /* device pointers of the current background / last analysis (extended layout) for tests */
 DAB_API double* dab_cycler_background_ptr(dab_handle* h);
