@@ -57,8 +57,19 @@ transform_kernel(const TransformArgs a) {
           sp = a.src[owner] + (gp - (long long)owner * a.n_loc);
         }
       }
-      for (int m = tid / TC; m < KP; m += blockDim.x / TC)
-        Xs[m * XLD + i] = (sp != nullptr && m < k) ? sp[(long long)m * a.src_ld] : 0.0;
+      // 16 independent loads in flight per thread (trip count is a compile-time constant), so
+      // L2 / NVLink latency is paid once per tile, not once per row.
+      constexpr int ROWS_PER_PASS = (32 * K8) / TC;
+      constexpr int PASSES = KP / ROWS_PER_PASS;
+      const int m0 = tid / TC;
+      double v[PASSES];
+#pragma unroll
+      for (int it = 0; it < PASSES; ++it) {
+        const int m = m0 + it * ROWS_PER_PASS;
+        v[it] = (sp != nullptr && m < k) ? sp[(long long)m * a.src_ld] : 0.0;
+      }
+#pragma unroll
+      for (int it = 0; it < PASSES; ++it) Xs[(m0 + it * ROWS_PER_PASS) * XLD + i] = v[it];
     }
     __syncthreads();
     double* drow = a.dst + (long long)(8 * warp + fm) * a.dst_ld + a.dst_base;
