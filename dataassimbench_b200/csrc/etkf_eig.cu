@@ -29,6 +29,13 @@
 
 namespace dab {
 
+// -DDAB_EIG_TIMING: warp 0 accumulates clock64() per section into lam_out[0..5] (debug builds only).
+#ifdef DAB_EIG_TIMING
+#define DAB_TICK(acc) do { const long long now_ = clock64(); (acc) += now_ - tick_; tick_ = now_; } while (0)
+#else
+#define DAB_TICK(acc) do { } while (0)
+#endif
+
 template <int LPP>
 __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
@@ -98,10 +105,30 @@ __device__ __forceinline__ void build_transform(double* G, double* aux, int ncol
     for (int c = 0; c < k; ++c) s = fma(G[c * LD + r] * da[c], proj[c], s);
     wa[r] = s;
   }
-  // Wa = (V diag(dw)) V^T on the tensor core -> Tout (raw).  Strip `st` = rows 8*st..8*st+7.
+  // column means of Wa without forming it: cmean_j = (1/k) sum_c V[j][c] dw_c (1^T v_c)
+  for (int c = warp; c < k; c += nwarp) {
+    double u = 0.0;
+    for (int r = lane; r < ROWS; r += 32) u += G[c * LD + r];
+    u = group_sum<32>(u);
+    if (lane == 0) lam[c] = u * dw[c];             // lam[] is free now (copied to lam_out above)
+  }
+  __syncthreads();
+  for (int r = tid; r < k; r += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < k; ++c) s = fma(G[c * LD + r], lam[c], s);
+    cmean[r] = s * inv_k;
+  }
+  double wsum = 0.0;
+  for (int r = 0; r < k; ++r) wsum += wa[r];       // every thread, same order: identical value
+  const double wmean = wsum * inv_k;
+  __syncthreads();
+  // Wa = (V diag(dw)) V^T on the tensor core, epilogue writes
+  // T[m][j] = 1/k + (wa[m] - mean(wa)) + (Wa[m][j] - colmean_j).  Strip `st` = rows 8*st..8*st+7.
   {
     const int fm = lane >> 2, fr = lane & 3;
     for (int st = warp; st < k8; st += nwarp) {
+      const int row = 8 * st + fm;
+      const double base = row < k ? inv_k + (wa[row] - wmean) : 0.0;
       for (int tj = 0; tj < k8; ++tj) {
         double c0 = 0.0, c1 = 0.0;
         for (int ks = 0; ks < 2 * k8; ++ks) {
@@ -110,29 +137,13 @@ __device__ __forceinline__ void build_transform(double* G, double* aux, int ncol
           const double b = G[c * LD + 8 * tj + fm];
           dmma884(c0, c1, a, b);
         }
-        const int row = 8 * st + fm, col = 8 * tj + 2 * fr;
+        const int col = 8 * tj + 2 * fr;
         if (row < k) {
-          if (col < k) Tout[row * k + col] = c0;
-          if (col + 1 < k) Tout[row * k + col + 1] = c1;
+          if (col < k) Tout[row * k + col] = base + (c0 - cmean[col]);
+          if (col + 1 < k) Tout[row * k + col + 1] = base + (c1 - cmean[col + 1]);
         }
       }
     }
-  }
-  __syncthreads();
-  // column means of Wa and mean of wa
-  for (int j = tid; j < k; j += blockDim.x) {
-    double s = 0.0;
-    for (int mm = 0; mm < k; ++mm) s += Tout[mm * k + j];
-    cmean[j] = s * inv_k;
-  }
-  double wsum = 0.0;
-  for (int r = 0; r < k; ++r) wsum += wa[r];   // every thread, same order: identical value
-  const double wmean = wsum * inv_k;
-  __syncthreads();
-  // T[m][j] = 1/k + (wa[m] - mean(wa)) + (Wa[m][j] - colmean_j)
-  for (int e = tid; e < k * k; e += blockDim.x) {
-    const int mm = e / k, j = e - mm * k;
-    Tout[e] = inv_k + (wa[mm] - wmean) + (Tout[e] - cmean[j]);
   }
   if (info_out && tid == 0) *info_out = sweeps;
 }
@@ -260,6 +271,7 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
   const int nb = ncol >> 2;
   double* G = sm;
   double* aux = G + ncol * LD;
+  double* nrm = aux + 6 * ncol;                // squared column norms, carried with the columns
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane & 7, grp = lane >> 3;
 
@@ -277,8 +289,12 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
   const double quad2 = 1e-16;
   const int m = nb - 1;
   int sweeps = 0;
+#ifdef DAB_EIG_TIMING
+  long long tA = 0, tLoad = 0, tSub = 0, tStore = 0, tFlags = 0, tick_ = clock64();
+#endif
   for (; sweeps < 40; ++sweeps) {
     int rotated = 0, big = 0;
+    DAB_TICK(tFlags);
     // ---- phase A: the 6 pairs inside every block, 3 rounds through shared memory
 #pragma unroll 1
     for (int t = 0; t < 3; ++t) {
@@ -304,7 +320,8 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
         rotated = 1;
         if (g2 > quad2 * ab) big = 1;
         const double tau = be - al;
-        const double r = rsqrt(fma(tau, tau, 4.0 * g2));
+        const double q_ = fma(tau, tau, 4.0 * g2);
+        const double r = rsqrt(q_);
         const double x = fma(0.5 * fabs(tau), r, 0.5);
         const double ic = rsqrt(x);
         const double c_ = x * ic;
@@ -314,9 +331,15 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
           gp[LPP * i] = fma(c_, xp[i], -s_ * xq[i]);
           gq[LPP * i] = fma(s_, xp[i], c_ * xq[i]);
         }
+        // the rotation diagonalises the 2x2 Gram: norms' = (al + be -/+ sgn(tau) h) / 2, h = sqrt(q)
+        const double hh = copysign(q_ * r, tau);
+        const double sum = al + be;
+        al = 0.5 * (sum - hh); be = 0.5 * (sum + hh);
       }
+      if (t == 2 && sub == 0) { nrm[4 * blk + p] = al; nrm[4 * blk + q] = be; }
       __syncthreads();
     }
+    DAB_TICK(tA);
     // ---- phase B: block round-robin, 16 cross pairs per block pair in registers
 #pragma unroll 1
     for (int R = 0; R < m; ++R) {
@@ -328,15 +351,16 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
       }
       double* ga_ptr = G + (4 * I + grp) * LD + sub;
       double xa[RPL], xb[RPL];
-      double na = 0.0, nbn = 0.0;
+      double na = nrm[4 * I + grp], nbn = nrm[4 * J + grp];
       {
         const double* gb_ptr = G + (4 * J + grp) * LD + sub;
 #pragma unroll
         for (int i = 0; i < RPL; ++i) { xa[i] = ga_ptr[LPP * i]; xb[i] = gb_ptr[LPP * i]; }
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) { na = fma(xa[i], xa[i], na); nbn = fma(xb[i], xb[i], nbn); }
-        na = group_sum<LPP>(na); nbn = group_sum<LPP>(nbn);
       }
+#ifdef DAB_EIG_TIMING
+      if (xa[0] + xb[0] + na == -1.2345e300) tLoad -= 1;   // make the loads complete before the tick
+#endif
+      DAB_TICK(tLoad);
 #pragma unroll
       for (int sr = 0; sr < 4; ++sr) {
         double g0 = xa[0] * xb[0], g1 = xa[1] * xb[1];
@@ -348,7 +372,8 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
           rotated = 1;
           if (g2 > quad2 * ab) big = 1;
           const double tau = nbn - na;
-          const double r = rsqrt(fma(tau, tau, 4.0 * g2));
+          const double q_ = fma(tau, tau, 4.0 * g2);
+          const double r = rsqrt(q_);
           const double x = fma(0.5 * fabs(tau), r, 0.5);
           const double ic = rsqrt(x);
           const double c_ = x * ic;
@@ -359,11 +384,10 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
             xa[i] = fma(c_, a_, -s_ * b_);
             xb[i] = fma(s_, a_, c_ * b_);
           }
-          // |a'|^2 = c^2 a + s^2 b - 2cs g ; |b'|^2 = s^2 a + c^2 b + 2cs g
-          const double cc = c_ * c_, ss = s_ * s_, cs2 = 2.0 * c_ * s_ * ga;
-          const double na2 = fma(cc, na, fma(ss, nbn, -cs2));
-          const double nb2 = fma(ss, na, fma(cc, nbn, cs2));
-          na = na2; nbn = nb2;
+          // norms' = (na + nb -/+ sgn(tau) h) / 2 with h = sqrt(q) = q r: off the c/s chain
+          const double hh = copysign(q_ * r, tau);
+          const double sum = na + nbn;
+          na = 0.5 * (sum - hh); nbn = 0.5 * (sum + hh);
         }
         if (sr < 3) {                           // pass the b columns to the previous lane group
           const int src = (lane + 8) & 31;
@@ -372,17 +396,32 @@ eig_block_kernel(const double* __restrict__ stats, int k, double rho,
           nbn = __shfl_sync(0xffffffffu, nbn, src);
         }
       }
+#ifdef DAB_EIG_TIMING
+      if (xa[0] + xb[0] == -1.2345e300) tSub -= 1;
+#endif
+      DAB_TICK(tSub);
       double* gb_out = G + (4 * J + ((grp + 3) & 3)) * LD + sub;
 #pragma unroll
       for (int i = 0; i < RPL; ++i) { ga_ptr[LPP * i] = xa[i]; gb_out[LPP * i] = xb[i]; }
+      if (sub == 0) { nrm[4 * I + grp] = na; nrm[4 * J + ((grp + 3) & 3)] = nbn; }
       __syncthreads();
+      DAB_TICK(tStore);
     }
     const int any_rot = __syncthreads_or(rotated);
     const int any_big = __syncthreads_or(big);
     if (!any_rot) break;
     if (!any_big) { ++sweeps; break; }
   }
+  DAB_TICK(tFlags);
   build_transform<LD, ROWS>(G, aux, ncol, stats, k, Tout, lam_out, info_out, sweeps);
+#ifdef DAB_EIG_TIMING
+  long long tBuild = 0;
+  DAB_TICK(tBuild);
+  if (tid == 0 && lam_out) {
+    lam_out[0] = (double)tA; lam_out[1] = (double)tLoad; lam_out[2] = (double)tSub;
+    lam_out[3] = (double)tStore; lam_out[4] = (double)tFlags; lam_out[5] = (double)tBuild;
+  }
+#endif
 }
 
 static int eig_lpp(int k) { return k <= 8 ? 1 : (k <= 16 ? 2 : (k <= 32 ? 4 : (k <= 64 ? 8 : 16))); }
@@ -391,7 +430,7 @@ size_t eig_smem_bytes(int k) {
   if (k > 32) {
     const int rows = k <= 64 ? 64 : 128;
     const int ncol = (k + 7) & ~7;
-    return ((size_t)ncol * (rows + 8) + 6 * (size_t)ncol + 8) * sizeof(double);
+    return ((size_t)ncol * (rows + 8) + 7 * (size_t)ncol + 8) * sizeof(double);
   }
   const int lpp = eig_lpp(k);
   const int ld = 8 * lpp + 8;
