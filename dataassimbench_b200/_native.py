@@ -76,6 +76,8 @@ _SIGNATURES = {
     "dab_cycler_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "dab_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dab_etkf_cycle_host_f64": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P, _P]),
+    "dab_etkf_cycle_batched_f64": (C.c_int, [_P, C.POINTER(CycleConfig), C.c_int, _P, _P, _P, _P, C.c_int,
+                                             _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -228,6 +230,12 @@ class Handle:
         a, b = C.c_double(), C.c_double()
         self._check(self._lib.dab_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return {"dfma_tflops": a.value, "dmma_tflops": b.value}
+
+    def etkf_cycle_batched(self, cfg, batch, rho, x0, obs_values, system_index, shared_index,
+                           padded_time_idx, out_analysis=None, out_mean=None, out_final=None):
+        self._check(self._lib.dab_etkf_cycle_batched_f64(
+            self._h, C.byref(cfg), int(batch), _ptr(rho), _ptr(x0), _ptr(obs_values), _ptr(system_index),
+            int(shared_index), _ptr(padded_time_idx), _ptr(out_analysis), _ptr(out_mean), _ptr(out_final)))
 
     def etkf_cycle_host(self, cfg, x0, obs_values, system_index, padded_time_idx, out_analysis):
         self._check(self._lib.dab_etkf_cycle_host_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),

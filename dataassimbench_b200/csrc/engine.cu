@@ -59,6 +59,7 @@ struct dab_handle {
   std::string err;
   long launches = 0;
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
+  DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
   Cycler cyc;
   // optional per-kernel timing (CUDA events on the launching stream)
   // forecast autotune cache: (n_loc, k, steps) -> CTA width
@@ -174,6 +175,8 @@ int dab_destroy(dab_handle* h) {
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_seg.release();
   h->s_partial.release(); h->s_stats.release(); h->s_T.release();
+  h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
+  h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -657,6 +660,63 @@ int dab_cycler_set_peer(dab_handle* h, int peer_rank, int which, const double* p
   Cycler& c = h->cyc;
   if (c.peer_open[peer_rank][which]) return fail(h, -1, "peer %d buffer %d already imported through IPC", peer_rank, which);
   c.peer[peer_rank][which] = ptr;
+  return 0;
+}
+
+int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int batch, const double* rho,
+                               const double* x0, const double* obs_values, const int64_t* system_index,
+                               int shared_index, const int64_t* padded_time_idx, double* out_analysis,
+                               double* out_mean, double* out_final) {
+  DAB_ARG(h, h != nullptr && cfg != nullptr && batch >= 1 && rho != nullptr && x0 != nullptr);
+  DAB_ARG(h, cfg->world == 1 && cfg->rank == 0);
+  DAB_ARG(h, cfg->system_dim >= 4 && cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= 32);
+  DAB_ARG(h, cfg->system_dim * cfg->ensemble_dim <= 4096);
+  DAB_ARG(h, cfg->n_steps >= 0 && cfg->n_cycles >= 0 && cfg->t_pad >= 0 && cfg->n_obs >= 0);
+  DAB_ARG(h, (long long)cfg->t_pad * cfg->n_obs * cfg->ensemble_dim <= 8192);
+  DAB_ARG(h, cfg->model_dt > 0.0 && (cfg->obs_error_sd > 0.0 || cfg->t_pad * cfg->n_obs == 0));
+  DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 || (obs_values != nullptr && system_index != nullptr));
+  DAB_ARG(h, cfg->n_cycles * cfg->t_pad == 0 || padded_time_idx != nullptr);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  const int k = cfg->ensemble_dim, N = (int)cfg->system_dim;
+  const size_t kN = (size_t)k * N;
+  const size_t n_obs_all = (size_t)cfg->n_obs_times * cfg->n_obs;
+  for (int b = 0; b < batch; ++b) DAB_ARG(h, rho[b] > 0.0);
+  for (size_t i = 0; i < n_obs_all * (shared_index ? 1 : (size_t)batch); ++i)
+    if (system_index[i] < 0 || system_index[i] >= N) return fail(h, -1, "system_index[%zu] = %lld out of range", i, (long long)system_index[i]);
+  for (long long i = 0; i < (long long)cfg->n_cycles * cfg->t_pad; ++i)
+    if (padded_time_idx[i] < 0 || padded_time_idx[i] > cfg->n_obs_times)
+      return fail(h, -1, "padded_time_idx[%lld] = %lld out of range", i, (long long)padded_time_idx[i]);
+  const size_t smem = batched_smem_bytes(k, N, cfg->t_pad, (int)cfg->n_obs);
+  if (smem > 227 * 1024) return fail(h, -1, "batched path: experiment needs %zu bytes of shared memory (> 227 KB)", smem);
+  cudaStream_t st = h->stream;
+  auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = buf.reserve(bytes ? bytes : 8);
+    if (e != cudaSuccess || bytes == 0) return e;
+    return cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  DAB_CUDA(h, up(h->b_x0, x0, sizeof(double) * kN * batch));
+  DAB_CUDA(h, up(h->b_val, obs_values, sizeof(double) * n_obs_all * batch));
+  DAB_CUDA(h, up(h->b_idx, system_index, sizeof(int64_t) * n_obs_all * (shared_index ? 1 : batch)));
+  DAB_CUDA(h, up(h->b_pad, padded_time_idx, sizeof(int64_t) * (size_t)cfg->n_cycles * cfg->t_pad));
+  DAB_CUDA(h, up(h->b_rho, rho, sizeof(double) * batch));
+  BatchedArgs a{};
+  a.x0 = h->b_x0.as<double>(); a.obs_val = h->b_val.as<double>();
+  a.obs_idx = h->b_idx.as<long long>(); a.idx_batch_stride = shared_index ? 0 : (long long)n_obs_all;
+  a.padded = h->b_pad.as<long long>(); a.rho = h->b_rho.as<double>();
+  if (out_analysis) { DAB_CUDA(h, h->b_out.reserve(sizeof(double) * kN * batch * cfg->n_cycles)); a.out_analysis = h->b_out.as<double>(); }
+  if (out_mean) { DAB_CUDA(h, h->b_mean.reserve(sizeof(double) * (size_t)N * batch * cfg->n_cycles)); a.out_mean = h->b_mean.as<double>(); }
+  if (out_final) { DAB_CUDA(h, h->b_fin.reserve(sizeof(double) * kN * batch)); a.out_final = h->b_fin.as<double>(); }
+  a.n_obs_times = cfg->n_obs_times;
+  a.k = k; a.N = N; a.n_steps = cfg->n_steps; a.n_cycles = cfg->n_cycles; a.t_pad = cfg->t_pad;
+  a.n_obs = (int)cfg->n_obs;
+  a.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
+  a.dt = cfg->model_dt; a.F = cfg->forcing; a.sd = cfg->obs_error_sd > 0.0 ? cfg->obs_error_sd : 1.0;
+  DAB_CUDA(h, batched_launch(a, batch, st));
+  h->launches++;
+  if (out_analysis) DAB_CUDA(h, cudaMemcpyAsync(out_analysis, a.out_analysis, sizeof(double) * kN * batch * cfg->n_cycles, cudaMemcpyDeviceToHost, st));
+  if (out_mean) DAB_CUDA(h, cudaMemcpyAsync(out_mean, a.out_mean, sizeof(double) * (size_t)N * batch * cfg->n_cycles, cudaMemcpyDeviceToHost, st));
+  if (out_final) DAB_CUDA(h, cudaMemcpyAsync(out_final, a.out_final, sizeof(double) * kN * batch, cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(h, cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -47,6 +47,24 @@ struct TransformArgs {
 };
 cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st);
 
+// etkf_batched.cu: one CTA per experiment, whole experiment in one launch
+struct BatchedArgs {
+  const double* x0;            // [batch][k][N]
+  const double* obs_val;       // [batch][n_obs_times][n_obs] (NaN = padded slot)
+  const long long* obs_idx;    // [batch or 1][n_obs_times][n_obs]
+  long long idx_batch_stride;  // 0 when the index set is shared by all experiments
+  const long long* padded;     // [n_cycles][t_pad], shared
+  const double* rho;           // [batch]
+  double* out_analysis;        // nullable [batch][n_cycles][k][N]
+  double* out_mean;            // nullable [batch][n_cycles][N]
+  double* out_final;           // nullable [batch][k][N]
+  long long n_obs_times;
+  int k, N, n_steps, n_cycles, t_pad, n_obs, empty_R;
+  double dt, F, sd;
+};
+size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs);
+cudaError_t batched_launch(const BatchedArgs& a, int batch, cudaStream_t st);
+
 // fp64_peak.cu: measured FP64 roofline denominators (TFLOP/s)
 cudaError_t fp64_peak_measure(int sms, double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
 

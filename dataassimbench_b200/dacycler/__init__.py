@@ -1,4 +1,5 @@
 from ._dacycler import DACycler
 from ._etkf import ETKF
+from ._batched import cycle_batched
 
-__all__ = ["DACycler", "ETKF"]
+__all__ = ["DACycler", "ETKF", "cycle_batched"]

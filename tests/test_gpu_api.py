@@ -124,3 +124,25 @@ def test_multicycle_rmse_within_one_percent_of_reference_style_run():
     assert abs(gpu - ref) / ref < 0.01, (gpu, ref)
     assert dab.metrics.rmse(out[-1].mean(axis=0), z["truth"][-1]) == pytest.approx(
         o_metrics.rmse(out[-1].mean(axis=0), z["truth"][-1]))
+
+
+def test_cycle_batched_inflation_sweep_matches_single_cycles():
+    """dacycler.cycle_batched: same objects as cycle(), one launch for the whole sweep."""
+    N, k, n_cycles, S = 40, 20, 10, 20
+    gen = dab.data.Lorenz96(system_dim=N, delta_t=0.01)
+    nature = gen.generate(n_steps=n_cycles * S + 1)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[::S], random_location_count=20,
+                                error_sd=1.0, random_seed=5).observe()
+    model = dab.model.Lorenz96Model(model_obj=gen)
+    X0 = nature['x'].values[0] + np.random.default_rng(1).standard_normal((k, N))
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), X0)}, coords={'index': np.arange(N)})
+    rhos = [1.0, 1.1, 1.25, 1.4]
+    cyclers = [dab.dacycler.ETKF(system_dim=N, delta_t=0.01, model_obj=model, ensemble_dim=k,
+                                 multiplicative_inflation=r) for r in rhos]
+    out = dab.dacycler.cycle_batched(cyclers, init, 0.0, obs, n_cycles, analysis_window=0.2)
+    assert out['x'].shape == (4, n_cycles, k, N)
+    for b, dc in enumerate(cyclers):
+        single = dc.cycle(init, 0.0, obs, n_cycles, analysis_window=0.2)
+        assert rel_err(out['x'].values[b], single['x'].values) < 1e-10
+    m = dab.dacycler.cycle_batched(cyclers, init, 0.0, obs, n_cycles, analysis_window=0.2, return_mean_only=True)
+    assert rel_err(m['x_mean'].values, out['x'].values.mean(axis=2)) < 1e-12
