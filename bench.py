@@ -218,6 +218,37 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_c2_batched(H, B=4096, n_cycles=50):
+    """4096 independent Lorenz-96 N=40, k=20 ETKF experiments (inflation sweep 1.0..1.5), S=20,
+    through dab_etkf_cycle_batched_f64 with host buffers; wall clock of the second call."""
+    from dataassimbench_b200 import _native
+    from oracle import l96 as o_l96
+    N, k, S, n_obs, sd, dt = 40, 20, 20, 20, 1.0, 0.01
+    rng = np.random.default_rng(1)
+    truth0 = o_l96.rk4_forecast(8 + rng.standard_normal(N), 1000, dt)
+    _, truth = o_l96.rk4_forecast(truth0, n_cycles * S, dt, return_traj=True)
+    tidx = np.arange(0, n_cycles * S + 1, S)
+    locs = rng.choice(N, n_obs, replace=False, shuffle=False)
+    vals1 = truth[tidx][:, locs] + sd * rng.standard_normal((len(tidx), n_obs))
+    vals = np.ascontiguousarray(np.broadcast_to(vals1, (B,) + vals1.shape))
+    idx = np.ascontiguousarray(np.tile(locs, (len(tidx), 1)).astype(np.int64))
+    x0 = np.ascontiguousarray(truth[0] + rng.standard_normal((B, k, N)))
+    rho = np.linspace(1.0, 1.5, B)
+    padded = np.arange(1, n_cycles + 1, dtype=np.int64)[:, None].copy()
+    cfg = _native.CycleConfig(system_dim=N, ensemble_dim=k, n_steps=S, model_dt=dt, forcing=8.0, rho=1.0,
+                              obs_error_sd=sd, n_obs_times=len(tidx), n_obs=n_obs, stationary=1,
+                              n_cycles=n_cycles, t_pad=1, rank=0, world=1)
+    mean = np.empty((B, n_cycles, N))
+    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)
+    t0 = time.perf_counter()
+    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)
+    t1 = time.perf_counter()
+    return {"workload": "%d x (Lorenz96 N=40, k=20) ETKF, inflation sweep, %d cycles, S=20, one launch" % (B, n_cycles),
+            "experiment_cycles_per_s": B * n_cycles / (t1 - t0), "member_steps_per_s": B * n_cycles * k * S / (t1 - t0),
+            "seconds": t1 - t0, "all_finite": bool(np.isfinite(mean).all()),
+            "timer": "host wall clock, host buffers in, ensemble-mean analyses out"}
+
+
 # ------------------------------------------------------------------------------ product arm
 def run_product(args):
     import torch
@@ -314,6 +345,11 @@ def run_product(args):
                "timer": "host wall clock around dab_etkf_cycle_host_f64 (setup, H2D, %d cycles, "
                         "per-cycle D2H of the analysis, sync)" % BLOCK, "steps": reps * BLOCK}
 
+    # ---- BASELINE configs[1] in passing (N=1 only): 4096 x (N=40, k=20) inflation sweep, one launch
+    c2 = None
+    if world == 1 and w["name"] == "c3":
+        c2 = run_c2_batched(H)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,7 +426,7 @@ def run_product(args):
         "point_steps_per_s": cps * k * S * N,
         "all_finite": final,
         "roofline": roofline, "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "c2_batched": c2,
         "clocks": sampler.summary(t_wall0, t_wall1),
     }
     print(json.dumps(line))

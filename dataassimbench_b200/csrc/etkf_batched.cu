@@ -34,7 +34,6 @@ etkf_batched_kernel(const BatchedArgs a) {
   double* stats = dv + nyp;                             // k*k + k
   double* Tm = stats + k * k + k;                       // k*k
   double* ew = Tm + k * k;                              // eigensolver workspace
-  int* locs = reinterpret_cast<int*>(ew + eig_small_smem_doubles(k));   // nyp
 
   const double rho = a.rho[b];
   const double r_inv = 1.0 / (a.sd * a.sd);
@@ -79,7 +78,6 @@ etkf_batched_kernel(const BatchedArgs a) {
         loc = (int)idx_b[(ti - 1) * a.n_obs + o];
         if (y != y) { loc = -1; y = 0.0; }              // NaN = padded slot of a non-stationary network
       }
-      locs[r] = loc;
       double sum = 0.0;
       for (int j = 0; j < k; ++j) {
         const double v = loc >= 0 ? cur[j * NP + 2 + loc] : 0.0;
@@ -174,7 +172,7 @@ size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs) {
   const int nyp = t_pad * n_obs;
   size_t d = 2 * (size_t)k * (N + 3) + (size_t)k * nyp + nyp + ((size_t)k * k + k) + (size_t)k * k +
              (size_t)eig_small_smem_doubles(k);
-  return d * sizeof(double) + (size_t)nyp * sizeof(int) + 16;
+  return d * sizeof(double) + 16;
 }
 
 cudaError_t batched_launch(const BatchedArgs& a, int batch, cudaStream_t st) {
