@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,6 +61,8 @@ struct dab_handle {
   std::string err;
   long launches = 0;
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
+  DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
+  int eig_method = kEigAuto;
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
   Cycler cyc;
   // optional per-kernel timing (CUDA events on the launching stream)
@@ -164,7 +167,13 @@ int dab_create(dab_handle** out, int device) {
   memset(h->cyc.peer_open, 0, sizeof(h->cyc.peer_open));
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete h; return fail(nullptr, (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = h->ns_ws.reserve(ns_ws_bytes(kMaxEns));
+  if (e == cudaSuccess) e = cudaMemset(h->ns_ws.p, 0, 16);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, (int)e, "dab_create: %s", cudaGetErrorString(e)); }
+  if (const char* ev = getenv("DAB_EIG_METHOD")) {
+    if (!strcmp(ev, "jacobi")) h->eig_method = kEigJacobi;
+    else if (!strcmp(ev, "ns")) h->eig_method = kEigNewtonSchulz;
+  }
   *out = h;
   return 0;
 }
@@ -175,7 +184,7 @@ int dab_destroy(dab_handle* h) {
   cudaDeviceSynchronize();
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_seg.release();
-  h->s_partial.release(); h->s_stats.release(); h->s_T.release();
+  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
   h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -190,6 +199,13 @@ int dab_sync(dab_handle* h) {
   DAB_CUDA(h, cudaSetDevice(h->device));
   DAB_CUDA(h, cudaStreamSynchronize(h->stream));
   DAB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  return 0;
+}
+
+int dab_set_eig_method(dab_handle* h, int method) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, method == DAB_EIG_AUTO || method == DAB_EIG_JACOBI || method == DAB_EIG_NEWTON_SCHULZ);
+  h->eig_method = method;
   return 0;
 }
 
@@ -287,7 +303,8 @@ int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, dou
   DAB_ARG(h, (stats != nullptr || empty_R) && T != nullptr);
   DAB_ARG(h, k >= 2 && k <= DAB_MAX_ENSEMBLE && rho > 0.0);
   DAB_CUDA(h, cudaSetDevice(h->device));
-  DAB_CUDA(h, eig_transform_launch(stats, k, rho, empty_R, T, lam, sweeps, static_cast<cudaStream_t>(stream)));
+  DAB_CUDA(h, eig_transform_launch(stats, k, rho, empty_R, T, lam, sweeps, h->ns_ws.as<double>(), h->eig_method,
+                                   static_cast<cudaStream_t>(stream)));
   h->launches++;
   return 0;
 }
@@ -311,7 +328,7 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
     if (rc) return rc;
   }
   DAB_CUDA(h, eig_transform_launch(h->s_stats.as<double>(), k, rho, empty_R, h->s_T.as<double>(),
-                                   nullptr, nullptr, st));
+                                   nullptr, nullptr, h->ns_ws.as<double>(), h->eig_method, st));
   TransformArgs a{};
   a.T = h->s_T.as<double>();
   a.src[0] = Xb; a.src_ld = N;
@@ -558,7 +575,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   const int eb = cycle & 1;
   prof_mark(h, PROF_START);
   DAB_CUDA(h, eig_transform_launch(c.stats.as<double>(), k, c.cfg.rho, c.empty_R, c.T.as<double>(),
-                                   c.lam.as<double>(), c.info.as<int>(), h->stream));
+                                   nullptr, c.info.as<int>(), h->ns_ws.as<double>(), h->eig_method, h->stream));
   prof_mark(h, PROF_EIG);
   if (c.copied_pending[eb]) {                 // the D2H of cycle-2's analysis still reads ext[eb]
     DAB_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_copied[eb], 0));

@@ -51,7 +51,10 @@ eig_transform_kernel(const double* __restrict__ stats, int k, double rho, int em
 template <int RPL>
 __global__ void __launch_bounds__(512)
 eig_block_kernel(const double* __restrict__ stats, int k, double rho,
-                 double* __restrict__ Tout, double* __restrict__ lam_out, int* __restrict__ info_out, int skew) {
+                 double* __restrict__ Tout, double* __restrict__ lam_out, int* __restrict__ info_out, int skew,
+                 const int* __restrict__ run_flag) {
+  // enqueued behind the Newton-Schulz kernel (etkf_ns.cu) as its fallback: runs only if asked to
+  if (run_flag != nullptr && *run_flag == 0) return;
   constexpr int LPP = 8;
   constexpr int ROWS = RPL * LPP;
   constexpr int LD = ROWS + 8;
@@ -238,18 +241,27 @@ size_t eig_smem_bytes(int k) {
 }
 
 cudaError_t eig_transform_launch(const double* stats, int k, double rho, int empty_R, double* T,
-                                 double* lam_out, int* info_out, cudaStream_t st) {
+                                 double* lam_out, int* info_out, double* ns_ws, int method,
+                                 cudaStream_t st) {
   const size_t smem = eig_smem_bytes(k);
   if (k > 32 && !empty_R) {
+    // Newton-Schulz on a CTA cluster unless eigenvalues are wanted; Jacobi stays enqueued behind it
+    // as the fallback for ill-conditioned or non-finite statistics (one flag read when not needed).
+    const int* run_flag = nullptr;
+    if (method != kEigJacobi && lam_out == nullptr && ns_ws != nullptr) {
+      cudaError_t e = ns_transform_launch(stats, k, rho, ns_ws, T, info_out, st);
+      if (e != cudaSuccess) return e;
+      run_flag = reinterpret_cast<const int*>(ns_ws);
+    }
     const int threads = 32 * (((k + 7) & ~7) / 8);
     int skew = 150;          // cycles; measured optimum 100-200 on B200 (4 % faster than 0)
     if (const char* ev = getenv("DAB_EIG_SKEW")) skew = atoi(ev);
     if (k <= 64) {
       cudaFuncSetAttribute(eig_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      eig_block_kernel<8><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out, skew);
+      eig_block_kernel<8><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out, skew, run_flag);
     } else {
       cudaFuncSetAttribute(eig_block_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      eig_block_kernel<16><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out, skew);
+      eig_block_kernel<16><<<1, threads, smem, st>>>(stats, k, rho, T, lam_out, info_out, skew, run_flag);
     }
     return cudaGetLastError();
   }

@@ -1,0 +1,366 @@
+// K4 (fast path, 32 < k <= 128) -- the transform matrix T without an eigendecomposition.
+//
+// Replaces the same reference lines as etkf_eig.cu (dabench/dacycler/_etkf.py:142-161):
+//   Pa = pinv(A),  Wa = sqrtm((k-1) Pa),  wa = Pa g,   A = (k-1)/rho I + Y'^T R^-1 Y',
+// folded into  T = U + (I-U)(wa 1^T + Wa).  Both matrix functions are  A^{-1/2}:
+//   Wa = sqrt(k-1) A^{-1/2},   wa = A^{-1/2} (A^{-1/2} g).
+// A is symmetric positive definite with lambda_min(A) = (k-1)/rho EXACTLY (Y' is centred, so
+// C 1 = 0) and lambda_max(A) <= min(|A|_F, |A|_inf) =: s.  With the spectrum of A/s inside a
+// KNOWN interval [l0^2, 1], the coupled Newton-Schulz iteration (Higham, Functions of Matrices,
+// eq. 6.35 -- the numerically stable ordering Y <- Y T, Z <- T Z) with the optimal interval
+// scaling of Chen & Chow (2014) converges in a number of steps that is known in advance:
+//   M = Z Y,  T = (alpha/2)(3 I - alpha^2 M),  Y <- Y T,  Z <- T Z,   Z -> (A/s)^{-1/2}
+//   alpha^2 = 3/(1 + l + l^2),  l <- alpha l (3 - alpha^2 l^2)/2      (9 steps at cond 1e3)
+// Everything is k x k x k GEMM work, so -- unlike Jacobi, whose rotation chain is serial -- it
+// spreads over a thread-block cluster:
+//   * a cluster of 8 CTAs; CTA r owns rows R = [ROWS r, ROWS (r+1)) of Z and of Y^T (= columns
+//     of Y), ROWS = KP/8;
+//   * per step every CTA forms FOUR row-strip products on the FP64 tensor core (DMMA.8x8x4):
+//       M[R,:] = Z[R,:] Y          and  M[:,R]^T = Y^T[R,:] Z^T        (phase 1)
+//       Z'[R,:] = T[R,:] Z         and  Y'^T[R,:] = T[:,R]^T Y^T       (phase 2)
+//     (both the row AND the column strip of M are computed: using M[R,:]^T for M[:,R] is the
+//     unstable T Y ordering -- measured divergence at cond >= 1e5);
+//   * the A operand of every product is the CTA's own strip in shared memory; the B operand is
+//     the full matrix, streamed as DMMA fragments straight from L2 (ld.global.cg, 16-byte loads,
+//     every fetched sector fully used) and prefetched into registers a whole unit ahead;
+//   * the new strips go to a double-buffered global scratch (L2-resident, 4 KP^2 doubles) and ONE
+//     cluster barrier (release/acquire) per step publishes them.
+// Accuracy: error of T ~ cond(A) * 1e-17 (measured 1e-14 at cond 1e3, 2e-12 at 7e5).  When the
+// bound s/lambda_min exceeds kNsMaxCond, or the statistics are not finite, the kernel raises a
+// flag in the scratch header and the Jacobi eigensolver (etkf_eig.cu), always enqueued behind
+// it, runs instead (it exits at once when the flag is clear).
+#include <cmath>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dab {
+
+namespace {
+
+constexpr double kNsMaxCond = 1e7;
+constexpr int kNsMaxIter = 40;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// L2 load (the data was written by another SM a moment ago: never L1)
+__device__ __forceinline__ double2 ldcg2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+template <int KP, int NW>
+struct NsCfg {
+  static constexpr int ROWS = KP / 8;            // rows of a CTA's strips (cluster of 8)
+  static constexpr int MT = ROWS / 8;            // 8-row DMMA tiles per strip
+  static constexpr int LDS = KP + 8;             // strip stride: LDS.128 fragments conflict-free
+  static constexpr int NT8 = KP / 8;             // 8-column tiles across
+  static constexpr int NT16 = KP / 16;           // interleaved tile pairs across
+  static constexpr int J1 = 2 * NT8 / NW;        // phase-1 jobs per warp (product, tile)
+  static constexpr int V1 = KP / 8;              // 16-byte B loads per phase-1 job
+  static constexpr int J2 = 2 * NT16 / NW;       // phase-2 jobs per warp (product, tile pair)
+  static constexpr int V2 = KP / 4;              // 16-byte B loads per phase-2 job
+  static constexpr int UV = 16;                  // loads per prefetch unit
+  static constexpr int U1 = J1 * V1 / UV;        // prefetch units in phase 1
+  static constexpr int U2 = J2 * V2 / UV;
+  static constexpr int LDF = KP + 1;             // final stage: full Z in shared memory
+  static_assert(J1 >= 1 && J2 >= 1 && U1 >= 1 && U2 >= 1, "warp count does not divide the job list");
+  static_assert((J1 * V1) % UV == 0 && (J2 * V2) % UV == 0, "unit size");
+};
+
+}  // namespace
+
+// ws: [16 ints header][2 parities][Z | Yt][KP*KP] doubles.
+template <int KP, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ ws,
+                    double* __restrict__ Tout, int* __restrict__ info_out) {
+  using C = NsCfg<KP, NW>;
+  constexpr int ROWS = C::ROWS, MT = C::MT, LDS = C::LDS, NT = NW * 32;
+  extern __shared__ __align__(16) double sm[];
+  double* Zs = sm;                               // own rows of Z        [ROWS][LDS]
+  double* Yts = Zs + ROWS * LDS;                 // own rows of Y^T
+  double* Ts0 = Yts + ROWS * LDS;                // T[R,:]
+  double* Ts1 = Ts0 + ROWS * LDS;                // T[:,R]^T
+  __shared__ double red_sq[KP], red_abs[KP];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, q = lane & 3;
+  const int rank = (int)cluster_cta_rank();
+  const int R0 = ROWS * rank;
+  int* flags = reinterpret_cast<int*>(ws);
+  double* mats = ws + 2;                         // 16-byte header
+  const double shift = (double)(k - 1) / rho;
+
+  // ---- scale: s = min(|A|_F, |A|_inf) >= lambda_max; non-finite statistics poison |A|_F
+  for (int i = warp; i < k; i += NW) {
+    double sq = 0.0, ab = 0.0;
+    for (int j = lane; j < k; j += 32) {
+      const double a = stats[i * k + j] + (i == j ? shift : 0.0);
+      sq = fma(a, a, sq);
+      ab += fabs(a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    if (lane == 0) { red_sq[i] = sq; red_abs[i] = ab; }
+  }
+  __syncthreads();
+  double fro2 = 0.0, rmax = 0.0;
+  for (int i = 0; i < k; ++i) { fro2 += red_sq[i]; rmax = red_abs[i] > rmax ? red_abs[i] : rmax; }
+  const double fro = sqrt(fro2);
+  const double s = fro < rmax ? fro : rmax;
+  const bool ok = (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * shift);
+  if (!ok) {                                     // uniform over the cluster: same inputs, same code
+    if (rank == 0 && tid == 0) flags[0] = 1;
+    return;
+  }
+  const double inv_s = 1.0 / s;
+
+  // ---- Z0 = I, Y0 = A/s (identity on the padding): own strips to shared memory and to buffer 0
+  {
+    double* Zg = mats;
+    double* Ytg = mats + KP * KP;
+    for (int e = tid; e < ROWS * KP; e += NT) {
+      const int r = e / KP, j = e - r * KP, i = R0 + r;
+      const double z = (i == j) ? 1.0 : 0.0;
+      double y = z;
+      if (i < k && j < k) y = (stats[j * k + i] + (i == j ? shift : 0.0)) * inv_s;   // Yt[i][j] = A'[j][i]
+      Zs[r * LDS + j] = z; Yts[r * LDS + j] = y;
+      Zg[i * KP + j] = z; Ytg[i * KP + j] = y;
+    }
+  }
+  cluster_sync_all();
+
+  double l = sqrt(shift * inv_s) * (1.0 - 1e-6);
+  int par = 0, iters = 0;
+  for (; iters < kNsMaxIter; ++iters) {
+    const double al2 = 3.0 / (1.0 + l + l * l);
+    const double al = sqrt(al2);
+    const double c1 = 1.5 * al, c2 = -0.5 * al * al2;
+    const double* Zg = mats + (size_t)par * 2 * KP * KP;
+    const double* Ytg = Zg + KP * KP;
+    double* Zn = mats + (size_t)(par ^ 1) * 2 * KP * KP;
+    double* Ytn = Zn + KP * KP;
+
+    double2 b1[2][C::UV], b2[2][C::UV];          // double-buffered B fragments (constant-indexed)
+    // phase-1 B fragment g of the job list: transposed access, k-steps (2kk, 2kk+1) <-> j = 8kk+2q, +1
+    auto load1 = [&](int u, double2* dst) {
+#pragma unroll
+      for (int v = 0; v < C::UV; ++v) {
+        const int g = C::UV * u + v, ji = g / C::V1, kk = g % C::V1;
+        const int jg = warp + NW * ji, prod = jg / C::NT8, nt = jg % C::NT8;
+        const double* B = prod == 0 ? Ytg : Zg;
+        dst[v] = ldcg2(B + (8 * nt + fm) * KP + 8 * kk + 2 * q);
+      }
+    };
+    // phase-2 B fragment: straight access, one k-step per load, columns 16t+2fm, +1 (tile pair)
+    auto load2 = [&](int u, double2* dst) {
+#pragma unroll
+      for (int v = 0; v < C::UV; ++v) {
+        const int g = C::UV * u + v, ji = g / C::V2, ks = g % C::V2;
+        const int jg = warp + NW * ji, prod = jg / C::NT16, t = jg % C::NT16;
+        const double* B = prod == 0 ? Zg : Ytg;
+        const int j = 8 * (ks >> 1) + 2 * q + (ks & 1);
+        dst[v] = ldcg2(B + j * KP + 16 * t + 2 * fm);
+      }
+    };
+
+    // ---- phase 1: M[R,:] and M[:,R]^T
+    double acc1[C::J1][MT][2];
+#pragma unroll
+    for (int a = 0; a < C::J1; ++a)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) { acc1[a][m][0] = 0.0; acc1[a][m][1] = 0.0; }
+    load1(0, b1[0]);
+    if (C::U1 == 1) load2(0, b2[0]);             // short phase: the phase-2 unit rides along
+#pragma unroll
+    for (int u = 0; u < C::U1; ++u) {
+      if (u + 1 < C::U1) load1(u + 1, b1[(u + 1) & 1]);
+      else if (C::U1 > 1) load2(0, b2[0]);
+#pragma unroll
+      for (int v = 0; v < C::UV; ++v) {
+        const int g = C::UV * u + v, ji = g / C::V1, kk = g % C::V1;
+        const int jg = warp + NW * ji, prod = jg / C::NT8;
+        const double* As = prod == 0 ? Zs : Yts;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const double2 a = *reinterpret_cast<const double2*>(As + (8 * m + fm) * LDS + 8 * kk + 2 * q);
+          dmma884(acc1[ji][m][0], acc1[ji][m][1], a.x, b1[u & 1][v].x);
+          dmma884(acc1[ji][m][0], acc1[ji][m][1], a.y, b1[u & 1][v].y);
+        }
+      }
+    }
+    // T = c1 I + c2 M
+#pragma unroll
+    for (int ji = 0; ji < C::J1; ++ji) {
+      const int jg = warp + NW * ji, prod = jg / C::NT8, nt = jg % C::NT8;
+      double* Ts = prod == 0 ? Ts0 : Ts1;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int row = R0 + 8 * m + fm, col = 8 * nt + 2 * q;
+        double2 t;
+        t.x = fma(c2, acc1[ji][m][0], row == col ? c1 : 0.0);
+        t.y = fma(c2, acc1[ji][m][1], row == col + 1 ? c1 : 0.0);
+        *reinterpret_cast<double2*>(Ts + (8 * m + fm) * LDS + col) = t;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: Z'[R,:] = T[R,:] Z and Y'^T[R,:] = T[:,R]^T Y^T
+    double acc2[C::J2][2][MT][2];
+#pragma unroll
+    for (int a = 0; a < C::J2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { acc2[a][e][m][0] = 0.0; acc2[a][e][m][1] = 0.0; }
+#pragma unroll
+    for (int u = 0; u < C::U2; ++u) {
+      if (u + 1 < C::U2) load2(u + 1, b2[(u + 1) & 1]);
+#pragma unroll
+      for (int v = 0; v < C::UV; v += 2) {
+        const int g = C::UV * u + v, ji = g / C::V2, ks = g % C::V2;
+        const int jg = warp + NW * ji, prod = jg / C::NT16;
+        const double* As = prod == 0 ? Ts0 : Ts1;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const double2 a = *reinterpret_cast<const double2*>(As + (8 * m + fm) * LDS + 8 * (ks >> 1) + 2 * q);
+          dmma884(acc2[ji][0][m][0], acc2[ji][0][m][1], a.x, b2[u & 1][v].x);
+          dmma884(acc2[ji][1][m][0], acc2[ji][1][m][1], a.x, b2[u & 1][v].y);
+          dmma884(acc2[ji][0][m][0], acc2[ji][0][m][1], a.y, b2[u & 1][v + 1].x);
+          dmma884(acc2[ji][1][m][0], acc2[ji][1][m][1], a.y, b2[u & 1][v + 1].y);
+        }
+      }
+    }
+    // new strips: own shared memory (next step's A operand) and the other global buffer
+#pragma unroll
+    for (int ji = 0; ji < C::J2; ++ji) {
+      const int jg = warp + NW * ji, prod = jg / C::NT16, t = jg % C::NT16;
+      double* Ss = prod == 0 ? Zs : Yts;
+      double* Sg = prod == 0 ? Zn : Ytn;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int r = 8 * m + fm, col = 16 * t + 4 * q;
+        const double2 lo = make_double2(acc2[ji][0][m][0], acc2[ji][1][m][0]);
+        const double2 hi = make_double2(acc2[ji][0][m][1], acc2[ji][1][m][1]);
+        *reinterpret_cast<double2*>(Ss + r * LDS + col) = lo;
+        *reinterpret_cast<double2*>(Ss + r * LDS + col + 2) = hi;
+        *reinterpret_cast<double2*>(Sg + (R0 + r) * KP + col) = lo;
+        *reinterpret_cast<double2*>(Sg + (R0 + r) * KP + col + 2) = hi;
+      }
+    }
+    cluster_sync_all();
+    par ^= 1;
+    l = 0.5 * al * l * (3.0 - al2 * l * l);
+    if (1.0 - l < 1e-13) { ++iters; break; }
+  }
+
+  // ---- T = U + (I-U)(wa 1^T + Wa),  Wa = sqrt((k-1)/s) Z,  wa = Z (Z g) / s; rows R of T
+  {
+    constexpr int LDF = C::LDF;
+    double* Zf = sm;                             // overlays the strips (all CTAs are past the barrier)
+    double* gs = Zf + KP * LDF;                  // g, zero beyond k
+    double* us = gs + KP;                        // u = Z g
+    double* cs = us + KP;                        // column sums of Z over the real rows
+    double* was = cs + KP;                       // wa on the own rows, then [ROWS] = mean(wa)
+    const double* Zg = mats + (size_t)par * 2 * KP * KP;
+    for (int e = tid; e < KP * KP / 2; e += NT) {
+      const int i = (2 * e) / KP, j = (2 * e) - i * KP;
+      const double2 v = ldcg2(Zg + 2 * e);
+      Zf[i * LDF + j] = v.x; Zf[i * LDF + j + 1] = v.y;
+    }
+    for (int j = tid; j < KP; j += NT) gs[j] = j < k ? stats[k * k + j] : 0.0;
+    __syncthreads();
+    for (int w = tid; w < 2 * KP; w += NT) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (w < KP) {                              // u_i = sum_j Z[i][j] g_j
+        const double* zr = Zf + w * LDF;
+        for (int j = 0; j < KP; j += 4) {
+          a0 = fma(zr[j], gs[j], a0); a1 = fma(zr[j + 1], gs[j + 1], a1);
+          a2 = fma(zr[j + 2], gs[j + 2], a2); a3 = fma(zr[j + 3], gs[j + 3], a3);
+        }
+        us[w] = (a0 + a1) + (a2 + a3);
+      } else {                                   // cs_j = sum_{i<k} Z[i][j]
+        const double* zc = Zf + (w - KP);
+        int i = 0;
+        for (; i + 3 < k; i += 4) {
+          a0 += zc[i * LDF]; a1 += zc[(i + 1) * LDF]; a2 += zc[(i + 2) * LDF]; a3 += zc[(i + 3) * LDF];
+        }
+        for (; i < k; ++i) a0 += zc[i * LDF];
+        cs[w - KP] = (a0 + a1) + (a2 + a3);
+      }
+    }
+    __syncthreads();
+    const double inv_k = 1.0 / (double)k;
+    for (int w = tid; w <= ROWS; w += NT) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const double* zr = w < ROWS ? Zf + (R0 + w) * LDF : cs;   // the last one: mean(wa) = cs . u / (k s)
+      for (int j = 0; j < KP; j += 4) {
+        a0 = fma(zr[j], us[j], a0); a1 = fma(zr[j + 1], us[j + 1], a1);
+        a2 = fma(zr[j + 2], us[j + 2], a2); a3 = fma(zr[j + 3], us[j + 3], a3);
+      }
+      const double v = ((a0 + a1) + (a2 + a3)) * inv_s;
+      was[w] = w < ROWS ? v : v * inv_k;
+    }
+    __syncthreads();
+    const double cw = sqrt((double)(k - 1) * inv_s);
+    const double wmean = was[ROWS];
+    for (int e = tid; e < ROWS * KP; e += NT) {
+      const int r = e / KP, j = e - r * KP, i = R0 + r;
+      if (i < k && j < k)
+        Tout[i * k + j] = inv_k + (was[r] - wmean) + cw * (Zf[i * LDF + j] - cs[j] * inv_k);
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    flags[0] = 0;
+    if (info_out) *info_out = iters;
+  }
+}
+
+size_t ns_ws_bytes(int k) {
+  const size_t kp = k <= 64 ? 64 : 128;
+  return 16 + sizeof(double) * 4 * kp * kp;
+}
+
+namespace {
+template <int KP, int NW>
+cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, double* T, int* info_out,
+                        cudaStream_t st) {
+  using C = NsCfg<KP, NW>;
+  size_t strips = sizeof(double) * 4 * C::ROWS * C::LDS;
+  size_t fin = sizeof(double) * ((size_t)KP * C::LDF + 4 * KP + C::ROWS + 8);
+  size_t smem = strips > fin ? strips : fin;
+  auto kern = ns_transform_kernel<KP, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(8);
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, stats, k, rho, ws, T, info_out);
+}
+}  // namespace
+
+cudaError_t ns_transform_launch(const double* stats, int k, double rho, double* ws, double* T,
+                                int* info_out, cudaStream_t st) {
+  if (k <= 64) return ns_launch_t<64, 8>(stats, k, rho, ws, T, info_out, st);
+  return ns_launch_t<128, 8>(stats, k, rho, ws, T, info_out, st);
+}
+
+}  // namespace dab

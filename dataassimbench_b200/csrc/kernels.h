@@ -30,10 +30,17 @@ cudaError_t gather_launch(const double* X, long long ld, int k, const long long*
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
                             long long n_y, int* loc, double* val, cudaStream_t st);
 
-// K4  etkf_eig.cu
+// K4  etkf_eig.cu (Jacobi eigensolver) and etkf_ns.cu (cluster Newton-Schulz, 32 < k <= 128)
+enum { kEigAuto = 0, kEigJacobi = 1, kEigNewtonSchulz = 2 };
 size_t eig_smem_bytes(int k);
+// ns_ws: ns_ws_bytes(k) bytes of device scratch (nullable: Jacobi only).  The Newton-Schulz path is
+// taken when method != kEigJacobi, k > 32, lam_out == nullptr (it has no eigenvalues to report).
 cudaError_t eig_transform_launch(const double* stats, int k, double rho, int empty_R, double* T,
-                                 double* lam_out, int* info_out, cudaStream_t st);
+                                 double* lam_out, int* info_out, double* ns_ws, int method,
+                                 cudaStream_t st);
+size_t ns_ws_bytes(int k);
+cudaError_t ns_transform_launch(const double* stats, int k, double rho, double* ws, double* T,
+                                int* info_out, cudaStream_t st);
 
 // K5  etkf_transform.cu
 struct TransformArgs {

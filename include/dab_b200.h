@@ -48,6 +48,16 @@ DAB_API int dab_destroy(dab_handle* h);
 DAB_API int dab_sync(dab_handle* h);
 DAB_API const char* dab_last_error(const dab_handle* h);   /* h may be NULL: last create() error */
 
+/* How the k x k part of the analysis (pinv + sqrtm, dabench/dacycler/_etkf.py:142-154) is solved
+ * for 32 < k <= 128.  AUTO: Newton-Schulz inverse square root on an 8-CTA cluster, with the
+ * Jacobi eigensolver as the automatic fallback (ill-conditioned or non-finite statistics, or when
+ * eigenvalues are requested); JACOBI: always the eigensolver.  k <= 32 always uses Jacobi.
+ * Also settable with the environment variable DAB_EIG_METHOD=jacobi|ns before dab_create. */
+#define DAB_EIG_AUTO 0
+#define DAB_EIG_JACOBI 1
+#define DAB_EIG_NEWTON_SCHULZ 2
+DAB_API int dab_set_eig_method(dab_handle* h, int method);
+
 /* ---- K1: Lorenz-96 RK4 ensemble forecast -----------------------------------------------
  * Replaces ETKF._step_forecast (dabench/dacycler/_etkf.py:64-80) -> Model.forecast ->
  * Data.generate (dabench/data/_data.py:86-211) -> integrate (dabench/data/_utils.py:16-57)
@@ -78,7 +88,8 @@ DAB_API int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, 
                        double* stats, void* stream);
 /* T [k][k] dev row-major with Xa[N,k] = Xb[N,k] T  (dabench/dacycler/_etkf.py:142-161);
  * empty_R != 0 selects the reference's zero branch (:149-152).
- * lam nullable dev [k]: eigenvalues of (k-1)/rho I + C; sweeps nullable dev int. */
+ * lam nullable dev [k]: eigenvalues of (k-1)/rho I + C (asking for them selects the Jacobi
+ * eigensolver); sweeps nullable dev int: Jacobi sweeps or Newton-Schulz steps used. */
 DAB_API int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, double rho,
                                   int empty_R, double* T, double* lam, int* sweeps, void* stream);
 

@@ -166,6 +166,77 @@ def test_transform_matrix_matches_oracle(H, k, rho):
     assert rel_err(T.cpu().numpy(), T_ref) < 1e-11
 
 
+def _random_stats(k, rho, scale, seed):
+    rng = np.random.default_rng(seed)
+    n_y = max(3, 3 * k)
+    Yp = rng.standard_normal((k, n_y)) * np.logspace(0, scale, n_y)
+    Yp -= Yp.mean(axis=0)
+    C = Yp @ Yp.T
+    g = Yp @ rng.standard_normal(n_y)
+    return C, g
+
+
+@pytest.mark.parametrize("k", [33, 40, 64, 65, 100, 128])
+@pytest.mark.parametrize("rho,scale", [(1.0, 0.0), (1.3, 1.0), (1.0, 2.0), (1.05, 3.0)])
+def test_transform_matrix_newton_schulz_path(H, k, rho, scale):
+    """32 < k <= 128 without an eigenvalue request: the cluster Newton-Schulz kernel
+    (csrc/etkf_ns.cu).  Same tolerance as the eigensolver path, and agreement with it."""
+    C, g = _random_stats(k, rho, scale, seed=1000 * k + int(10 * scale))
+    T_ref = o_etkf.transform_from_stats(C, g, k, rho)
+    stats = dev(np.concatenate([C.ravel(), g]))
+    st = torch.cuda.current_stream().cuda_stream
+    T = torch.full((k, k), float('nan'), dtype=torch.float64, device='cuda')
+    steps = torch.zeros(1, dtype=torch.int32, device='cuda')
+    H.set_eig_method(H.EIG_AUTO)
+    H.etkf_transform_matrix(stats, k, rho, False, T, None, steps, st)
+    torch.cuda.synchronize()
+    cond = np.linalg.cond((k - 1) / rho * np.eye(k) + C)
+    assert 0 < int(steps.item()) < 30, (int(steps.item()), cond)
+    assert rel_err(T.cpu().numpy(), T_ref) < 1e-11, cond
+    T_j = torch.empty_like(T)
+    H.set_eig_method(H.EIG_JACOBI)
+    try:
+        H.etkf_transform_matrix(stats, k, rho, False, T_j, None, None, st)
+        torch.cuda.synchronize()
+    finally:
+        H.set_eig_method(H.EIG_AUTO)
+    assert rel_err(T.cpu().numpy(), T_j.cpu().numpy()) < 1e-11
+    # bit-reproducible from call to call (the sharded cycler replicates K4 on every rank)
+    T2 = torch.empty_like(T)
+    H.etkf_transform_matrix(stats, k, rho, False, T2, None, None, st)
+    torch.cuda.synchronize()
+    assert torch.equal(T, T2)
+
+
+@pytest.mark.parametrize("k", [64, 128])
+def test_transform_matrix_newton_schulz_falls_back(H, k):
+    """Ill-conditioned (bound on cond(A) > 1e7) or non-finite statistics: the Jacobi eigensolver
+    enqueued behind the Newton-Schulz kernel takes over; the result keeps the oracle tolerance."""
+    rho = 1.0
+    C, g = _random_stats(k, rho, 4.0, seed=k)
+    assert np.linalg.cond((k - 1) / rho * np.eye(k) + C) > 3e7      # cond <= the kernel's bound
+    T_ref = o_etkf.transform_from_stats(C, g, k, rho)
+    st = torch.cuda.current_stream().cuda_stream
+    T = torch.full((k, k), float('nan'), dtype=torch.float64, device='cuda')
+    sweeps = torch.zeros(1, dtype=torch.int32, device='cuda')
+    H.etkf_transform_matrix(dev(np.concatenate([C.ravel(), g])), k, rho, False, T, None, sweeps, st)
+    torch.cuda.synchronize()
+    assert int(sweeps.item()) > 0
+    assert rel_err(T.cpu().numpy(), T_ref) < 1e-10                  # eigh itself is ~cond*eps here
+    # a well-conditioned problem right after it: the fallback flag is cleared again
+    C, g = _random_stats(k, rho, 0.0, seed=k + 1)
+    T_ref = o_etkf.transform_from_stats(C, g, k, rho)
+    H.etkf_transform_matrix(dev(np.concatenate([C.ravel(), g])), k, rho, False, T, None, None, st)
+    torch.cuda.synchronize()
+    assert rel_err(T.cpu().numpy(), T_ref) < 1e-11
+    bad = np.concatenate([C.ravel(), g])
+    bad[5] = np.nan
+    T.zero_()
+    H.etkf_transform_matrix(dev(bad), k, rho, False, T, None, None, st)
+    torch.cuda.synchronize()
+    assert not np.all(np.isfinite(T.cpu().numpy()))
+
+
 def test_transform_matrix_empty_R_and_no_obs(H):
     k = 12
     T = torch.empty((k, k), dtype=torch.float64, device='cuda')
