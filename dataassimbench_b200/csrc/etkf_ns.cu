@@ -57,6 +57,13 @@ __device__ __forceinline__ double2 ldcg2(const double* p) {
   return v;
 }
 
+// -DDAB_NS_TIMING: thread 0 of CTA 0 accumulates clock64() per section and prints them (debug builds only)
+#ifdef DAB_NS_TIMING
+#define NS_TICK(i) do { const long long now_ = clock64(); ns_t[i] += now_ - ns_tick; ns_tick = now_; } while (0)
+#else
+#define NS_TICK(i) do { } while (0)
+#endif
+
 template <int KP, int NW>
 struct NsCfg {
   static constexpr int ROWS = KP / 8;            // rows of a CTA's strips (cluster of 8)
@@ -99,25 +106,50 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   int* flags = reinterpret_cast<int*>(ws);
   double* mats = ws + 2;                         // 16-byte header
   const double shift = (double)(k - 1) / rho;
+#ifdef DAB_NS_TIMING
+  long long ns_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ns_tick = clock64();
+#endif
 
-  // ---- scale: s = min(|A|_F, |A|_inf) >= lambda_max; non-finite statistics poison |A|_F
-  for (int i = warp; i < k; i += NW) {
+  // ---- scale: s = min(|A|_F, |A|_inf) >= lambda_max; non-finite statistics poison |A|_F.
+  // TPR threads per row, interleaved columns (all loads in flight at once, sectors fully used)
+  {
+    constexpr int TPR = NT / KP, CPT = KP / TPR;
+    const int i = tid / TPR, c = tid % TPR;
+    double v[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; ++m) {
+      const int j = c + TPR * m;
+      v[m] = (i < k && j < k) ? stats[i * k + j] + (i == j ? shift : 0.0) : 0.0;
+    }
     double sq = 0.0, ab = 0.0;
-    for (int j = lane; j < k; j += 32) {
-      const double a = stats[i * k + j] + (i == j ? shift : 0.0);
-      sq = fma(a, a, sq);
-      ab += fabs(a);
+#pragma unroll
+    for (int m = 0; m < CPT; ++m) { sq = fma(v[m], v[m], sq); ab += fabs(v[m]); }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    if (c == 0) { red_sq[i] = sq; red_abs[i] = ab; }
+  }
+  __syncthreads();
+  double fro2 = 0.0, rmax = 0.0;
+  {
+    // every warp reduces the KP row values redundantly: fixed order, identical in every thread
+    double sq = 0.0, ab = 0.0;
+#pragma unroll
+    for (int m = 0; m < KP / 32; ++m) {
+      sq += red_sq[lane + 32 * m];
+      const double a = red_abs[lane + 32 * m];
+      ab = a > ab ? a : ab;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+      const double a = __shfl_xor_sync(0xffffffffu, ab, o);
+      ab = a > ab ? a : ab;
     }
-    if (lane == 0) { red_sq[i] = sq; red_abs[i] = ab; }
+    fro2 = sq; rmax = ab;
   }
-  __syncthreads();
-  double fro2 = 0.0, rmax = 0.0;
-  for (int i = 0; i < k; ++i) { fro2 += red_sq[i]; rmax = red_abs[i] > rmax ? red_abs[i] : rmax; }
   const double fro = sqrt(fro2);
   const double s = fro < rmax ? fro : rmax;
   const bool ok = (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * shift);
@@ -135,12 +167,13 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
       const int r = e / KP, j = e - r * KP, i = R0 + r;
       const double z = (i == j) ? 1.0 : 0.0;
       double y = z;
-      if (i < k && j < k) y = (stats[j * k + i] + (i == j ? shift : 0.0)) * inv_s;   // Yt[i][j] = A'[j][i]
+      if (i < k && j < k) y = (stats[i * k + j] + (i == j ? shift : 0.0)) * inv_s;   // Y0 := (A/s)^T = A/s up to the rounding asymmetry of C
       Zs[r * LDS + j] = z; Yts[r * LDS + j] = y;
       Zg[i * KP + j] = z; Ytg[i * KP + j] = y;
     }
   }
   cluster_sync_all();
+  NS_TICK(0);
 
   double l = sqrt(shift * inv_s) * (1.0 - 1e-6);
   int par = 0, iters = 0;
@@ -201,6 +234,10 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
         }
       }
     }
+#ifdef DAB_NS_TIMING
+    if (acc1[0][0][0] == -1.2345e300) ns_t[7] -= 1;   // make the tick wait for the DMMA chain
+#endif
+    NS_TICK(1);
     // T = c1 I + c2 M
 #pragma unroll
     for (int ji = 0; ji < C::J1; ++ji) {
@@ -216,6 +253,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
       }
     }
     __syncthreads();
+    NS_TICK(2);
 
     // ---- phase 2: Z'[R,:] = T[R,:] Z and Y'^T[R,:] = T[:,R]^T Y^T
     double acc2[C::J2][2][MT][2];
@@ -243,6 +281,10 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
         }
       }
     }
+#ifdef DAB_NS_TIMING
+    if (acc2[0][0][0][0] == -1.2345e300) ns_t[7] -= 1;
+#endif
+    NS_TICK(3);
     // new strips: own shared memory (next step's A operand) and the other global buffer
 #pragma unroll
     for (int ji = 0; ji < C::J2; ++ji) {
@@ -260,7 +302,9 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
         *reinterpret_cast<double2*>(Sg + (R0 + r) * KP + col + 2) = hi;
       }
     }
+    NS_TICK(4);
     cluster_sync_all();
+    NS_TICK(5);
     par ^= 1;
     l = 0.5 * al * l * (3.0 - al2 * l * l);
     if (1.0 - l < 1e-13) { ++iters; break; }
@@ -275,43 +319,59 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
     double* cs = us + KP;                        // column sums of Z over the real rows
     double* was = cs + KP;                       // wa on the own rows, then [ROWS] = mean(wa)
     const double* Zg = mats + (size_t)par * 2 * KP * KP;
-    for (int e = tid; e < KP * KP / 2; e += NT) {
-      const int i = (2 * e) / KP, j = (2 * e) - i * KP;
-      const double2 v = ldcg2(Zg + 2 * e);
-      Zf[i * LDF + j] = v.x; Zf[i * LDF + j + 1] = v.y;
+    {
+      constexpr int NL = KP * KP / 2 / NT;       // all loads in flight before the first store
+      double2 v[NL];
+#pragma unroll
+      for (int m = 0; m < NL; ++m) v[m] = ldcg2(Zg + 2 * (tid + NT * m));
+#pragma unroll
+      for (int m = 0; m < NL; ++m) {
+        const int e = tid + NT * m, i = (2 * e) / KP, j = (2 * e) - i * KP;
+        Zf[i * LDF + j] = v[m].x; Zf[i * LDF + j + 1] = v[m].y;
+      }
     }
     for (int j = tid; j < KP; j += NT) gs[j] = j < k ? stats[k * k + j] : 0.0;
     __syncthreads();
-    for (int w = tid; w < 2 * KP; w += NT) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      if (w < KP) {                              // u_i = sum_j Z[i][j] g_j
-        const double* zr = Zf + w * LDF;
-        for (int j = 0; j < KP; j += 4) {
-          a0 = fma(zr[j], gs[j], a0); a1 = fma(zr[j + 1], gs[j + 1], a1);
-          a2 = fma(zr[j + 2], gs[j + 2], a2); a3 = fma(zr[j + 3], gs[j + 3], a3);
-        }
-        us[w] = (a0 + a1) + (a2 + a3);
-      } else {                                   // cs_j = sum_{i<k} Z[i][j]
-        const double* zc = Zf + (w - KP);
-        int i = 0;
-        for (; i + 3 < k; i += 4) {
-          a0 += zc[i * LDF]; a1 += zc[(i + 1) * LDF]; a2 += zc[(i + 2) * LDF]; a3 += zc[(i + 3) * LDF];
-        }
-        for (; i < k; ++i) a0 += zc[i * LDF];
-        cs[w - KP] = (a0 + a1) + (a2 + a3);
+    {
+      // TPR threads per row/column: u_i = sum_j Z[i][j] g_j and cs_j = sum_{i<k} Z[i][j]
+      constexpr int TPR = NT / KP, CPT = KP / TPR;
+      const int i = tid / TPR, c = tid % TPR;
+      double u0 = 0.0, u1 = 0.0, s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < CPT; m += 2) {
+        const int j0 = c + TPR * m, j1 = j0 + TPR;
+        u0 = fma(Zf[i * LDF + j0], gs[j0], u0);
+        u1 = fma(Zf[i * LDF + j1], gs[j1], u1);
+        s0 += j0 < k ? Zf[j0 * LDF + i] : 0.0;
+        s1 += j1 < k ? Zf[j1 * LDF + i] : 0.0;
       }
+      u0 += u1; s0 += s1;
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) {
+        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      }
+      if (c == 0) { us[i] = u0; cs[i] = s0; }
     }
     __syncthreads();
     const double inv_k = 1.0 / (double)k;
-    for (int w = tid; w <= ROWS; w += NT) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      const double* zr = w < ROWS ? Zf + (R0 + w) * LDF : cs;   // the last one: mean(wa) = cs . u / (k s)
-      for (int j = 0; j < KP; j += 4) {
-        a0 = fma(zr[j], us[j], a0); a1 = fma(zr[j + 1], us[j + 1], a1);
-        a2 = fma(zr[j + 2], us[j + 2], a2); a3 = fma(zr[j + 3], us[j + 3], a3);
+    {
+      // wa on the own rows (TPW threads per row), and mean(wa) = cs . u / (k s) in every warp
+      constexpr int TPW = NT / ROWS, CPW = KP / TPW;
+      const int r = tid / TPW, c = tid % TPW;
+      const double* zr = Zf + (R0 + r) * LDF;
+      double a0 = 0.0, m0 = 0.0;
+#pragma unroll
+      for (int m = 0; m < CPW; ++m) a0 = fma(zr[c + TPW * m], us[c + TPW * m], a0);
+#pragma unroll
+      for (int m = 0; m < KP / 32; ++m) m0 = fma(cs[lane + 32 * m], us[lane + 32 * m], m0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        if (o < TPW) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
       }
-      const double v = ((a0 + a1) + (a2 + a3)) * inv_s;
-      was[w] = w < ROWS ? v : v * inv_k;
+      if (c == 0) was[r] = a0 * inv_s;
+      if (tid == 0) was[ROWS] = m0 * inv_s * inv_k;
     }
     __syncthreads();
     const double cw = sqrt((double)(k - 1) * inv_s);
@@ -322,9 +382,14 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
         Tout[i * k + j] = inv_k + (was[r] - wmean) + cw * (Zf[i * LDF + j] - cs[j] * inv_k);
     }
   }
+  NS_TICK(6);
   if (rank == 0 && tid == 0) {
     flags[0] = 0;
     if (info_out) *info_out = iters;
+#ifdef DAB_NS_TIMING
+    printf("ns k=%d iters=%d cycles: prologue %lld | phase1(+L2 wait) %lld epi1+sync %lld phase2 %lld store %lld cluster_barrier %lld | final %lld\n",
+           k, iters, ns_t[0], ns_t[1], ns_t[2], ns_t[3], ns_t[4], ns_t[5], ns_t[6]);
+#endif
   }
 }
 

@@ -7,7 +7,7 @@
 //   Lorenz96.rhs                    dabench/data/_lorenz96.py:119-151
 // (fixed-step classical RK4 instead of adaptive Dormand-Prince, as BASELINE.json's north star asks).
 //
-// Design (B200, FP64-pipe bound: 19 DFMA/DADD per grid point per step, 16 bytes of HBM per
+// Design (B200, FP64-pipe bound: 17 DFMA/DADD per grid point per step, 16 bytes of HBM per
 // grid point per WINDOW):
 //   * one CTA = one member x one tile of W = blockDim*P consecutive grid points, held in
 //     REGISTERS (P points per thread, blocked) for all n_steps steps of the window;
@@ -74,14 +74,23 @@ l96_rk4_window_kernel(const L96Args a) {
   }
   __syncthreads();
 
-  double x[P], s[P], acc[P];
+  // 17 FP64 instructions per point and step (DADD d, DFMA t, DFMA next stage, DFMA weighted sum;
+  // the last stage needs no next-stage value, plus two DADDs per step for the bases):
+  //   t_j = (y_{i+1} - y_{i-2}) y_{i-1} - y_i           (k_j = t_j + F: F is folded into the bases)
+  //   y_2 = xh + h/2 t_1,  y_3 = xh + h/2 t_2,  y_4 = xd + h t_3,    xh = x + h/2 F,  xd = x + h F
+  //   x'  = xd + h/6 t_1 + h/3 t_2 + h/3 t_3 + h/6 t_4  (= x + h/6 (k_1 + 2 k_2 + 2 k_3 + k_4))
+  double s[P], xh[P], xd[P], acc[P];
+  const double dt = a.dt, F = a.F;
+  const double h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
+  const double h2F = h2 * F, dtF = dt * F;
 #pragma unroll
-  for (int i = 0; i < P; ++i) { x[i] = stage[phys<P>(t * P + i)]; s[i] = x[i]; }
+  for (int i = 0; i < P; ++i) {
+    s[i] = stage[phys<P>(t * P + i)];
+    xh[i] = s[i] + h2F; xd[i] = s[i] + dtF;
+  }
 
   const int tl = t > 0 ? t - 1 : 0;
   const int tr = t < T - 1 ? t + 1 : T - 1;
-  const double dt = a.dt, F = a.F;
-  const double h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
 
   // edges of the stage-1 input (x itself)
   int buf = 0;
@@ -103,14 +112,14 @@ l96_rk4_window_kernel(const L96Args a) {
       const double cw = (st == 0 || st == 3) ? h6 : h3;      // RK4 weight
       double kk[P];
       // edge points first so the next stage's edges can be published early
-      kk[0] = fma((P > 1 ? s[1] : R) - L.x, L.y, F - s[0]);
-      if (P > 1) kk[1] = fma((P > 2 ? s[2] : R) - L.y, s[0], F - s[1]);
-      if (P > 2) kk[P - 1] = fma(R - s[P - 3], s[P - 2], F - s[P - 1]);
-      if (P > 3) kk[P - 2] = fma(s[P - 1] - s[P - 4], s[P - 3], F - s[P - 2]);
+      kk[0] = fma((P > 1 ? s[1] : R) - L.x, L.y, -s[0]);
+      if (P > 1) kk[1] = fma((P > 2 ? s[2] : R) - L.y, s[0], -s[1]);
+      if (P > 2) kk[P - 1] = fma(R - s[P - 3], s[P - 2], -s[P - 1]);
+      if (P > 3) kk[P - 2] = fma(s[P - 1] - s[P - 4], s[P - 3], -s[P - 2]);
       if (st < 3) {
-        const double n0 = fma(ca, kk[0], x[0]);
-        const double n2 = fma(ca, kk[P - 2], x[P - 2]);
-        const double n1 = fma(ca, kk[P - 1], x[P - 1]);
+        const double n0 = fma(ca, kk[0], st == 2 ? xd[0] : xh[0]);
+        const double n2 = fma(ca, kk[P - 2], st == 2 ? xd[P - 2] : xh[P - 2]);
+        const double n1 = fma(ca, kk[P - 1], st == 2 ? xd[P - 1] : xh[P - 1]);
         e_first[buf * T + t] = n0;
         e_last2[buf * T + t] = make_double2(n2, n1);
       } else {
@@ -121,13 +130,13 @@ l96_rk4_window_kernel(const L96Args a) {
         e_last2[buf * T + t] = make_double2(n2, n1);
       }
 #pragma unroll
-      for (int i = 2; i < P - 2; ++i) kk[i] = fma(s[i + 1] - s[i - 2], s[i - 1], F - s[i]);
+      for (int i = 2; i < P - 2; ++i) kk[i] = fma(s[i + 1] - s[i - 2], s[i - 1], -s[i]);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        if (st == 0) acc[i] = fma(cw, kk[i], x[i]);
-        else acc[i] = fma(cw, kk[i], acc[i]);
-        if (st < 3) s[i] = fma(ca, kk[i], x[i]);
-        else { x[i] = acc[i]; s[i] = acc[i]; }
+        if (st == 0) acc[i] = fma(cw, kk[i], xd[i]);
+        else if (st < 3) acc[i] = fma(cw, kk[i], acc[i]);
+        if (st < 3) s[i] = fma(ca, kk[i], st == 2 ? xd[i] : xh[i]);
+        else { s[i] = fma(cw, kk[i], acc[i]); xh[i] = s[i] + h2F; xd[i] = s[i] + dtF; }
       }
     }
     if (a.traj != nullptr) {
@@ -135,7 +144,7 @@ l96_rk4_window_kernel(const L96Args a) {
 #pragma unroll
       for (int i = 0; i < P; ++i) {
         const long long g = g0 + (long long)t * P + i;
-        if (g >= out_lo && g < out_hi) trow[g] = x[i];
+        if (g >= out_lo && g < out_hi) trow[g] = s[i];
       }
     }
   }
@@ -143,7 +152,7 @@ l96_rk4_window_kernel(const L96Args a) {
   // ---- coalesced store of the useful (still valid) centre of the tile
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < P; ++i) stage[phys<P>(t * P + i)] = x[i];
+  for (int i = 0; i < P; ++i) stage[phys<P>(t * P + i)] = s[i];
   __syncthreads();
   double* out_row = a.out + (long long)member * a.out_ld;
 #pragma unroll
@@ -363,6 +372,7 @@ template <int P>
 static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, cudaStream_t st) {
   if (getenv("DAB_L96_OCC4") && T <= 256 && P == 8) return launch_pb<P, 256, 4>(a, k, T, periodic, st);
   if (T <= 256 && P == 8) return launch_pb<P, 256, 3>(a, k, T, periodic, st);
+  if (T <= 384 && P == 8) return launch_pb<P, 384, 2>(a, k, T, periodic, st);
   return launch_pb<P, 512, 1>(a, k, T, periodic, st);
 }
 
