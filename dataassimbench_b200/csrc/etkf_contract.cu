@@ -10,9 +10,9 @@
 // with R = sigma^2 I (`_calc_default_R`, _dacycler.py:68-72), so Rinv is the scalar 1/sigma^2
 // applied once in the reduction.
 //
-// K3: a CTA walks blocks of 32 observation rows; the k x 32 tile Yb^T is gathered straight
-// from the state (never materialised in HBM), centred in registers, parked in shared memory
-// and contracted with DMMA.8x8x4 (FP64 tensor core): warp w owns the 8-row strip w of C.
+// K3: a CTA walks its rows in blocks of 32; the k x 32 tile Yb^T is gathered straight from the
+// state (never materialised in HBM), centred in registers, parked in shared memory and
+// contracted with DMMA.8x8x4 (FP64 tensor core): warp w owns the 8-row strip w of C.
 // Every CTA writes its partial (C, g) to a workspace; `stats_reduce_kernel` sums the partials
 // in a fixed order (bit-reproducible, no atomics) and applies 1/sigma^2.
 #include "common.cuh"
@@ -25,6 +25,23 @@ constexpr int YLD = RB + 4;      // smem row stride (doubles): (4*j + r) mod 16 
 
 // One analysis's observation rows: up to `n_seg` segments of a CSR store.
 //   seg[s] = {begin (into obs_loc/obs_val), count, first row number}
+// Every CTA owns one contiguous range of rows (rows are ordered by grid location, so a CTA's
+// gathers stay in one neighbourhood of the state) and walks it in blocks of RB rows, software-
+// pipelined: the gather of block b+1 (L2/HBM latency) is in flight while the tensor core
+// contracts block b, and the (location, value) pairs of block b+2 are fetched one block earlier
+// still.  A short last block runs only the k-steps it has rows for.
+__device__ __forceinline__ void fetch_row(const int* __restrict__ obs_loc, const double* __restrict__ obs_val,
+                                          const long long* __restrict__ seg, int n_seg, long long r,
+                                          long long r_end, int& loc, double& val) {
+  loc = -1; val = 0.0;
+  if (r < r_end) {
+    int s = 0;
+    while (s + 1 < n_seg && seg[3 * (s + 1) + 2] <= r) ++s;
+    const long long p = seg[3 * s] + (r - seg[3 * s + 2]);
+    loc = obs_loc[p]; val = obs_val[p];
+  }
+}
+
 template <int K8>
 __global__ void __launch_bounds__(32 * K8)
 contract_kernel(const double* __restrict__ X, long long ld, int k,
@@ -35,8 +52,8 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
   __shared__ double Ys[KP * YLD];     // centred Yb^T tile [member][row]
   __shared__ double psum[K8][RB];     // per-warp partial row sums
   __shared__ double dvec[RB];         // innovation y - ybar (0 for padding rows)
-  __shared__ int s_loc[RB];
-  __shared__ double s_val[RB];
+  __shared__ int s_loc[2][RB];
+  __shared__ double s_val[2][RB];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inv_k = 1.0 / (double)k;
@@ -46,33 +63,37 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
   for (int t = 0; t < K8; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
   double gacc = 0.0;
 
-  const long long n_blocks = (n_rows + RB - 1) / RB;
-  for (long long b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    __syncthreads();                                   // previous block's tile fully consumed
-    if (tid < RB) {
-      const long long r = b * RB + tid;
-      int loc = -1; double val = 0.0;
-      if (r < n_rows) {
-        int s = 0;
-        while (s + 1 < n_seg && seg[3 * (s + 1) + 2] <= r) ++s;
-        const long long p = seg[3 * s] + (r - seg[3 * s + 2]);
-        loc = obs_loc[p]; val = obs_val[p];
-      }
-      s_loc[tid] = loc; s_val[tid] = val;
-    }
-    __syncthreads();
-    // gather: this thread owns row `lane`, members warp, warp+K8, ... (8 of them)
-    const int loc = s_loc[lane];
-    double v[8];
+  // contiguous, balanced row range of this CTA
+  const long long per = n_rows / gridDim.x, extra = n_rows % gridDim.x;
+  const long long r_begin = blockIdx.x * per + (blockIdx.x < extra ? blockIdx.x : extra);
+  const long long r_end = r_begin + per + (blockIdx.x < extra ? 1 : 0);
+  const int n_blocks = (int)((r_end - r_begin + RB - 1) / RB);
+
+  // pipeline prologue: rows of block 0 -> shared, rows of block 1 -> registers, gather of block 0
+  int nloc = -1; double nval = 0.0;          // (tid < RB) the row `tid` of the block after next
+  if (tid < RB) {
+    fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + tid, r_end, nloc, nval);
+    s_loc[0][tid] = nloc; s_val[0][tid] = nval;
+    fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + RB + tid, r_end, nloc, nval);
+  }
+  __syncthreads();
+  double v[8];
+  int loc = s_loc[0][lane];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = warp + i * K8;
+    v[i] = (loc >= 0 && j < k) ? X[(long long)j * ld + loc] : 0.0;
+  }
+
+  for (int b = 0; b < n_blocks; ++b) {
+    const int cur = b & 1;
+    // ---- centre block b (its gather has landed in v) and park it in shared memory
     double ps = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = warp + i * K8;
-      v[i] = (loc >= 0 && j < k) ? X[(long long)j * ld + loc] : 0.0;
-      ps += v[i];
-    }
+    for (int i = 0; i < 8; ++i) ps += v[i];
     psum[warp][lane] = ps;
-    __syncthreads();
+    if (tid < RB) { s_loc[cur ^ 1][tid] = nloc; s_val[cur ^ 1][tid] = nval; }   // rows of block b+1
+    __syncthreads();                                   // also: every warp is done with tile b-1
     double tot = 0.0;
 #pragma unroll
     for (int w = 0; w < K8; ++w) tot += psum[w][lane];
@@ -82,12 +103,22 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
       const int j = warp + i * K8;
       Ys[j * YLD + lane] = (loc >= 0 && j < k) ? v[i] - ybar : 0.0;
     }
-    if (warp == 0) dvec[lane] = (loc >= 0) ? s_val[lane] - ybar : 0.0;
+    if (warp == 0) dvec[lane] = (loc >= 0) ? s_val[cur][lane] - ybar : 0.0;
     __syncthreads();
-    // C strip `warp` += Y'^T Y' over the 32 rows, 4 rows per DMMA
-    const int fm = lane >> 2, fr = lane & 3;
+    // ---- put the next gather (block b+1) and the rows of block b+2 in flight
+    loc = s_loc[cur ^ 1][lane];
 #pragma unroll
-    for (int r0 = 0; r0 < RB; r0 += 4) {
+    for (int i = 0; i < 8; ++i) {
+      const int j = warp + i * K8;
+      v[i] = (loc >= 0 && j < k) ? X[(long long)j * ld + loc] : 0.0;
+    }
+    if (tid < RB) fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + (long long)(b + 2) * RB + tid, r_end, nloc, nval);
+    // ---- C strip `warp` += Y'^T Y' over the rows of block b, 4 rows per DMMA
+    const long long left = r_end - (r_begin + (long long)b * RB);
+    const int rows_here = left < RB ? (int)left : RB;
+    const int fm = lane >> 2, fr = lane & 3;
+#pragma unroll 2
+    for (int r0 = 0; r0 < rows_here; r0 += 4) {
       const double a = Ys[(8 * warp + fm) * YLD + r0 + fr];
 #pragma unroll
       for (int t = 0; t < K8; ++t) {
@@ -108,33 +139,44 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
 #pragma unroll
   for (int t = 0; t < K8; ++t) {
     const int col = 8 * t + 2 * (lane & 3);
-    out[row * KP + col] = c0[t];
-    out[row * KP + col + 1] = c1[t];
+    *reinterpret_cast<double2*>(out + row * KP + col) = make_double2(c0[t], c1[t]);
   }
   if (tid < KP) out[KP * KP + tid] = gacc;
 }
 
 // stats[0 .. k*k) = r_inv * sum_p C_p (row-major k x k), stats[k*k .. k*k+k) = r_inv * sum_p g_p.
-// 8 slices per element, each summing its partials in order; slices combined in order.
-__global__ void __launch_bounds__(256)
+// 16 slices per element, each summing its partials in a fixed order (four interleaved chains so
+// the loads overlap); slices combined in order: bit-reproducible, no atomics.
+__global__ void __launch_bounds__(512)
 stats_reduce_kernel(const double* __restrict__ partial, int n_part, int kp, int k, double r_inv,
                     double* __restrict__ stats) {
-  __shared__ double sl[8][32];
+  constexpr int NS = 16;
+  __shared__ double sl[NS][32];
   const int el = blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5;
   const int n_el = k * k + k;
-  double s = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (el < n_el) {
     const int src = el < k * k ? (el / k) * kp + (el % k) : kp * kp + (el - k * k);
     const long long stride = (long long)kp * kp + kp;
-    for (int p = slice; p < n_part; p += 8) s += partial[(long long)p * stride + src];
+    const double* pp = partial + src;
+    int p = slice;
+    for (; p + 3 * NS < n_part; p += 4 * NS) {
+      s0 += pp[(long long)p * stride];
+      s1 += pp[(long long)(p + NS) * stride];
+      s2 += pp[(long long)(p + 2 * NS) * stride];
+      s3 += pp[(long long)(p + 3 * NS) * stride];
+    }
+    if (p < n_part) s0 += pp[(long long)p * stride];
+    if (p + NS < n_part) s1 += pp[(long long)(p + NS) * stride];
+    if (p + 2 * NS < n_part) s2 += pp[(long long)(p + 2 * NS) * stride];
   }
-  sl[slice][threadIdx.x & 31] = s;
+  sl[slice][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (slice == 0 && el < n_el) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sl[i][threadIdx.x];
+    for (int i = 0; i < NS; ++i) t += sl[i][threadIdx.x];
     stats[el] = t * r_inv;
   }
 }
@@ -169,7 +211,7 @@ cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs
 cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
                                 cudaStream_t st) {
   const int n_el = k * k + k;
-  stats_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats);
+  stats_reduce_kernel<<<(n_el + 31) / 32, 512, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats);
   return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ constexpr int kMaxRanks = 8;
 
 // K1  l96_forecast.cu
 int l96_max_steps_per_launch();
+constexpr int kL96WideCode = 10000;      // forced_T = kL96WideCode + T: 16 points per thread instead of 8
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,

@@ -99,6 +99,25 @@ def test_forecast_linearity_free_property_full_size(H):
     assert rel_err(x_out[:2].cpu().numpy(), ref) < 1e-11
 
 
+@pytest.mark.parametrize("shape", ["10128", "10256", "384", "192"])
+@pytest.mark.parametrize("N,k,steps", [(20000, 3, 20), (4099, 2, 7)])
+def test_forecast_cta_shapes_agree(H, shape, N, k, steps, monkeypatch):
+    """Every CTA shape the autotuner may pick (8 or 16 points per thread, 2-3 or 1 CTA per SM) runs the
+    same per-point arithmetic: identical bits, and the oracle tolerance."""
+    X, _ = make_ensemble(N, k, seed=N, spinup=50)
+    ref = o_l96.rk4_forecast(X, steps, 0.01)
+    x_in = dev(X)
+    st = torch.cuda.current_stream().cuda_stream
+    base = torch.empty_like(x_in)
+    H.l96_forecast(x_in, base, None, N, k, steps, 0.01, 8.0, st)
+    monkeypatch.setenv("DAB_L96_T", shape)
+    out = torch.empty_like(x_in)
+    H.l96_forecast(x_in, out, None, N, k, steps, 0.01, 8.0, st)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), ref) < 1e-11
+    assert torch.equal(out, base)
+
+
 # ------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("N,k,n_y", [(36, 10, 18), (40, 20, 20), (65536, 64, 19661), (1000, 7, 1), (50, 3, 0)])
 def test_gather_bit_exact(H, N, k, n_y):
