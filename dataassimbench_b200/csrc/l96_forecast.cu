@@ -18,11 +18,7 @@
 //   * per RK stage a thread needs 3 neighbour values (2 from the left thread, 1 from the right):
 //     they go through a double-buffered shared-memory edge array, one __syncthreads per stage;
 //   * loads/stores are staged through padded shared memory so HBM sees fully coalesced 8-byte
-//     accesses while each thread ends up with P consecutive points;
-//   * CTAs are persistent (one per resident slot) and walk the (member, tile) list; the next
-//     tile is fetched with cp.async into the second staging buffer while the current one is
-//     integrated, so a tile's load latency (3-5 us per CTA, measured with the per-CTA trace of
-//     tools/l96_trace.py: 11 % of a CTA's life at 8 points per thread, 28 % at 16) is hidden.
+//     accesses while each thread ends up with P consecutive points.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -39,7 +35,7 @@ struct L96Args {
   long long in_lo, in_hi;    // EXT mode: valid slab-coordinate range [in_lo, in_hi) of an input row
   long long n;               // PERIODIC: ring size; EXT: slab length
   long long traj_stride;     // doubles between consecutive trajectory steps
-  int n_steps, halo_l, useful, tiles_per_member, total_tiles;
+  int n_steps, halo_l, useful, tiles_per_member;
   double dt, F;
 };
 
@@ -49,15 +45,13 @@ struct L96Args {
 __device__ long long* g_l96_trace = nullptr;
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int smid() { int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define L96_TRACE(i) do { if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * blockIdx.x + (i)] = gtime(); } while (0)
+#else
+#define L96_TRACE(i) do { } while (0)
 #endif
 
 template <int P>
 __device__ __forceinline__ int phys(int e) { return e + e / P; }   // +1 double per P: conflict-free blocked reads
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
 
 template <int P, bool PERIODIC, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
@@ -65,149 +59,127 @@ l96_rk4_window_kernel(const L96Args a) {
   extern __shared__ __align__(16) double smem[];
   const int T = blockDim.x;
   const int t = threadIdx.x;
-  const int SW = phys<P>(T * P) + 2;                    // one staging buffer (doubles)
   double2* e_last2 = reinterpret_cast<double2*>(smem);  // [2][T] (s_{P-2}, s_{P-1}) of every thread
   double* e_first = smem + 4 * T;                       // [2][T] s_0 of every thread
-  double* stage0 = e_first + 2 * T;                     // [2][SW] load/store staging, double-buffered
+  double* stage = e_first + 2 * T;                      // phys(W) doubles, load/store staging
 
-  // asynchronous, coalesced fetch of one tile into a staging buffer
-  auto issue_load = [&](int tile_id, double* st) {
-    const int member = tile_id / a.tiles_per_member;
-    const int tile = tile_id - member * a.tiles_per_member;
-    const long long g0 = (long long)tile * a.useful - a.halo_l;
-    const double* in_row = a.in + (long long)member * a.in_ld;
+  const int member = blockIdx.x / a.tiles_per_member;
+  const int tile = blockIdx.x - member * a.tiles_per_member;
+  const long long tile_start = (long long)tile * a.useful;   // slab coordinate of first useful point
+  const long long g0 = tile_start - a.halo_l;                // slab coordinate of ext position 0
+  const double* in_row = a.in + (long long)member * a.in_ld;
+  L96_TRACE(0);
+#ifdef DAB_L96_TRACE
+  if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * blockIdx.x + 4] = smid();
+#endif
+
+  // ---- coalesced load into padded shared memory
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int e = t + j * T;
-      long long g = g0 + e;
-      const double* src;
-      if (PERIODIC) {
-        if ((unsigned long long)g >= (unsigned long long)a.n) g = pmod(g, a.n);   // only tiles at the seam
-        src = in_row + g;
-      } else {
-        g = g < a.in_lo ? a.in_lo : (g >= a.in_hi ? a.in_hi - 1 : g);
-        src = in_row + a.in_base + g;
-      }
-      cp_async8(&st[phys<P>(e)], src);
+  for (int j = 0; j < P; ++j) {
+    const int e = t + j * T;
+    long long g = g0 + e;
+    double v;
+    if (PERIODIC) {
+      if ((unsigned long long)g >= (unsigned long long)a.n) g = pmod(g, a.n);   // only tiles at the seam
+      v = in_row[g];
+    } else {
+      g = g < a.in_lo ? a.in_lo : (g >= a.in_hi ? a.in_hi - 1 : g);
+      v = in_row[a.in_base + g];
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+    stage[phys<P>(e)] = v;
+  }
+  __syncthreads();
+  L96_TRACE(1);
 
+  // 17 FP64 instructions per point and step (DADD d, DFMA t, DFMA next stage, DFMA weighted sum;
+  // the last stage needs no next-stage value, plus two DADDs per step for the bases):
+  //   t_j = (y_{i+1} - y_{i-2}) y_{i-1} - y_i           (k_j = t_j + F: F is folded into the bases)
+  //   y_2 = xh + h/2 t_1,  y_3 = xh + h/2 t_2,  y_4 = xd + h t_3,    xh = x + h/2 F,  xd = x + h F
+  //   x'  = xd + h/6 t_1 + h/3 t_2 + h/3 t_3 + h/6 t_4  (= x + h/6 (k_1 + 2 k_2 + 2 k_3 + k_4))
+  double s[P], xh[P], xd[P], acc[P];
   const double dt = a.dt, F = a.F;
   const double h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
   const double h2F = h2 * F, dtF = dt * F;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    s[i] = stage[phys<P>(t * P + i)];
+    xh[i] = s[i] + h2F; xd[i] = s[i] + dtF;
+  }
+
   const int tl = t > 0 ? t - 1 : 0;
   const int tr = t < T - 1 ? t + 1 : T - 1;
 
-  int it = 0;
-  if ((int)blockIdx.x < a.total_tiles) issue_load(blockIdx.x, stage0);
-  for (int tile_id = blockIdx.x; tile_id < a.total_tiles; tile_id += gridDim.x, ++it) {
-#ifdef DAB_L96_TRACE
-    if (g_l96_trace && threadIdx.x == 0) { g_l96_trace[8 * tile_id] = gtime(); g_l96_trace[8 * tile_id + 4] = smid(); }
-#endif
-    double* stage = stage0 + (it & 1) * SW;
-    const int member = tile_id / a.tiles_per_member;
-    const int tile = tile_id - member * a.tiles_per_member;
-    const long long tile_start = (long long)tile * a.useful;   // slab coordinate of first useful point
-    const long long g0 = tile_start - a.halo_l;                // slab coordinate of ext position 0
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                           // tile landed; previous tile's store is done
-#ifdef DAB_L96_TRACE
-    if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * tile_id + 1] = gtime();
-#endif
+  // edges of the stage-1 input (x itself)
+  int buf = 0;
+  e_first[t] = s[0];
+  e_last2[t] = make_double2(s[P - 2], s[P - 1]);
 
-    // 17 FP64 instructions per point and step (DADD d, DFMA t, DFMA next stage, DFMA weighted sum;
-    // the last stage needs no next-stage value, plus two DADDs per step for the bases):
-    //   t_j = (y_{i+1} - y_{i-2}) y_{i-1} - y_i           (k_j = t_j + F: F is folded into the bases)
-    //   y_2 = xh + h/2 t_1,  y_3 = xh + h/2 t_2,  y_4 = xd + h t_3,    xh = x + h/2 F,  xd = x + h F
-    //   x'  = xd + h/6 t_1 + h/3 t_2 + h/3 t_3 + h/6 t_4  (= x + h/6 (k_1 + 2 k_2 + 2 k_3 + k_4))
-    double s[P], xh[P], xd[P], acc[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-      s[i] = stage[phys<P>(t * P + i)];
-      xh[i] = s[i] + h2F; xd[i] = s[i] + dtF;
-    }
-    {                                                          // next tile -> the other staging buffer
-      const int next = tile_id + gridDim.x;
-      if (next < a.total_tiles) issue_load(next, stage0 + ((it + 1) & 1) * SW);
-    }
+  const long long out_lo = tile_start;
+  long long out_hi = tile_start + a.useful;
+  if (out_hi > a.n) out_hi = a.n;
 
-    // edges of the stage-1 input (x itself)
-    int buf = 0;
-    e_first[t] = s[0];
-    e_last2[t] = make_double2(s[P - 2], s[P - 1]);
-
-    const long long out_lo = tile_start;
-    long long out_hi = tile_start + a.useful;
-    if (out_hi > a.n) out_hi = a.n;
-
-    for (int step = 0; step < a.n_steps; ++step) {
+  for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll
-      for (int st = 0; st < 4; ++st) {
-        __syncthreads();
-        const double2 L = e_last2[buf * T + tl];
-        const double R = e_first[buf * T + tr];
-        buf ^= 1;
-        const double ca = (st == 2) ? dt : h2;                 // next-stage coefficient
-        const double cw = (st == 0 || st == 3) ? h6 : h3;      // RK4 weight
-        double kk[P];
-        // edge points first so the next stage's edges can be published early
-        kk[0] = fma((P > 1 ? s[1] : R) - L.x, L.y, -s[0]);
-        if (P > 1) kk[1] = fma((P > 2 ? s[2] : R) - L.y, s[0], -s[1]);
-        if (P > 2) kk[P - 1] = fma(R - s[P - 3], s[P - 2], -s[P - 1]);
-        if (P > 3) kk[P - 2] = fma(s[P - 1] - s[P - 4], s[P - 3], -s[P - 2]);
-        if (st < 3) {
-          const double n0 = fma(ca, kk[0], st == 2 ? xd[0] : xh[0]);
-          const double n2 = fma(ca, kk[P - 2], st == 2 ? xd[P - 2] : xh[P - 2]);
-          const double n1 = fma(ca, kk[P - 1], st == 2 ? xd[P - 1] : xh[P - 1]);
-          e_first[buf * T + t] = n0;
-          e_last2[buf * T + t] = make_double2(n2, n1);
-        } else {
-          const double n0 = fma(cw, kk[0], acc[0]);
-          const double n2 = fma(cw, kk[P - 2], acc[P - 2]);
-          const double n1 = fma(cw, kk[P - 1], acc[P - 1]);
-          e_first[buf * T + t] = n0;
-          e_last2[buf * T + t] = make_double2(n2, n1);
-        }
-#pragma unroll
-        for (int i = 2; i < P - 2; ++i) kk[i] = fma(s[i + 1] - s[i - 2], s[i - 1], -s[i]);
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-          if (st == 0) acc[i] = fma(cw, kk[i], xd[i]);
-          else if (st < 3) acc[i] = fma(cw, kk[i], acc[i]);
-          if (st < 3) s[i] = fma(ca, kk[i], st == 2 ? xd[i] : xh[i]);
-          else { s[i] = fma(cw, kk[i], acc[i]); xh[i] = s[i] + h2F; xd[i] = s[i] + dtF; }
-        }
+    for (int st = 0; st < 4; ++st) {
+      __syncthreads();
+      const double2 L = e_last2[buf * T + tl];
+      const double R = e_first[buf * T + tr];
+      buf ^= 1;
+      const double ca = (st == 2) ? dt : h2;                 // next-stage coefficient
+      const double cw = (st == 0 || st == 3) ? h6 : h3;      // RK4 weight
+      double kk[P];
+      // edge points first so the next stage's edges can be published early
+      kk[0] = fma((P > 1 ? s[1] : R) - L.x, L.y, -s[0]);
+      if (P > 1) kk[1] = fma((P > 2 ? s[2] : R) - L.y, s[0], -s[1]);
+      if (P > 2) kk[P - 1] = fma(R - s[P - 3], s[P - 2], -s[P - 1]);
+      if (P > 3) kk[P - 2] = fma(s[P - 1] - s[P - 4], s[P - 3], -s[P - 2]);
+      if (st < 3) {
+        const double n0 = fma(ca, kk[0], st == 2 ? xd[0] : xh[0]);
+        const double n2 = fma(ca, kk[P - 2], st == 2 ? xd[P - 2] : xh[P - 2]);
+        const double n1 = fma(ca, kk[P - 1], st == 2 ? xd[P - 1] : xh[P - 1]);
+        e_first[buf * T + t] = n0;
+        e_last2[buf * T + t] = make_double2(n2, n1);
+      } else {
+        const double n0 = fma(cw, kk[0], acc[0]);
+        const double n2 = fma(cw, kk[P - 2], acc[P - 2]);
+        const double n1 = fma(cw, kk[P - 1], acc[P - 1]);
+        e_first[buf * T + t] = n0;
+        e_last2[buf * T + t] = make_double2(n2, n1);
       }
-      if (a.traj != nullptr) {
-        double* trow = a.traj + (long long)step * a.traj_stride + (long long)member * a.out_ld;
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-          const long long g = g0 + (long long)t * P + i;
-          if (g >= out_lo && g < out_hi) trow[g] = s[i];
-        }
+      for (int i = 2; i < P - 2; ++i) kk[i] = fma(s[i + 1] - s[i - 2], s[i - 1], -s[i]);
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        if (st == 0) acc[i] = fma(cw, kk[i], xd[i]);
+        else if (st < 3) acc[i] = fma(cw, kk[i], acc[i]);
+        if (st < 3) s[i] = fma(ca, kk[i], st == 2 ? xd[i] : xh[i]);
+        else { s[i] = fma(cw, kk[i], acc[i]); xh[i] = s[i] + h2F; xd[i] = s[i] + dtF; }
       }
     }
-
-    // ---- coalesced store of the useful (still valid) centre of the tile, through the staging
-    //      buffer this tile was loaded into (the other one is receiving the next tile)
-#ifdef DAB_L96_TRACE
-    if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * tile_id + 2] = gtime();
-#endif
+    if (a.traj != nullptr) {
+      double* trow = a.traj + (long long)step * a.traj_stride + (long long)member * a.out_ld;
 #pragma unroll
-    for (int i = 0; i < P; ++i) stage[phys<P>(t * P + i)] = s[i];
-    __syncthreads();
-    double* out_row = a.out + (long long)member * a.out_ld;
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int e = t + j * T;
-      const long long g = g0 + e;
-      if (g >= out_lo && g < out_hi) out_row[g] = stage[phys<P>(e)];
+      for (int i = 0; i < P; ++i) {
+        const long long g = g0 + (long long)t * P + i;
+        if (g >= out_lo && g < out_hi) trow[g] = s[i];
+      }
     }
-#ifdef DAB_L96_TRACE
-    if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * tile_id + 3] = gtime();
-#endif
   }
+
+  // ---- coalesced store of the useful (still valid) centre of the tile
+  __syncthreads();
+  L96_TRACE(2);
+#pragma unroll
+  for (int i = 0; i < P; ++i) stage[phys<P>(t * P + i)] = s[i];
+  __syncthreads();
+  double* out_row = a.out + (long long)member * a.out_ld;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int e = t + j * T;
+    const long long g = g0 + e;
+    if (g >= out_lo && g < out_hi) out_row[g] = stage[phys<P>(e)];
+  }
+  L96_TRACE(3);
 }
 
 #ifdef DAB_L96_TRACE
@@ -223,61 +195,37 @@ namespace dab {
 // 12 points per step must stay a modest fraction of the tile); longer windows are chunked.
 static size_t l96_smem_bytes(int T, int P) {
   const int W = T * P;
-  return (2 * (size_t)(W + W / P + 2) + 6 * (size_t)T) * sizeof(double);   // two staging buffers + edge arrays
+  return ((size_t)(W + W / P) + 6 * (size_t)T) * sizeof(double);
 }
 
 int l96_max_steps_per_launch() { return 32; }
 
-// Persistent grid: one CTA per resident slot (occupancy query, cached per kernel/shape), capped by
-// the tile count.
-struct OccEntry { const void* kern; int T; int occ; };
-
-template <typename Kern>
-static cudaError_t launch_persistent(Kern kern, L96Args a, int k, int T, size_t smem, int sms, cudaStream_t st) {
-  // (kernel, CTA width) -> resident CTAs per SM; the shared-memory opt-in is set on the same occasion
-  static OccEntry cache[64];
-  static int n_cache = 0;
-  int cached_occ = 0;
-  for (int i = 0; i < n_cache; ++i)
-    if (cache[i].kern == (const void*)kern && cache[i].T == T) cached_occ = cache[i].occ;
-  if (cached_occ == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l96_smem_bytes(512, 16));
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
-    if (e != cudaSuccess) return e;
-    cached_occ = occ < 1 ? 1 : occ;
-    if (n_cache < 64) cache[n_cache++] = OccEntry{(const void*)kern, T, cached_occ};
-  }
-  const long long total = (long long)a.tiles_per_member * k;
-  // every SM gets the same number of CTAs: tile t goes to CTA t mod grid, i.e. (CTAs being placed
-  // breadth-first) the tiles are dealt round-robin over the SMs
-  long long grid = (long long)sms * cached_occ;
-  if (grid > total) grid = total;
-  a.total_tiles = (int)total;
-  kern<<<(unsigned)grid, T, smem, st>>>(a);
-  return cudaGetLastError();
-}
-
 template <int P, int MAXT, int MINB>
-static cudaError_t launch_pb(const L96Args& a, int k, int T, bool periodic, int sms, cudaStream_t st) {
+static cudaError_t launch_pb(const L96Args& a, int k, int T, bool periodic, cudaStream_t st) {
   const size_t smem = l96_smem_bytes(T, P);
-  if (periodic) return launch_persistent(l96_rk4_window_kernel<P, true, MAXT, MINB>, a, k, T, smem, sms, st);
-  return launch_persistent(l96_rk4_window_kernel<P, false, MAXT, MINB>, a, k, T, smem, sms, st);
+  dim3 grid((unsigned)((long long)a.tiles_per_member * k));
+  if (periodic) {
+    cudaFuncSetAttribute(l96_rk4_window_kernel<P, true, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    l96_rk4_window_kernel<P, true, MAXT, MINB><<<grid, T, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(l96_rk4_window_kernel<P, false, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    l96_rk4_window_kernel<P, false, MAXT, MINB><<<grid, T, smem, st>>>(a);
+  }
+  return cudaGetLastError();
 }
 
 // CTAs of <= 256 threads use the register-capped build (<= 80 registers: three CTAs per SM, so
 // that one CTA's barrier/exchange bubbles are covered by the other two); wider CTAs the plain one.
 template <int P>
-static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, int sms, cudaStream_t st) {
+static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, cudaStream_t st) {
   if constexpr (P == 8) {
-    if (T <= 256) return launch_pb<P, 256, 3>(a, k, T, periodic, sms, st);
-    if (T <= 384) return launch_pb<P, 384, 2>(a, k, T, periodic, sms, st);
-    return launch_pb<P, 512, 1>(a, k, T, periodic, sms, st);
+    if (T <= 256) return launch_pb<P, 256, 3>(a, k, T, periodic, st);
+    if (T <= 384) return launch_pb<P, 384, 2>(a, k, T, periodic, st);
+    return launch_pb<P, 512, 1>(a, k, T, periodic, st);
   } else if constexpr (P == 16) {
-    return launch_pb<P, 256, 1>(a, k, T, periodic, sms, st);   // 16 points per thread, <= 255 registers
+    return launch_pb<P, 256, 1>(a, k, T, periodic, st);   // 16 points per thread, <= 255 registers
   } else {
-    return launch_pb<P, 512, 1>(a, k, T, periodic, sms, st);
+    return launch_pb<P, 512, 1>(a, k, T, periodic, st);
   }
 }
 
@@ -308,7 +256,7 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
                                 long long traj_stride, int sms, int forced_T, cudaStream_t st) {
   // forced_T >= kL96WideCode selects 16 points per thread (half the exchanges per flop, half the halo
-  // share at the same thread count, one CTA per SM): forced_T = kL96WideCode + CTA width <= 256.
+  // share at the same thread count): forced_T = kL96WideCode + CTA width <= 256.
   if (const char* ev = getenv("DAB_L96_T")) {            // experiment/test knob: force the CTA shape
     const int t = atoi(ev) % kL96WideCode;
     if (t >= 32 && t <= 512 && t % 32 == 0) forced_T = atoi(ev);
@@ -323,10 +271,10 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
   a.in_ld = in_ld; a.out_ld = out_ld; a.in_base = in_base; a.in_lo = in_lo; a.in_hi = in_hi;
   a.n = n; a.traj_stride = traj_stride;
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
-  a.dt = dt; a.F = F; a.total_tiles = 0;
-  if (P == 4) return launch_p<4>(a, k, T, periodic, sms, st);
-  if (P == 16) return launch_p<16>(a, k, T, periodic, sms, st);
-  return launch_p<8>(a, k, T, periodic, sms, st);
+  a.dt = dt; a.F = F;
+  if (P == 4) return launch_p<4>(a, k, T, periodic, st);
+  if (P == 16) return launch_p<16>(a, k, T, periodic, st);
+  return launch_p<8>(a, k, T, periodic, st);
 }
 
 }  // namespace dab
