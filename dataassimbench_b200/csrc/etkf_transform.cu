@@ -37,45 +37,53 @@ transform_kernel(const TransformArgs a) {
     af[ks] = (m < k && j < k) ? a.T[m * k + j] : 0.0;
   }
 
+  // Balanced split: the extended row is cut into 8-column DMMA tiles and every CTA takes the same
+  // number of them (+-1) as ONE contiguous range, walked in chunks of up to TC columns -- no
+  // last-round stragglers (1028 64-column tiles on 592 CTAs used to leave 26 % of the second round idle).
   const long long e_lo = -(long long)a.halo_l;
-  const long long n_cols = a.n_loc + a.halo_l + a.halo_r;
-  const long long n_tiles = (n_cols + TC - 1) / TC;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long e0 = e_lo + tile * TC;
-    __syncthreads();
-    // load tile: Xs[m][i] = Xb_owner[m][src col]; a thread keeps one column i (blockDim % TC == 0)
-    {
-      const int i = tid % TC;
-      const long long e = e0 + i;
-      const double* sp = nullptr;
-      if (e < a.n_loc + a.halo_r) {
-        if (e >= 0 && e < a.n_loc) {
-          sp = a.src[a.rank] + e;                      // interior: own slab
-        } else {                                       // halo: periodic neighbour (peer pointer)
-          const long long gp = pmod(a.n0 + e, a.n_global);
-          const int owner = (int)(gp / a.n_loc);
-          sp = a.src[owner] + (gp - (long long)owner * a.n_loc);
-        }
+  const long long e_hi = a.n_loc + a.halo_r;
+  const long long n8 = (e_hi - e_lo + 7) / 8;
+  const long long t_begin = n8 * blockIdx.x / gridDim.x, t_end = n8 * (blockIdx.x + 1) / gridDim.x;
+  // a thread keeps one column i of a chunk (blockDim % TC == 0) and PASSES rows of it
+  constexpr int ROWS_PER_PASS = (32 * K8) / TC;
+  constexpr int PASSES = KP / ROWS_PER_PASS;
+  const int i = tid % TC, m0 = tid / TC;
+  double v[PASSES];
+  // chunk [t0, t0 + 8) -> registers: Xb_owner[m][src col]; all PASSES loads are independent, so
+  // L2 / NVLink latency is paid once per chunk, not once per row
+  auto fetch = [&](long long t0) {
+    const int tiles_here = (int)(t_end - t0 < TC / 8 ? t_end - t0 : TC / 8);
+    const long long e = e_lo + t0 * 8 + i;
+    const double* sp = nullptr;
+    if (t0 < t_end && i < 8 * tiles_here && e < e_hi) {
+      if (e >= 0 && e < a.n_loc) {
+        sp = a.src[a.rank] + e;                      // interior: own slab
+      } else {                                       // halo: periodic neighbour (peer pointer)
+        const long long gp = pmod(a.n0 + e, a.n_global);
+        const int owner = (int)(gp / a.n_loc);
+        sp = a.src[owner] + (gp - (long long)owner * a.n_loc);
       }
-      // 16 independent loads in flight per thread (trip count is a compile-time constant), so
-      // L2 / NVLink latency is paid once per tile, not once per row.
-      constexpr int ROWS_PER_PASS = (32 * K8) / TC;
-      constexpr int PASSES = KP / ROWS_PER_PASS;
-      const int m0 = tid / TC;
-      double v[PASSES];
-#pragma unroll
-      for (int it = 0; it < PASSES; ++it) {
-        const int m = m0 + it * ROWS_PER_PASS;
-        v[it] = (sp != nullptr && m < k) ? sp[(long long)m * a.src_ld] : 0.0;
-      }
-#pragma unroll
-      for (int it = 0; it < PASSES; ++it) Xs[(m0 + it * ROWS_PER_PASS) * XLD + i] = v[it];
     }
+#pragma unroll
+    for (int it = 0; it < PASSES; ++it) {
+      const int m = m0 + it * ROWS_PER_PASS;
+      v[it] = (sp != nullptr && m < k) ? sp[(long long)m * a.src_ld] : 0.0;
+    }
+  };
+  fetch(t_begin);
+  for (long long t0 = t_begin; t0 < t_end; t0 += TC / 8) {
+    const int tiles_here = (int)(t_end - t0 < TC / 8 ? t_end - t0 : TC / 8);
+    const long long e0 = e_lo + t0 * 8;
+    __syncthreads();                                 // every warp is done with the previous chunk
+#pragma unroll
+    for (int it = 0; it < PASSES; ++it) Xs[(m0 + it * ROWS_PER_PASS) * XLD + i] = v[it];
     __syncthreads();
+    fetch(t0 + TC / 8);                              // next chunk in flight behind this chunk's DMMAs
     double* drow = a.dst + (long long)(8 * warp + fm) * a.dst_ld + a.dst_base;
     const bool row_ok = (8 * warp + fm) < k;
+    const bool vec_ok = ((a.dst_ld | a.dst_base) & 1) == 0 && (reinterpret_cast<unsigned long long>(a.dst) & 15) == 0;
 #pragma unroll 2
-    for (int ti = 0; ti < TC / 8; ++ti) {
+    for (int ti = 0; ti < tiles_here; ++ti) {
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll
       for (int ks = 0; ks < 2 * K8; ++ks) {
@@ -84,8 +92,12 @@ transform_kernel(const TransformArgs a) {
       }
       const long long e = e0 + 8 * ti + 2 * fr;
       if (row_ok) {
-        if (e < a.n_loc + a.halo_r) drow[e] = c0;
-        if (e + 1 < a.n_loc + a.halo_r) drow[e + 1] = c1;
+        if (vec_ok && e + 1 < e_hi && ((e - e_lo) & 1) == 0 && (a.halo_l & 1) == 0) {
+          *reinterpret_cast<double2*>(drow + e) = make_double2(c0, c1);
+        } else {
+          if (e < e_hi) drow[e] = c0;
+          if (e + 1 < e_hi) drow[e + 1] = c1;
+        }
       }
     }
   }
@@ -96,13 +108,19 @@ cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st) {
   const long long n_cols = a.n_loc + a.halo_l + a.halo_r;
   const long long n_tiles = (n_cols + TC - 1) / TC;
   const size_t smem = (size_t)8 * k8 * XLD * sizeof(double);
-  long long g = n_tiles;
-  const long long cap = (long long)sms * (k8 <= 8 ? 4 : 2);
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
+  long long g = n_tiles;                       // small problems: one 64-column chunk per CTA
+  static int occ_cache[17] = {0};              // resident CTAs per SM of transform_kernel<K8>
 #define DAB_TR_CASE(K)                                                                              \
   {                                                                                                 \
-    cudaFuncSetAttribute(transform_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (occ_cache[K] == 0) {                                                                        \
+      cudaFuncSetAttribute(transform_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      int occ = 0;                                                                                  \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transform_kernel<K>, 32 * K, smem);       \
+      occ_cache[K] = occ < 1 ? 1 : occ;                                                             \
+    }                                                                                               \
+    const long long cap = (long long)sms * occ_cache[K];   /* every resident slot gets an equal share */ \
+    if (g > cap) g = cap;                                                                           \
+    if (g < 1) g = 1;                                                                               \
     transform_kernel<K><<<(unsigned)g, 32 * K, smem, st>>>(a);                                      \
   }
   switch (k8) {
