@@ -532,9 +532,12 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
     cudaEvent_t e0, e1;
     DAB_CUDA(h, cudaEventCreate(&e0));
     DAB_CUDA(h, cudaEventCreate(&e1));
-    const int n_cand = 11;
-    const int cand[n_cand] = {128, 192, 256, 320, 384, 512, kL96WideCode + 128, kL96WideCode + 160,
-                              kL96WideCode + 192, kL96WideCode + 224, kL96WideCode + 256};
+    const int n_cand = 17;
+    const int cand[n_cand] = {128, 192, 256, 320, 384, 512,
+                              l96_shape_code(16, 128), l96_shape_code(16, 160), l96_shape_code(16, 192),
+                              l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
+                              l96_shape_code(17, 160), l96_shape_code(17, 192),
+                              l96_shape_code(12, 128), l96_shape_code(12, 160), l96_shape_code(12, 192)};
     const int cand_chunks[3] = {1, 2, 4};
     float best_ms = 1e30f;
     for (int cc = 0; cc < 3; ++cc) {
@@ -542,9 +545,8 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
       if (chunks > 1 && c.first_steps < 2 * chunks) continue;
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
-        const int width = cand[ci] >= kL96WideCode ? 16 * (cand[ci] - kL96WideCode) : 8 * cand[ci];
-        if (width < 12 * longest + 16) continue;
-        if (chunks > 1 && cand[ci] >= kL96WideCode) continue;
+        if (l96_shape_width(cand[ci]) < 12 * longest + 16) continue;
+        if (chunks > 1 && cand[ci] >= 1000) continue;
         float ms = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
           DAB_CUDA(h, cudaEventRecord(e0, h->stream));

@@ -10,7 +10,10 @@ constexpr int kMaxRanks = 8;
 
 // K1  l96_forecast.cu
 int l96_max_steps_per_launch();
-constexpr int kL96WideCode = 10000;      // forced_T = kL96WideCode + T: 16 points per thread instead of 8
+// CTA shape code of the forecast kernel (`forced_T`): T alone = 8 points per thread; 1000 * c + T with
+// c = 12 / 16: 12 / 16 points per thread, c = 17: 16 points per thread, 170-register build (T <= 192).
+constexpr int l96_shape_code(int c, int T) { return 1000 * c + T; }
+constexpr int l96_shape_width(int code) { return code < 1000 ? 8 * code : (code / 1000 == 12 ? 12 : 16) * (code % 1000); }
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,

@@ -216,14 +216,23 @@ static cudaError_t launch_pb(const L96Args& a, int k, int T, bool periodic, cuda
 
 // CTAs of <= 256 threads use the register-capped build (<= 80 registers: three CTAs per SM, so
 // that one CTA's barrier/exchange bubbles are covered by the other two); wider CTAs the plain one.
+// Kernel builds.  8 points per thread: <= 80 registers, 3 (T <= 256) or 2 (T <= 384) CTAs per SM, or
+// the uncapped build for wider CTAs.  16 points per thread (half the exchanges per flop, half the
+// halo share at the same thread count): <= 255 registers (two 128-thread CTAs per SM), or the
+// 170-register build `dense` (three 128-thread or two 192-thread CTAs per SM).  12 points per thread: <= 168
+// registers, two 192-thread CTAs per SM.  The autotuner (engine.cu) measures them per shape.
 template <int P>
-static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, cudaStream_t st) {
+static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, bool dense, cudaStream_t st) {
   if constexpr (P == 8) {
     if (T <= 256) return launch_pb<P, 256, 3>(a, k, T, periodic, st);
     if (T <= 384) return launch_pb<P, 384, 2>(a, k, T, periodic, st);
     return launch_pb<P, 512, 1>(a, k, T, periodic, st);
   } else if constexpr (P == 16) {
-    return launch_pb<P, 256, 1>(a, k, T, periodic, st);   // 16 points per thread, <= 255 registers
+    if (dense && T <= 128) return launch_pb<P, 128, 3>(a, k, T, periodic, st);
+    if (dense && T <= 192) return launch_pb<P, 192, 2>(a, k, T, periodic, st);
+    return launch_pb<P, 256, 1>(a, k, T, periodic, st);
+  } else if constexpr (P == 12) {
+    return launch_pb<P, 192, 2>(a, k, T <= 192 ? T : 192, periodic, st);
   } else {
     return launch_pb<P, 512, 1>(a, k, T, periodic, st);
   }
@@ -255,14 +264,22 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
                                 long long traj_stride, int sms, int forced_T, cudaStream_t st) {
-  // forced_T >= kL96WideCode selects 16 points per thread (half the exchanges per flop, half the halo
-  // share at the same thread count): forced_T = kL96WideCode + CTA width <= 256.
+  // CTA shape code: plain T = 8 points per thread; 1000 * c + T with c = 12 / 16 points per thread,
+  // c = 17: 16 points per thread in the 170-register build (kernels.h: l96_shape_code).
   if (const char* ev = getenv("DAB_L96_T")) {            // experiment/test knob: force the CTA shape
-    const int t = atoi(ev) % kL96WideCode;
+    const int t = atoi(ev) % 1000;
     if (t >= 32 && t <= 512 && t % 32 == 0) forced_T = atoi(ev);
   }
   int P = 8;
-  if (forced_T >= kL96WideCode) { P = 16; forced_T -= kL96WideCode; if (forced_T > 256) forced_T = 256; }
+  bool dense = false;
+  if (forced_T >= 1000) {
+    const int c = forced_T / 1000;
+    forced_T %= 1000;
+    P = c == 12 ? 12 : 16;
+    dense = c == 17;
+    const int tmax = P == 12 ? 192 : (dense ? 192 : 256);
+    if (forced_T > tmax) forced_T = tmax;
+  }
   if (const char* ev = getenv("DAB_L96_P")) { if (atoi(ev) == 4) P = 4; }   // experiment knob
   int T = 256, useful = 0, tiles = 0;
   l96_plan(n, k, n_steps, sms, P, P == 8 ? 88 : 72, forced_T, &T, &useful, &tiles);
@@ -272,9 +289,10 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
   a.n = n; a.traj_stride = traj_stride;
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
   a.dt = dt; a.F = F;
-  if (P == 4) return launch_p<4>(a, k, T, periodic, st);
-  if (P == 16) return launch_p<16>(a, k, T, periodic, st);
-  return launch_p<8>(a, k, T, periodic, st);
+  if (P == 4) return launch_p<4>(a, k, T, periodic, dense, st);
+  if (P == 12) return launch_p<12>(a, k, T, periodic, dense, st);
+  if (P == 16) return launch_p<16>(a, k, T, periodic, dense, st);
+  return launch_p<8>(a, k, T, periodic, dense, st);
 }
 
 }  // namespace dab

@@ -99,7 +99,7 @@ def test_forecast_linearity_free_property_full_size(H):
     assert rel_err(x_out[:2].cpu().numpy(), ref) < 1e-11
 
 
-@pytest.mark.parametrize("shape", ["10128", "10256", "384", "192"])
+@pytest.mark.parametrize("shape", ["16128", "16256", "17128", "12192", "384", "192"])
 @pytest.mark.parametrize("N,k,steps", [(20000, 3, 20), (4099, 2, 7)])
 def test_forecast_cta_shapes_agree(H, shape, N, k, steps, monkeypatch):
     """Every CTA shape the autotuner may pick (8 or 16 points per thread, 2-3 or 1 CTA per SM) runs the

@@ -12,7 +12,7 @@ N, k, S = int(os.environ.get("N", 65536)), int(os.environ.get("K", 64)), int(os.
 x = (8 + torch.randn(k, N, dtype=torch.float64, device="cuda"))
 out = torch.empty_like(x)
 st = torch.cuda.current_stream().cuda_stream
-for shape in os.environ.get("SHAPES", "256,10128,10256,384").split(","):
+for shape in os.environ.get("SHAPES", "256,16128,17128,12192,384").split(","):
     os.environ["DAB_L96_T"] = shape
     buf = torch.zeros(8 * 20000, dtype=torch.int64, device="cuda")
     lib.dab_debug_l96_trace.argtypes = [ctypes.c_void_p]
