@@ -26,12 +26,13 @@
 //   * the new strips go to a double-buffered global scratch (L2-resident, 4 KP^2 doubles) and ONE
 //     cluster barrier (release/acquire) per step publishes them.
 // Accuracy: error of T ~ cond(A) * 1e-17 (measured 1e-14 at cond 1e3, 2e-12 at 7e5).  When the
-// bound s/lambda_min exceeds kNsMaxCond, or the statistics are not finite, the kernel raises a
-// flag in the scratch header and the Jacobi eigensolver (etkf_eig.cu), always enqueued behind
-// it, runs instead (it exits at once when the flag is clear).
+// bound on cond(A') exceeds kNsMaxCond, or the statistics are not finite, the Jacobi eigensolver
+// takes over: for k <= 64 inside this kernel (CTA 0 has exactly its geometry), for k > 64 through
+// a flag in the scratch header that the eigensolver kernel enqueued behind this one checks.
 #include <cmath>
 
 #include "common.cuh"
+#include "etkf_eig_device.cuh"
 #include "kernels.h"
 
 namespace dab {
@@ -110,51 +111,93 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   long long ns_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ns_tick = clock64();
 #endif
 
-  // ---- scale: s = min(|A|_F, |A|_inf) >= lambda_max; non-finite statistics poison |A|_F.
-  // TPR threads per row, interleaved columns (all loads in flight at once, sectors fully used)
+  // ---- deflation and scale.  1 is an eigenvector of A with eigenvalue lambda_min = shift, and T only
+  // needs A^{-1/2} on its orthogonal complement ((I-U) U = 0 and g is orthogonal to 1), so the
+  // iteration runs on  A' = A + delta U  with  delta = tr(C)/(k-1): the known smallest eigenvalue is
+  // moved to the mean of the others.  What is left is the spread of the NONZERO eigenvalues of C,
+  // bounded below by Gershgorin's circles on A' (adding delta/k to every entry cancels the mean
+  // off-diagonal -c_ii/(k-1) that the centring puts there):
+  //   spectrum(A') in [max(shift, min_i(a'_ii - sum_{j != i} |a'_ij|)), min(|A'|_F, |A'|_inf)].
+  // C3's first cycle: cond bound 640 -> 2.5, 8 steps -> 5.  Non-finite statistics poison |A'|_F.
+  // TPR threads per row, interleaved columns (all loads in flight at once, sectors fully used).
+  __shared__ double red_g[KP];
+  double delta_k = 0.0;
   {
     constexpr int TPR = NT / KP, CPT = KP / TPR;
     const int i = tid / TPR, c = tid % TPR;
     double v[CPT];
+    double dg = 0.0;                               // c_ii, in the thread that holds it
 #pragma unroll
     for (int m = 0; m < CPT; ++m) {
       const int j = c + TPR * m;
-      v[m] = (i < k && j < k) ? stats[i * k + j] + (i == j ? shift : 0.0) : 0.0;
+      v[m] = (i < k && j < k) ? stats[i * k + j] : 0.0;
+      if (i == j) dg = v[m];
     }
-    double sq = 0.0, ab = 0.0;
+    if (i % TPR == c) red_sq[i] = dg;
+    __syncthreads();
+    {
+      double tr = 0.0;                             // every warp: same order, same value
 #pragma unroll
-    for (int m = 0; m < CPT; ++m) { sq = fma(v[m], v[m], sq); ab += fabs(v[m]); }
+      for (int m = 0; m < KP / 32; ++m) tr += red_sq[lane + 32 * m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+      delta_k = k > 1 ? tr / ((double)(k - 1) * (double)k) : 0.0;
+      if (!(delta_k >= 0.0)) delta_k = 0.0;        // C is positive semi-definite; NaN is caught below
+    }
+    __syncthreads();
+    double sq = 0.0, ab = 0.0, di = 0.0;
+#pragma unroll
+    for (int m = 0; m < CPT; ++m) {
+      const int j = c + TPR * m;
+      const double a = (i < k && j < k) ? v[m] + delta_k + (i == j ? shift : 0.0) : 0.0;
+      sq = fma(a, a, sq);
+      ab += fabs(a);
+      if (i == j) di = a;
+    }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) {
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
       ab += __shfl_xor_sync(0xffffffffu, ab, o);
+      di += __shfl_xor_sync(0xffffffffu, di, o);
     }
-    if (c == 0) { red_sq[i] = sq; red_abs[i] = ab; }
+    if (c == 0) { red_sq[i] = sq; red_abs[i] = ab; red_g[i] = i < k ? 2.0 * di - ab : 1e300; }
   }
   __syncthreads();
-  double fro2 = 0.0, rmax = 0.0;
+  double fro2 = 0.0, rmax = 0.0, gmin = 1e300;
   {
     // every warp reduces the KP row values redundantly: fixed order, identical in every thread
-    double sq = 0.0, ab = 0.0;
+    double sq = 0.0, ab = 0.0, gm = 1e300;
 #pragma unroll
     for (int m = 0; m < KP / 32; ++m) {
       sq += red_sq[lane + 32 * m];
       const double a = red_abs[lane + 32 * m];
       ab = a > ab ? a : ab;
+      const double g_ = red_g[lane + 32 * m];
+      gm = g_ < gm ? g_ : gm;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const double a = __shfl_xor_sync(0xffffffffu, ab, o);
       ab = a > ab ? a : ab;
+      const double g_ = __shfl_xor_sync(0xffffffffu, gm, o);
+      gm = g_ < gm ? g_ : gm;
     }
-    fro2 = sq; rmax = ab;
+    fro2 = sq; rmax = ab; gmin = gm;
   }
   const double fro = sqrt(fro2);
   const double s = fro < rmax ? fro : rmax;
-  const bool ok = (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * shift);
+  const double lower = gmin > shift ? gmin : shift;          // A' >= A >= shift I (delta >= 0)
+  const bool ok = (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * lower);
   if (!ok) {                                     // uniform over the cluster: same inputs, same code
-    if (rank == 0 && tid == 0) flags[0] = 1;
+    if (KP == 64) {                              // k <= 64: CTA 0 IS the Jacobi eigensolver's CTA (8 warps, 64 columns)
+      if (rank == 0) {
+        if (tid == 0) flags[0] = 0;
+        eig_block_body<8>(stats, k, 64, rho, Tout, nullptr, info_out, 0, sm);
+      }
+    } else if (rank == 0 && tid == 0) {
+      flags[0] = 1;                              // k > 64: the eigensolver kernel enqueued behind this one runs
+    }
     return;
   }
   const double inv_s = 1.0 / s;
@@ -167,7 +210,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
       const int r = e / KP, j = e - r * KP, i = R0 + r;
       const double z = (i == j) ? 1.0 : 0.0;
       double y = z;
-      if (i < k && j < k) y = (stats[i * k + j] + (i == j ? shift : 0.0)) * inv_s;   // Y0 := (A/s)^T = A/s up to the rounding asymmetry of C
+      if (i < k && j < k) y = (stats[i * k + j] + delta_k + (i == j ? shift : 0.0)) * inv_s;   // Y0 := A'/s (its transpose, up to the rounding asymmetry of C)
       Zs[r * LDS + j] = z; Yts[r * LDS + j] = y;
       Zg[i * KP + j] = z; Ytg[i * KP + j] = y;
     }
@@ -175,7 +218,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   cluster_sync_all();
   NS_TICK(0);
 
-  double l = sqrt(shift * inv_s) * (1.0 - 1e-6);
+  double l = sqrt(lower * inv_s) * (1.0 - 1e-6);
   int par = 0, iters = 0;
   for (; iters < kNsMaxIter; ++iters) {
     const double al2 = 3.0 / (1.0 + l + l * l);
@@ -307,7 +350,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
     NS_TICK(5);
     par ^= 1;
     l = 0.5 * al * l * (3.0 - al2 * l * l);
-    if (1.0 - l < 1e-13) { ++iters; break; }
+    if (1.0 - l < 1e-12) { ++iters; break; }
   }
 
   // ---- T = U + (I-U)(wa 1^T + Wa),  Wa = sqrt((k-1)/s) Z,  wa = Z (Z g) / s; rows R of T
@@ -406,6 +449,7 @@ cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, doub
   size_t strips = sizeof(double) * 4 * C::ROWS * C::LDS;
   size_t fin = sizeof(double) * ((size_t)KP * C::LDF + 4 * KP + C::ROWS + 8);
   size_t smem = strips > fin ? strips : fin;
+  if (KP == 64 && smem < eig_smem_bytes(64)) smem = eig_smem_bytes(64);   // in-kernel Jacobi fallback
   auto kern = ns_transform_kernel<KP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
