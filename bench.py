@@ -75,6 +75,15 @@ def make_workload(name, seed=42):
     return w
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------ CPU oracle
 _POOL = None
 
@@ -215,7 +224,7 @@ def run_reference(args):
         "e2e": {"value": cps, "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_c2_batched(H, B=4096, n_cycles=50):
@@ -429,7 +438,7 @@ def run_product(args):
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "c2_batched": c2,
         "clocks": sampler.summary(t_wall0, t_wall1),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -444,6 +453,13 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU oracle time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # line when the box sets NCCL_DEBUG): point fd 1 at stderr for the run and give the real stdout
+    # only to the final print.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

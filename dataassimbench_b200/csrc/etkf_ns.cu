@@ -4,13 +4,17 @@
 //   Pa = pinv(A),  Wa = sqrtm((k-1) Pa),  wa = Pa g,   A = (k-1)/rho I + Y'^T R^-1 Y',
 // folded into  T = U + (I-U)(wa 1^T + Wa).  Both matrix functions are  A^{-1/2}:
 //   Wa = sqrt(k-1) A^{-1/2},   wa = A^{-1/2} (A^{-1/2} g).
-// A is symmetric positive definite with lambda_min(A) = (k-1)/rho EXACTLY (Y' is centred, so
-// C 1 = 0) and lambda_max(A) <= min(|A|_F, |A|_inf) =: s.  With the spectrum of A/s inside a
+// A is symmetric positive definite and 1 is an eigenvector with the SMALLEST eigenvalue,
+// (k-1)/rho exactly (Y' is centred, so C 1 = 0).  T never needs that direction ((I-U) U = 0, g is
+// orthogonal to 1), so it is deflated: A' = A + delta U moves it to the mean of the other
+// eigenvalues, and the spectrum of A' is bracketed by Gershgorin's circles below and by
+// min(|A'|_F, |A'|_inf) =: s above (see the kernel prologue).  With the spectrum of A'/s inside a
 // KNOWN interval [l0^2, 1], the coupled Newton-Schulz iteration (Higham, Functions of Matrices,
 // eq. 6.35 -- the numerically stable ordering Y <- Y T, Z <- T Z) with the optimal interval
 // scaling of Chen & Chow (2014) converges in a number of steps that is known in advance:
-//   M = Z Y,  T = (alpha/2)(3 I - alpha^2 M),  Y <- Y T,  Z <- T Z,   Z -> (A/s)^{-1/2}
-//   alpha^2 = 3/(1 + l + l^2),  l <- alpha l (3 - alpha^2 l^2)/2      (9 steps at cond 1e3)
+//   M = Z Y,  T = (alpha/2)(3 I - alpha^2 M),  Y <- Y T,  Z <- T Z,   Z -> (A'/s)^{-1/2}
+//   alpha^2 = 3/(1 + l + l^2),  l <- alpha l (3 - alpha^2 l^2)/2
+//   (4-5 steps on the bench workloads; 9 at cond 1e3, 12 at cond 3e6)
 // Everything is k x k x k GEMM work, so -- unlike Jacobi, whose rotation chain is serial -- it
 // spreads over a thread-block cluster:
 //   * a cluster of 8 CTAs; CTA r owns rows R = [ROWS r, ROWS (r+1)) of Z and of Y^T (= columns

@@ -2,6 +2,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches_r01.csv profiles/launches_r01_summary.md
   python tools/ncu_summary.py kernel gpurun_out/prof_forecast_r01.ncu-rep profiles/forecast_r01_ncu.md
+  python tools/ncu_summary.py kernel gpurun_out/prof_analysis_r01.ncu-rep profiles/ns_r01_ncu.md ns_transform
 """
 import collections
 import csv
@@ -15,7 +16,7 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
-        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'dram__bytes_read.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_active.avg', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'dram__bytes_read.sum',
         'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 
@@ -42,17 +43,22 @@ def launches(src, dst):
             f.write('| `%s` | %s | %s | %d | %.1f | %.3f |\n' % (name[:80], blk, grd, v[0], v[1] / v[0], v[1] / tot))
 
 
-def kernel(src, dst):
-    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+def kernel(src, dst, name_filter=None):
+    flt = ['-k', 'regex:' + name_filter] if name_filter else []
+    raw = subprocess.run(['ncu', '-i', src] + flt + ['--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     got = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-    srcp = subprocess.run(['ncu', '-i', src, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    srcp = subprocess.run(['ncu', '-i', src] + flt + ['--page', 'source', '--csv'], capture_output=True, text=True).stdout
     srows = list(csv.reader(srcp.splitlines()))
     name = srows[0][1]
     sh = srows[1]
     si = {h: i for i, h in enumerate(sh)}
-    data = srows[2:]
+    data = []
+    for r in srows[2:]:                     # first kernel section only
+        if len(r) < len(sh) or r[0] == 'Kernel Name':
+            break
+        data.append(r)
     tot = sum(int(r[si['# Samples']]) for r in data) or 1
     stalls = [h for h in sh if h.startswith('stall_') and 'Not Issued' not in h]
     agg = sorted(((sum(int(r[si[s]]) for r in data) / tot, s) for s in stalls), reverse=True)
@@ -82,5 +88,5 @@ if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3])
     else:
-        t = kernel(sys.argv[2], sys.argv[3])
+        t = kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
         print(json.dumps({'dram_bytes_per_launch': t}))
