@@ -64,6 +64,7 @@ _SIGNATURES = {
     "dab_cycler_get_state": (C.c_int, [_P, _P, C.c_int]),
     "dab_cycler_run": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "dab_cycler_stats": (C.c_int, [_P, C.c_int]),
+    "dab_cycler_stats_exchange": (C.c_int, [_P]),
     "dab_cycler_stats_ptr": (_P, [_P]),
     "dab_cycler_update": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_export": (C.c_int, [_P, C.c_int, _P]),
@@ -190,6 +191,10 @@ class Handle:
 
     def cycler_stats(self, cycle):
         self._check(self._lib.dab_cycler_stats(self._h, cycle))
+
+    def cycler_stats_exchange(self):
+        """True when dab_cycler_stats sums the ranks' statistics itself (device-side exchange over peer memory)."""
+        return bool(self._lib.dab_cycler_stats_exchange(self._h))
 
     def cycler_stats_ptr(self):
         return self._lib.dab_cycler_stats_ptr(self._h)

@@ -49,11 +49,25 @@ struct Cycler {
   int l96_T = 0;                           // autotuned CTA width of the forecast kernel (0 = heuristic)
   int l96_chunks = 1;                      // autotuned number of launches one window is split into
   DevBuf chunk_ext[2];                     // extended-layout scratch between the chunks of a window
-  const double* peer[kMaxRanks][2];        // peer-mapped Xb buffers
-  bool peer_open[kMaxRanks][2];
+  const double* peer[kMaxRanks][3];        // peer-mapped buffers: Xb[0], Xb[1], statistics exchange
+  bool peer_open[kMaxRanks][3];
+  // statistics exchange over peer memory (world > 1): [2 parities][kMaxRanks] flags (256 bytes), then
+  // [2 parities][world][k*k+k] slots; rank r writes slot r of every rank (stats_reduce_kernel)
+  DevBuf xchg, xchg_ctr;
+  unsigned long long xchg_seq = 0;
   cudaEvent_t ev_xa[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool copied_pending[2] = {false, false};
 };
+
+constexpr size_t kXchgHeader = 256;       // 2 parities x kMaxRanks 64-bit flags, padded
+
+// the device-side statistics exchange needs every peer's exchange buffer (IPC import or set_peer)
+static bool stats_exchange_ready(const Cycler& c) {
+  if (c.cfg.world <= 1 || c.xchg.p == nullptr) return false;
+  for (int r = 0; r < c.cfg.world; ++r)
+    if (r != c.cfg.rank && c.peer[r][2] == nullptr) return false;
+  return true;
+}
 
 }  // namespace
 
@@ -115,7 +129,7 @@ static int fail(dab_handle* h, int code, const char* fmt, ...) {
 static void cycler_close_peers(dab_handle* h) {
   Cycler& c = h->cyc;
   for (int r = 0; r < kMaxRanks; ++r)
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < 3; ++w) {
       if (c.peer_open[r][w]) { cudaIpcCloseMemHandle(const_cast<double*>(c.peer[r][w])); c.peer_open[r][w] = false; }
       c.peer[r][w] = nullptr;
     }
@@ -139,6 +153,7 @@ static void cycler_free(dab_handle* h) {
   c.xb_bytes = 0;
   c.obs_loc.release(); c.obs_val.release(); c.seg.release(); c.partial.release();
   c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
+  c.xchg.release(); c.xchg_ctr.release();
   c.ready = false;
 }
 
@@ -319,7 +334,7 @@ static int stats_from_arrays(dab_handle* h, const double* X, const double* y, co
   DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
   DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
                               h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, st));
-  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, 1.0 / (sd * sd), stats, st));
+  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, 1.0 / (sd * sd), stats, nullptr, st));
   h->launches += (n_y > 0 ? 1 : 0) + 2;
   return 0;
 }
@@ -520,6 +535,13 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   DAB_CUDA(h, c.T.reserve(sizeof(double) * (size_t)k * k));
   DAB_CUDA(h, c.lam.reserve(sizeof(double) * (size_t)k));
   DAB_CUDA(h, c.info.reserve(sizeof(int) * 4));
+  if (cfg->world > 1) {
+    DAB_CUDA(h, c.xchg.reserve(kXchgHeader + sizeof(double) * 2 * (size_t)cfg->world * ((size_t)k * k + k)));
+    DAB_CUDA(h, cudaMemsetAsync(c.xchg.p, 0, c.xchg.bytes, h->stream));
+    DAB_CUDA(h, c.xchg_ctr.reserve(sizeof(unsigned int) * 4));
+    DAB_CUDA(h, cudaMemsetAsync(c.xchg_ctr.p, 0, c.xchg_ctr.bytes, h->stream));
+  }
+  c.xchg_seq = 0;
   DAB_CUDA(h, cudaStreamSynchronize(h->stream));               // host vectors go out of scope
   // ---- measure, don't guess: pick the forecast kernel's CTA width for this shape with CUDA events
   c.l96_T = 0;
@@ -609,12 +631,36 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
                               c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
                               c.partial.as<double>(), grid, h->stream));
   prof_mark(h, PROF_CONTRACT);
-  DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k,
-                                  1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd),
-                                  c.stats.as<double>(), h->stream));
+  const double r_inv = 1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd);
+  if (stats_exchange_ready(c)) {
+    // reduction fused with the all-gather of the ranks' statistics over peer memory, then the
+    // rank-ordered sum (replaces reduce + NCCL all-reduce; see stats_reduce_kernel)
+    const int G = c.cfg.world, me = c.cfg.rank;
+    const size_t len = (size_t)k * k + k;
+    const unsigned long long seq = ++c.xchg_seq;
+    const int par = (int)(seq & 1);
+    StatsPush push{};
+    push.world = G; push.seq = seq; push.done_ctr = c.xchg_ctr.as<unsigned int>();
+    for (int g = 0; g < G; ++g) {
+      char* base = g == me ? c.xchg.as<char>() : reinterpret_cast<char*>(const_cast<double*>(c.peer[g][2]));
+      push.flag[g] = reinterpret_cast<unsigned long long*>(base) + par * kMaxRanks + me;
+      push.slot[g] = reinterpret_cast<double*>(base + kXchgHeader) + ((size_t)par * G + me) * len;
+    }
+    DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k, r_inv, nullptr, &push, h->stream));
+    DAB_CUDA(h, stats_gather_launch(c.xchg.as<unsigned long long>() + par * kMaxRanks, seq,
+                                    reinterpret_cast<const double*>(c.xchg.as<char>() + kXchgHeader) + (size_t)par * G * len,
+                                    k, G, c.stats.as<double>(), h->stream));
+    h->launches += 1;
+  } else {
+    DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k, r_inv, c.stats.as<double>(), nullptr, h->stream));
+  }
   prof_mark(h, PROF_REDUCE);
   h->launches += 2;
   return 0;
+}
+
+int dab_cycler_stats_exchange(dab_handle* h) {
+  return (h && h->cyc.ready && stats_exchange_ready(h->cyc)) ? 1 : 0;
 }
 
 double* dab_cycler_stats_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.stats.as<double>() : nullptr; }
@@ -734,17 +780,18 @@ int dab_cycler_run(dab_handle* h, int c0, int c1, double* out_analysis, double* 
 }
 
 int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out) {
-  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_out != nullptr && (which == 0 || which == 1));
+  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_out != nullptr && which >= 0 && which <= 2);
+  DAB_ARG(h, which < 2 || h->cyc.xchg.p != nullptr);
   static_assert(sizeof(cudaIpcMemHandle_t) == DAB_IPC_HANDLE_BYTES, "IPC handle size");
   DAB_CUDA(h, cudaSetDevice(h->device));
   cudaIpcMemHandle_t mh;
-  DAB_CUDA(h, cudaIpcGetMemHandle(&mh, h->cyc.xb[which]));
+  DAB_CUDA(h, cudaIpcGetMemHandle(&mh, which < 2 ? static_cast<void*>(h->cyc.xb[which]) : h->cyc.xchg.p));
   memcpy(handle_out, &mh, sizeof(mh));
   return 0;
 }
 
 int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* handle_in) {
-  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_in != nullptr && (which == 0 || which == 1));
+  DAB_ARG(h, h != nullptr && h->cyc.ready && handle_in != nullptr && which >= 0 && which <= 2);
   DAB_ARG(h, peer_rank >= 0 && peer_rank < h->cyc.cfg.world && peer_rank != h->cyc.cfg.rank);
   DAB_CUDA(h, cudaSetDevice(h->device));
   cudaIpcMemHandle_t mh;
@@ -757,12 +804,12 @@ int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* h
 }
 
 double* dab_cycler_buffer_ptr(dab_handle* h, int which) {
-  if (!h || !h->cyc.ready || (which != 0 && which != 1)) return nullptr;
-  return h->cyc.xb[which];
+  if (!h || !h->cyc.ready || which < 0 || which > 2) return nullptr;
+  return which < 2 ? h->cyc.xb[which] : h->cyc.xchg.as<double>();
 }
 
 int dab_cycler_set_peer(dab_handle* h, int peer_rank, int which, const double* ptr) {
-  DAB_ARG(h, h != nullptr && h->cyc.ready && ptr != nullptr && (which == 0 || which == 1));
+  DAB_ARG(h, h != nullptr && h->cyc.ready && ptr != nullptr && which >= 0 && which <= 2);
   DAB_ARG(h, peer_rank >= 0 && peer_rank < h->cyc.cfg.world && peer_rank != h->cyc.cfg.rank);
   Cycler& c = h->cyc;
   if (c.peer_open[peer_rank][which]) return fail(h, -1, "peer %d buffer %d already imported through IPC", peer_rank, which);

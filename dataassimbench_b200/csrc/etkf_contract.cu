@@ -147,9 +147,16 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
 // stats[0 .. k*k) = r_inv * sum_p C_p (row-major k x k), stats[k*k .. k*k+k) = r_inv * sum_p g_p.
 // 16 slices per element, each summing its partials in a fixed order (four interleaved chains so
 // the loads overlap); slices combined in order: bit-reproducible, no atomics.
+//
+// Grid-sharded runs (push.world > 1): the k*k+k statistics of all ranks have to be summed.  Instead
+// of an NCCL all-reduce behind this kernel, the reduction is fused with an all-gather over peer
+// memory: every rank stores its reduced values straight into slot `rank` of EVERY rank's exchange
+// buffer (P2P stores over NVLink, 256 contiguous bytes per CTA and peer), and the last CTA to
+// finish raises this rank's sequence flag on every rank.  `stats_gather_kernel` then waits for the
+// flags of all ranks and adds the slots in rank order -- the same bits on every rank.
 __global__ void __launch_bounds__(512)
 stats_reduce_kernel(const double* __restrict__ partial, int n_part, int kp, int k, double r_inv,
-                    double* __restrict__ stats) {
+                    double* __restrict__ stats, const StatsPush push) {
   constexpr int NS = 16;
   __shared__ double sl[NS][32];
   const int el = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -177,7 +184,53 @@ stats_reduce_kernel(const double* __restrict__ partial, int n_part, int kp, int 
     double t = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) t += sl[i][threadIdx.x];
-    stats[el] = t * r_inv;
+    t *= r_inv;
+    if (push.world <= 1) {
+      stats[el] = t;
+    } else {
+      for (int g = 0; g < push.world; ++g) push.slot[g][el] = t;
+      __threadfence_system();
+    }
+  }
+  if (push.world > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(push.done_ctr, 1u);
+      if (prev == gridDim.x - 1) {               // every CTA of this rank has pushed (and fenced)
+        *push.done_ctr = 0;
+        __threadfence_system();
+        for (int g = 0; g < push.world; ++g) *reinterpret_cast<volatile unsigned long long*>(push.flag[g]) = push.seq;
+      }
+    }
+  }
+}
+
+// Waits until every rank's flag has reached `seq` (P2P stores, see above), then
+// stats = sum over ranks of their slots, in rank order.  A peer that never arrives is a lost
+// process: after 10 s the kernel traps instead of hanging the GPU.
+__global__ void __launch_bounds__(256)
+stats_gather_kernel(const unsigned long long* flags, unsigned long long seq, const double* slots,
+                    int n_el, int world, double* __restrict__ stats) {
+  if (threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int g = 0; g < world; ++g) {
+      const volatile unsigned long long* f = flags + g;
+      while (*f < seq) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) __trap();
+        __nanosleep(100);
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int el = blockIdx.x * blockDim.x + threadIdx.x;
+  if (el < n_el) {
+    double s = 0.0;
+    for (int g = 0; g < world; ++g) s += __ldcg(slots + (long long)g * n_el + el);
+    stats[el] = s;
   }
 }
 
@@ -209,9 +262,19 @@ cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs
 }
 
 cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
-                                cudaStream_t st) {
+                                const StatsPush* push, cudaStream_t st) {
   const int n_el = k * k + k;
-  stats_reduce_kernel<<<(n_el + 31) / 32, 512, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats);
+  StatsPush none{};
+  none.world = 1;
+  stats_reduce_kernel<<<(n_el + 31) / 32, 512, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats,
+                                                         push ? *push : none);
+  return cudaGetLastError();
+}
+
+cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,
+                                int k, int world, double* stats, cudaStream_t st) {
+  const int n_el = k * k + k;
+  stats_gather_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(flags, seq, slots, n_el, world, stats);
   return cudaGetLastError();
 }
 

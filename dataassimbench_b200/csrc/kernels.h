@@ -27,8 +27,19 @@ size_t contract_partial_doubles(int k, int n_cta);
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
                             const double* obs_val, const long long* seg, int n_seg,
                             long long n_rows, double* partial, int grid, cudaStream_t st);
+// Multi-rank statistics exchange fused into the reduction (etkf_contract.cu): where this rank's
+// reduced k*k+k values go on every rank, and the flags that announce them.
+struct StatsPush {
+  double* slot[kMaxRanks];               // slot `rank` of every rank's exchange buffer (this exchange's parity)
+  unsigned long long* flag[kMaxRanks];   // flag `rank` on every rank (same parity)
+  unsigned long long seq;                // exchange number, monotonic
+  int world;                             // <= 1: no exchange, results go to `stats`
+  unsigned int* done_ctr;                // local, zero: CTAs of the launch that have pushed
+};
 cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
-                                cudaStream_t st);
+                                const StatsPush* push /* nullable */, cudaStream_t st);
+cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,
+                                int k, int world, double* stats, cudaStream_t st);
 cudaError_t gather_launch(const double* X, long long ld, int k, const long long* idx,
                           const unsigned char* mask, long long n_y, double* Yb, cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,

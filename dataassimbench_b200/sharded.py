@@ -3,12 +3,14 @@
 The periodic Lorenz-96 grid is cut into `world` contiguous slabs.  Per cycle a
 rank runs
     K3  gather + contraction over the observations it owns        -> partial (C, g)
-        ONE all-reduce of k*k+k doubles (NCCL via torch.distributed)
-    K4  eigensolver (replicated, bit-identical on every rank)
+        ONE exchange of k*k+k doubles: the reduction kernel stores them into every rank's exchange
+        buffer over NVLink and a small kernel adds the slots in rank order (device-side, no host
+        involvement; DAB_STATS_EXCHANGE=nccl selects an NCCL all-reduce via torch.distributed instead)
+    K4  transform matrix (replicated, bit-identical on every rank)
     K5  transform of its slab AND of the halo columns it needs, the latter read from the
         neighbours' background through CUDA-IPC peer pointers (NVLink P2P loads)
     K1  RK4 window on slab + halo, no communication.
-The all-reduce is the only synchronisation point: it also orders the peer reads of K5 after the
+The exchange is the only synchronisation point: it also orders the peer reads of K5 after the
 neighbours' forecasts (two alternating background buffers make that race-free).
 
 This module holds the host logic only (partitioning, plumbing); it is testable on CPU with gloo
@@ -79,16 +81,21 @@ class ShardedCycler:
         if world > 1:
             import torch.distributed as dist
             self.dist = dist
-            handles = [self.H.cycler_ipc_export(0), self.H.cycler_ipc_export(1)]
+            import os
+            n_bufs = 2 if os.environ.get("DAB_STATS_EXCHANGE", "p2p") == "nccl" else 3
+            handles = [self.H.cycler_ipc_export(w_) for w_ in range(n_bufs)]
             gathered = [None] * world
             dist.all_gather_object(gathered, handles)
             for r in range(world):
                 if r != rank:
-                    self.H.cycler_ipc_import(r, 0, gathered[r][0])
-                    self.H.cycler_ipc_import(r, 1, gathered[r][1])
+                    for w_ in range(n_bufs):
+                        self.H.cycler_ipc_import(r, w_, gathered[r][w_])
             self.stats = torch.as_tensor(_DevArray(self.H.cycler_stats_ptr(), self.k * self.k + self.k),
                                          device="cuda")
             dist.barrier()
+        # statistics summed on the device (P2P all-gather fused into the reduction kernel) unless
+        # DAB_STATS_EXCHANGE=nccl asks for the torch.distributed all-reduce
+        self.device_exchange = world > 1 and self.H.cycler_stats_exchange()
         self.reset()
 
     def config(self, n_cycles):
@@ -110,7 +117,7 @@ class ShardedCycler:
         with torch.cuda.stream(self.stream):
             for c in range(c0, c1):
                 self.H.cycler_stats(c)
-                if self.world > 1:
+                if self.world > 1 and not self.device_exchange:
                     self.dist.all_reduce(self.stats)
                 out = None if out_analysis_dev is None else out_analysis_dev[c - c0]
                 self.H.cycler_update(c, out)

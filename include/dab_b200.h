@@ -136,12 +136,18 @@ DAB_API int dab_cycler_get_state(dab_handle* h, double* x, int is_host);
  * device->host overlapped with the next cycle's compute.  out_traj nullable DEVICE
  * [c1-c0][n_steps][k][N]: forecast steps 1..n_steps of every cycle (return_forecast=True). */
 DAB_API int dab_cycler_run(dab_handle* h, int c0, int c1, double* out_analysis, double* out_traj);
-/* Rank-parallel phases (world >= 1): stats -> [caller all-reduces dab_cycler_stats_ptr] -> update */
+/* Rank-parallel phases (world >= 1): stats -> update.  The k*k+k statistics of the ranks must be
+ * summed in between.  When every peer's exchange buffer (which = 2 below) is registered, that sum
+ * happens ON THE DEVICE inside dab_cycler_stats -- each rank's reduction kernel stores its values
+ * into all ranks' exchange buffers over NVLink and a small kernel adds them in rank order -- and
+ * dab_cycler_stats_exchange() returns 1.  Otherwise (returns 0) the caller all-reduces
+ * dab_cycler_stats_ptr itself (e.g. NCCL through torch.distributed) between the two calls. */
 DAB_API int dab_cycler_stats(dab_handle* h, int cycle);
+DAB_API int dab_cycler_stats_exchange(dab_handle* h);
 DAB_API double* dab_cycler_stats_ptr(dab_handle* h);            /* dev, k*k+k doubles */
 DAB_API int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev /* nullable [k][N/world] */);
-/* Peer plumbing for the fused halo exchange (CUDA IPC, one process per GPU):
- * which = 0/1 selects the two background (Xb) buffers. */
+/* Peer plumbing for the fused halo exchange and the statistics exchange (CUDA IPC, one process per
+ * GPU): which = 0/1 selects the two background (Xb) buffers, which = 2 the statistics exchange buffer. */
 DAB_API int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out /* 64 bytes */);
 DAB_API int dab_cycler_ipc_import(dab_handle* h, int peer_rank, int which, const void* handle_in);
 /* Same-process alternative (several handles in one process, e.g. one per peer-enabled GPU, or

@@ -1,8 +1,11 @@
-"""Grid-sharded cycling on ONE GPU: `world` handles act as the ranks, their kernels run one after
-the other on the same device (no rank ever waits on another inside a kernel), the all-reduce is a
-plain sum of the ranks' statistics, and peer pointers are registered directly.  This exercises
-everything the multi-GPU path adds: observation partition by owner, the K5 halo exchange through
-peer pointers, and the extended-layout forecast on a slab."""
+"""Grid-sharded cycling on ONE GPU: `world` handles act as the ranks, each with its own stream on
+the same device, and peer pointers are registered directly.  This exercises everything the
+multi-GPU path adds: observation partition by owner, the K5 halo exchange through peer pointers,
+the extended-layout forecast on a slab, and both ways of summing the ranks' statistics:
+`exchange="device"` -- the reduction kernels store into every rank's exchange buffer and a small
+kernel waits for all ranks' flags and adds the slots (what real multi-GPU runs do);
+`exchange="host"` -- the caller sums `dab_cycler_stats_ptr` between stats and update (the NCCL
+all-reduce's stand-in)."""
 import numpy as np
 import pytest
 
@@ -14,7 +17,7 @@ from test_gpu_kernels import cycler_case, run_gpu_cycler, rel_err
 from oracle import windows as o_win
 
 
-def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world):
+def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchange="host"):
     S, dt = case['S'], case['dt']
     times = o_win.get_all_times(case['start'], case['window'], n_cycles)
     padded = np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, case['obs_times'], case['window'])))
@@ -33,8 +36,9 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world):
     for r in range(world):
         for p in range(world):
             if p != r:
-                for which in (0, 1):
+                for which in ((0, 1, 2) if exchange == "device" else (0, 1)):
                     hs[r].cycler_set_peer(p, which, hs[p].cycler_buffer_ptr(which))
+    assert all(h.cycler_stats_exchange() == (exchange == "device") for h in hs)
 
     class Dev:
         def __init__(self, ptr, n):
@@ -45,12 +49,13 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world):
     for c in range(n_cycles):
         for h in hs:
             h.cycler_stats(c)
-        for h in hs:
-            h.sync()
-        total = torch.stack(stats).sum(dim=0)             # the all-reduce
-        for s in stats:
-            s.copy_(total)
-        torch.cuda.synchronize()
+        if exchange == "host":
+            for h in hs:
+                h.sync()
+            total = torch.stack(stats).sum(dim=0)             # the all-reduce
+            for s in stats:
+                s.copy_(total)
+            torch.cuda.synchronize()
         for r, h in enumerate(hs):
             h.cycler_update(c, slab[r])
         for r, h in enumerate(hs):
@@ -65,6 +70,7 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world):
     return out.cpu().numpy(), final
 
 
+@pytest.mark.parametrize("exchange", ["device", "host"])
 @pytest.mark.parametrize("N,k,n_obs,n_cycles,S,stationary,world", [
     (4096, 16, 1200, 5, 20, True, 2),
     (4096, 16, 1200, 5, 20, False, 4),
@@ -72,13 +78,13 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world):
     (640, 8, 200, 4, 10, True, 8),           # slab (80) shorter than the left halo (80): multi-owner halos
     (96, 6, 40, 4, 5, True, 4),              # slab (24) shorter than the halo (40/20): halos wrap past neighbours
 ])
-def test_sharded_equals_single_gpu(N, k, n_obs, n_cycles, S, stationary, world):
+def test_sharded_equals_single_gpu(N, k, n_obs, n_cycles, S, stationary, world, exchange):
     sd, rho = 1.0, 1.02
     case = cycler_case(N, k, n_obs, n_cycles, S, sd, rho, stationary, seed=N + world)
     H1 = _native.Handle(0)
     ref, ref_final, _ = run_gpu_cycler(H1, case, N, k, n_cycles, sd, rho, stationary)
     H1.close()
-    out, final = run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world)
+    out, final = run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchange)
     assert np.all(np.isfinite(out))
     # same kernels, only the summation order of the k*k+k statistics differs between 1 and G ranks
     assert rel_err(out, ref) < 1e-10

@@ -46,7 +46,7 @@ def main():
         ref = ref.cpu().numpy()
         err = float(np.max(np.abs(full - ref)) / np.max(np.abs(ref)))
         ok = bool(np.isfinite(full).all()) and err < 1e-10
-        print("multigpu_check world=%d rel_err=%.3e finite=%s %s" % (world, err, np.isfinite(full).all(),
+        print("multigpu_check world=%d device_exchange=%s rel_err=%.3e finite=%s %s" % (world, cyc.device_exchange, err, np.isfinite(full).all(),
                                                                     "OK" if ok else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
