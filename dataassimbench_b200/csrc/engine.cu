@@ -395,8 +395,11 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
 }
 
 // ------------------------------------------------------------------------------ the cycler
-int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
-                     const int64_t* system_index, const int64_t* padded_time_idx) {
+// `x0_host` (nullable): initial ensemble in host memory; its upload is enqueued as soon as the
+// buffers exist, so that it overlaps the host-side preparation of the observation tables.
+static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                             const int64_t* system_index, const int64_t* padded_time_idx,
+                             const double* x0_host) {
   DAB_ARG(h, h != nullptr && cfg != nullptr);
   DAB_ARG(h, cfg->system_dim >= 4 && cfg->system_dim < (1ll << 31));
   DAB_ARG(h, cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= DAB_MAX_ENSEMBLE);
@@ -442,6 +445,8 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
     if (!c.ev_xa[w]) DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_xa[w], cudaEventDisableTiming));
     if (!c.ev_copied[w]) DAB_CUDA(h, cudaEventCreateWithFlags(&c.ev_copied[w], cudaEventDisableTiming));
   }
+  if (x0_host != nullptr)
+    DAB_CUDA(h, cudaMemcpyAsync(c.xb[0], x0_host, slab, cudaMemcpyHostToDevice, h->stream));
   // ---- observations: CSR over observation times, rows owned by this rank, masked rows dropped
   const long long nt = cfg->n_obs_times, no = cfg->n_obs;
   c.csr_off.assign((size_t)nt + 1, 0);
@@ -594,6 +599,11 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   h->launches = 0;
   c.ready = true;
   return 0;
+}
+
+int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                     const int64_t* system_index, const int64_t* padded_time_idx) {
+  return cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, nullptr);
 }
 
 int dab_cycler_set_state(dab_handle* h, const double* x, int is_host) {
@@ -910,7 +920,7 @@ int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const do
                             const int64_t* padded_time_idx, double* out_analysis) {
   DAB_ARG(h, h != nullptr && cfg != nullptr && x0 != nullptr);
   DAB_ARG(h, cfg->world == 1);
-  int rc = dab_cycler_setup(h, cfg, obs_values, system_index, padded_time_idx);
+  int rc = cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, x0);   // uploads x0 too
   if (rc) return rc;
   // pin the output range if the caller did not, so the per-cycle D2H overlaps the next cycle
   bool registered = false;
@@ -924,8 +934,7 @@ int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const do
       else cudaGetLastError();
     }
   }
-  rc = dab_cycler_set_state(h, x0, 1);
-  if (!rc) rc = dab_cycler_run(h, 0, cfg->n_cycles, out_analysis, nullptr);
+  rc = dab_cycler_run(h, 0, cfg->n_cycles, out_analysis, nullptr);
   if (!rc) rc = dab_sync(h);
   if (registered) cudaHostUnregister(out_analysis);
   return rc;
