@@ -554,7 +554,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   const long long tkey = (c.n_loc * 256 + k) * 64 + c.first_steps;
   for (size_t i = 0; i < h->tune_key.size(); ++i)
     if (h->tune_key[i] == tkey) { c.l96_T = h->tune_T[i]; c.l96_chunks = h->tune_chunks[i]; }
-  if (c.l96_T == 0 && c.first_steps > 0 && (long long)k * c.n_loc >= (1ll << 20)) {
+  if (c.l96_T == 0 && c.first_steps > 0 && (long long)k * c.n_loc >= (1ll << 17)) {
     DAB_CUDA(h, cudaMemsetAsync(c.ext[0].p, 0, c.ext[0].bytes, h->stream));
     cudaEvent_t e0, e1;
     DAB_CUDA(h, cudaEventCreate(&e0));

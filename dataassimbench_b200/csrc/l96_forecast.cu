@@ -238,11 +238,11 @@ static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, bool 
   }
 }
 
-// CTA width for one launch of `steps` steps over slabs of n points and k members.  Measured on
-// B200 (tools/tune_forecast.py, C3 shape): 256 threads x 3 resident CTAs per SM (80 registers)
-// beats every other width by 8-25 % -- three independent CTAs cover each other's per-stage
-// exchange bubbles -- so that is the default; small problems use narrower CTAs to reach more SMs.
-// The cycler re-checks the choice with CUDA events at setup (engine.cu) and passes `forced_T`.
+// CTA width for one launch of `steps` steps over slabs of n points and k members when no shape is
+// forced: 8 points per thread, 256 threads (three CTAs per SM), narrower for small problems so that
+// more SMs get a tile, wider when the halo would exceed half of the tile.  Problems large enough to
+// matter do not come through here: the cycler measures all shapes at setup (engine.cu) and passes
+// the winner as `forced_T`.
 static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per_thread, int forced_T,
                      int* T_out, int* useful_out, int* tiles_out) {
   (void)regs_per_thread;
@@ -280,7 +280,6 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
     const int tmax = P == 12 ? 192 : (dense ? 192 : 256);
     if (forced_T > tmax) forced_T = tmax;
   }
-  if (const char* ev = getenv("DAB_L96_P")) { if (atoi(ev) == 4) P = 4; }   // experiment knob
   int T = 256, useful = 0, tiles = 0;
   l96_plan(n, k, n_steps, sms, P, P == 8 ? 88 : 72, forced_T, &T, &useful, &tiles);
   L96Args a;
@@ -289,7 +288,6 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
   a.n = n; a.traj_stride = traj_stride;
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
   a.dt = dt; a.F = F;
-  if (P == 4) return launch_p<4>(a, k, T, periodic, dense, st);
   if (P == 12) return launch_p<12>(a, k, T, periodic, dense, st);
   if (P == 16) return launch_p<16>(a, k, T, periodic, dense, st);
   return launch_p<8>(a, k, T, periodic, dense, st);

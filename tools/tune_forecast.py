@@ -1,5 +1,6 @@
-"""Experiment: forecast kernel time vs kernel variant / CTA width at the C3 shape.
-v1 = per-stage shared-memory exchange (env DAB_L96_T), v2 = persistent + shuffle (env DAB_L96_V2)."""
+"""Experiment: forecast kernel time vs CTA shape at one problem shape (default C3), through the
+standalone entry point with the shape forced by DAB_L96_T (see kernels.h: l96_shape_code).
+The cycler does the same measurement itself at setup (engine.cu; DAB_TUNE_VERBOSE=1 prints it)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,10 +13,11 @@ y = torch.empty_like(x)
 st = torch.cuda.current_stream().cuda_stream
 res = {}
 ref = None
-for var, T in [("v1", 0), ("v1", 256), ("v1", 512)] + [("v2", t) for t in range(128, 513, 64)]:
-    os.environ.pop("DAB_L96_T", None); os.environ.pop("DAB_L96_V2", None)
-    if T:
-        os.environ["DAB_L96_T" if var == "v1" else "DAB_L96_V2"] = str(T)
+shapes = [0, 128, 192, 256, 320, 384, 512, 12128, 12192, 16128, 16192, 16256, 17128, 17160, 17192]
+for code in shapes:
+    os.environ.pop("DAB_L96_T", None)
+    if code:
+        os.environ["DAB_L96_T"] = str(code)
     for _ in range(3):
         H.l96_forecast(x, y, None, N, k, S, 0.01, 8.0, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,6 +27,5 @@ for var, T in [("v1", 0), ("v1", 256), ("v1", 512)] + [("v2", t) for t in range(
     e1.record(); torch.cuda.synchronize()
     if ref is None:
         ref = y.clone()
-    same = bool(torch.equal(ref, y))
-    res["%s_%d" % (var, T)] = (round(e0.elapsed_time(e1) / 20 * 1e3, 1), same)
+    res[str(code)] = (round(e0.elapsed_time(e1) / 20 * 1e3, 1), bool(torch.equal(ref, y)))
 print(json.dumps(res))
