@@ -874,6 +874,7 @@ int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int b
   a.k = k; a.N = N; a.n_steps = cfg->n_steps; a.n_cycles = cfg->n_cycles; a.t_pad = cfg->t_pad;
   a.n_obs = (int)cfg->n_obs;
   a.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
+  a.force_jacobi = h->eig_method == kEigJacobi;
   a.dt = cfg->model_dt; a.F = cfg->forcing; a.sd = cfg->obs_error_sd > 0.0 ? cfg->obs_error_sd : 1.0;
   DAB_CUDA(h, batched_launch(a, batch, st));
   h->launches++;

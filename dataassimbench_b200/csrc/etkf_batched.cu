@@ -9,12 +9,14 @@
 // RK4 window all live in one CTA's shared memory / registers and the experiments spread over the
 // SMs with no communication at all ("replicas only").
 //
-// Same arithmetic as the large path: gather -> centred contraction -> one-sided Jacobi (the
-// device body of etkf_eig_device.cuh) -> T -> Xa = Xb T -> RK4 (fixed step) window.
+// Same arithmetic as the large path: gather -> centred contraction -> transform matrix T (in-CTA
+// Newton-Schulz, etkf_ns_device.cuh; Jacobi, etkf_eig_device.cuh, as its fallback) -> Xa = Xb T ->
+// RK4 (fixed step) window.
 #include <cmath>
 
 #include "common.cuh"
 #include "etkf_eig_device.cuh"
+#include "etkf_ns_device.cuh"
 #include "kernels.h"
 
 namespace dab {
@@ -102,10 +104,13 @@ etkf_batched_kernel(const BatchedArgs a) {
       stats[e] = s * r_inv;
     }
     __syncthreads();
-    // ---- k x k eigensolver -> T (shared memory)
-    if (lpp == 1) eig_small_body<1>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
-    else if (lpp == 2) eig_small_body<2>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
-    else eig_small_body<4>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
+    // ---- k x k transform matrix T (shared memory): Newton-Schulz inverse square root on the tensor
+    //      core; the Jacobi eigensolver for the empty-R branch, ill-conditioned or non-finite statistics
+    if (a.empty_R || a.force_jacobi || !ns_small_body(stats, k, rho, Tm, nullptr, ew)) {
+      if (lpp == 1) eig_small_body<1>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
+      else if (lpp == 2) eig_small_body<2>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
+      else eig_small_body<4>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
+    }
     __syncthreads();
     // ---- Xa = Xb T for this thread's points
     double x[PPT], acc[PPT];
@@ -171,7 +176,8 @@ etkf_batched_kernel(const BatchedArgs a) {
 size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs) {
   const int nyp = t_pad * n_obs;
   size_t d = 2 * (size_t)k * (N + 3) + (size_t)k * nyp + nyp + ((size_t)k * k + k) + (size_t)k * k +
-             (size_t)eig_small_smem_doubles(k);
+             (size_t)(eig_small_smem_doubles(k) > ns_small_smem_doubles() ? eig_small_smem_doubles(k)
+                                                                          : ns_small_smem_doubles());
   return d * sizeof(double) + 16;
 }
 

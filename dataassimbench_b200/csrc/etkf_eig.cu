@@ -28,9 +28,21 @@
 
 #include "common.cuh"
 #include "etkf_eig_device.cuh"
+#include "etkf_ns_device.cuh"
 #include "kernels.h"
 
 namespace dab {
+
+// k <= 32 without an eigenvalue request: in-CTA Newton-Schulz (etkf_ns_device.cuh), with the Jacobi
+// body as its fallback in the same kernel.  256 threads.
+template <int LPP>
+__global__ void __launch_bounds__(256)
+ns_small_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ Tout,
+                          int* __restrict__ info_out) {
+  extern __shared__ __align__(16) double sm[];
+  if (!ns_small_body(stats, k, rho, Tout, info_out, sm))
+    eig_small_body<LPP>(stats, k, rho, 0, Tout, nullptr, info_out, sm);
+}
 
 template <int LPP>
 __global__ void __launch_bounds__(1024)
@@ -94,6 +106,22 @@ cudaError_t eig_transform_launch(const double* stats, int k, double rho, int emp
     return cudaGetLastError();
   }
   const int lpp = eig_lpp(k);
+  if (k <= 32 && !empty_R && method != kEigJacobi && lam_out == nullptr) {
+    const size_t ns_smem = sizeof(double) * (size_t)(ns_small_smem_doubles() > eig_small_smem_doubles(k)
+                                                         ? ns_small_smem_doubles() : eig_small_smem_doubles(k));
+#define DAB_NS_SMALL_CASE(L)                                                                              \
+  {                                                                                                       \
+    cudaFuncSetAttribute(ns_small_transform_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem); \
+    ns_small_transform_kernel<L><<<1, 256, ns_smem, st>>>(stats, k, rho, T, info_out);                     \
+  }
+    switch (lpp) {
+      case 1: DAB_NS_SMALL_CASE(1) break;
+      case 2: DAB_NS_SMALL_CASE(2) break;
+      default: DAB_NS_SMALL_CASE(4) break;
+    }
+#undef DAB_NS_SMALL_CASE
+    return cudaGetLastError();
+  }
   const int npairs = ((k + 1) & ~1) / 2;
   const int ppw = 32 / lpp;
   int warps = (npairs + ppw - 1) / ppw;

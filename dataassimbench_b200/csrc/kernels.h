@@ -82,6 +82,7 @@ struct BatchedArgs {
   double* out_final;           // nullable [batch][k][N]
   long long n_obs_times;
   int k, N, n_steps, n_cycles, t_pad, n_obs, empty_R;
+  int force_jacobi;            // K4 by the Jacobi eigensolver only (dab_set_eig_method)
   double dt, F, sd;
 };
 size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs);

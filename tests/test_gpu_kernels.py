@@ -195,11 +195,12 @@ def _random_stats(k, rho, scale, seed):
     return C, g
 
 
-@pytest.mark.parametrize("k", [33, 40, 64, 65, 100, 128])
+@pytest.mark.parametrize("k", [2, 3, 8, 10, 20, 32, 33, 40, 64, 65, 100, 128])
 @pytest.mark.parametrize("rho,scale", [(1.0, 0.0), (1.3, 1.0), (1.0, 2.0), (1.05, 3.0)])
 def test_transform_matrix_newton_schulz_path(H, k, rho, scale):
-    """32 < k <= 128 without an eigenvalue request: the cluster Newton-Schulz kernel
-    (csrc/etkf_ns.cu).  Same tolerance as the eigensolver path, and agreement with it."""
+    """No eigenvalue request: the Newton-Schulz kernels -- on a thread-block cluster for 32 < k <= 128
+    (csrc/etkf_ns.cu), inside one CTA for k <= 32 (csrc/etkf_ns_device.cuh).  Same tolerance as the
+    eigensolver path, and agreement with it."""
     C, g = _random_stats(k, rho, scale, seed=1000 * k + int(10 * scale))
     T_ref = o_etkf.transform_from_stats(C, g, k, rho)
     stats = dev(np.concatenate([C.ravel(), g]))
@@ -227,7 +228,7 @@ def test_transform_matrix_newton_schulz_path(H, k, rho, scale):
     assert torch.equal(T, T2)
 
 
-@pytest.mark.parametrize("k", [64, 128])
+@pytest.mark.parametrize("k", [20, 64, 128])
 def test_transform_matrix_newton_schulz_falls_back(H, k):
     """Ill-conditioned (bound on cond(A) > 1e7) or non-finite statistics: the Jacobi eigensolver
     enqueued behind the Newton-Schulz kernel takes over; the result keeps the oracle tolerance."""
