@@ -239,7 +239,7 @@ def run_c2_batched(H, B=4096, n_cycles=50):
     tidx = np.arange(0, n_cycles * S + 1, S)
     locs = rng.choice(N, n_obs, replace=False, shuffle=False)
     vals1 = truth[tidx][:, locs] + sd * rng.standard_normal((len(tidx), n_obs))
-    vals = np.ascontiguousarray(np.broadcast_to(vals1, (B,) + vals1.shape))
+    vals1 = np.ascontiguousarray(vals1)          # one observation set for the whole sweep (shared_index = 3)
     idx = np.ascontiguousarray(np.tile(locs, (len(tidx), 1)).astype(np.int64))
     x0 = np.ascontiguousarray(truth[0] + rng.standard_normal((B, k, N)))
     rho = np.linspace(1.0, 1.5, B)
@@ -248,9 +248,9 @@ def run_c2_batched(H, B=4096, n_cycles=50):
                               obs_error_sd=sd, n_obs_times=len(tidx), n_obs=n_obs, stationary=1,
                               n_cycles=n_cycles, t_pad=1, rank=0, world=1)
     mean = np.empty((B, n_cycles, N))
-    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)
+    H.etkf_cycle_batched(cfg, B, rho, x0, vals1, idx, 3, padded, None, mean, None)
     t0 = time.perf_counter()
-    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)
+    H.etkf_cycle_batched(cfg, B, rho, x0, vals1, idx, 3, padded, None, mean, None)
     t1 = time.perf_counter()
     return {"workload": "%d x (Lorenz96 N=40, k=20) ETKF, inflation sweep, %d cycles, S=20, one launch" % (B, n_cycles),
             "experiment_cycles_per_s": B * n_cycles / (t1 - t0), "member_steps_per_s": B * n_cycles * k * S / (t1 - t0),

@@ -844,6 +844,8 @@ int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int b
   const int k = cfg->ensemble_dim, N = (int)cfg->system_dim;
   const size_t kN = (size_t)k * N;
   const size_t n_obs_all = (size_t)cfg->n_obs_times * cfg->n_obs;
+  const bool shared_vals = (shared_index & 2) != 0;       // bit 1: one observation set for all experiments
+  shared_index &= 1;
   for (int b = 0; b < batch; ++b) DAB_ARG(h, rho[b] > 0.0);
   for (size_t i = 0; i < n_obs_all * (shared_index ? 1 : (size_t)batch); ++i)
     if (system_index[i] < 0 || system_index[i] >= N) return fail(h, -1, "system_index[%zu] = %lld out of range", i, (long long)system_index[i]);
@@ -859,13 +861,14 @@ int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int b
     return cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st);
   };
   DAB_CUDA(h, up(h->b_x0, x0, sizeof(double) * kN * batch));
-  DAB_CUDA(h, up(h->b_val, obs_values, sizeof(double) * n_obs_all * batch));
+  DAB_CUDA(h, up(h->b_val, obs_values, sizeof(double) * n_obs_all * (shared_vals ? 1 : (size_t)batch)));
   DAB_CUDA(h, up(h->b_idx, system_index, sizeof(int64_t) * n_obs_all * (shared_index ? 1 : batch)));
   DAB_CUDA(h, up(h->b_pad, padded_time_idx, sizeof(int64_t) * (size_t)cfg->n_cycles * cfg->t_pad));
   DAB_CUDA(h, up(h->b_rho, rho, sizeof(double) * batch));
   BatchedArgs a{};
   a.x0 = h->b_x0.as<double>(); a.obs_val = h->b_val.as<double>();
   a.obs_idx = h->b_idx.as<long long>(); a.idx_batch_stride = shared_index ? 0 : (long long)n_obs_all;
+  a.val_batch_stride = shared_vals ? 0 : (long long)n_obs_all;
   a.padded = h->b_pad.as<long long>(); a.rho = h->b_rho.as<double>();
   if (out_analysis) { DAB_CUDA(h, h->b_out.reserve(sizeof(double) * kN * batch * cfg->n_cycles)); a.out_analysis = h->b_out.as<double>(); }
   if (out_mean) { DAB_CUDA(h, h->b_mean.reserve(sizeof(double) * (size_t)N * batch * cfg->n_cycles)); a.out_mean = h->b_mean.as<double>(); }

@@ -21,11 +21,23 @@
 
 namespace dab {
 
-template <int PPT>    // points per thread: ceil(k*N / 256)
+// -DDAB_BATCH_TIMING (debug builds): thread 0 of CTA 0 accumulates clock64() per section and prints them
+#ifdef DAB_BATCH_TIMING
+#define BT_TICK(i) do { const long long now_ = clock64(); bt_[i] += now_ - bt_tick; bt_tick = now_; } while (0)
+#else
+#define BT_TICK(i) do { } while (0)
+#endif
+
+// PPT points per thread.  BLOCKED: a thread owns PPT CONSECUTIVE points of one member
+// (ceil(N/PPT) threads per member, k * ceil(N/PPT) <= 256) and keeps them in registers through the
+// RK4 window, so a stage reads only 3 neighbour values from shared memory.  Otherwise (shapes that do
+// not fit that mapping) points are dealt round-robin, p = tid + 256 q, and a stage reads all 4 stencil
+// values of every point from shared memory.
+template <int PPT, bool BLOCKED>
 __global__ void __launch_bounds__(256)
 etkf_batched_kernel(const BatchedArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int k = a.k, N = a.N, NP = N + 3;              // member row: [x_{N-2} x_{N-1} | x_0..x_{N-1} | x_0]
+  const int k = a.k, N = a.N, NP = N + 3;              // member row stride (3 spare slots: odd strides spread the banks)
   const int kN = k * N, nyp = a.t_pad * a.n_obs;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
@@ -43,33 +55,50 @@ etkf_batched_kernel(const BatchedArgs a) {
   const double dt = a.dt, F = a.F, h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
   const int lpp = eig_small_lpp(k);
 
-  // this thread's grid points: p = tid + 256*q  ->  member j, column i, offset o into a state buffer
-  int off[PPT], mem[PPT], col[PPT];
+  // this thread's grid points: p = tid + 256*q  ->  member j, column i, offset o into a state buffer,
+  // and the offsets of its three stencil neighbours on the periodic ring (computed once: the RK4
+  // stage below is then 4 loads, the 17-instruction arithmetic of l96_forecast.cu and 1 store)
+  int off[PPT], mem[PPT], col[PPT], gix[PPT], o_m2[PPT], o_m1[PPT], o_p1[PPT];
+  const int tpm = (N + PPT - 1) / PPT;                  // BLOCKED: threads per member
+  int npts = 0;                                         // BLOCKED: valid points of this thread
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
-    const int p = tid + 256 * q;
-    const int j = p < kN ? p / N : 0;
-    mem[q] = j; col[q] = p - j * N; off[q] = p < kN ? j * NP + 2 + (p - j * N) : -1;
+    int j, i;
+    bool valid;
+    if (BLOCKED) {
+      j = tid / tpm; i = (tid - j * tpm) * PPT + q;
+      valid = j < k && i < N;
+      if (valid) npts = q + 1;
+    } else {
+      const int p = tid + 256 * q;
+      valid = p < kN;
+      j = valid ? p / N : 0; i = p - j * N;
+    }
+    if (!valid) { j = 0; i = 0; }
+    const int base = j * NP + 2;
+    mem[q] = j; col[q] = i; gix[q] = j * N + i; off[q] = valid ? base + i : -1;
+    o_m2[q] = base + (i >= 2 ? i - 2 : i - 2 + N);
+    o_m1[q] = base + (i >= 1 ? i - 1 : N - 1);
+    o_p1[q] = base + (i + 1 < N ? i + 1 : 0);
   }
-  auto put = [&](double* S, int q, double v) {          // store a point and its periodic halo copies
-    const int o = off[q], i = col[q], base = mem[q] * NP;
-    S[o] = v;
-    if (i >= N - 2) S[base + i - (N - 2)] = v;
-    if (i == 0) S[base + N + 2] = v;
-  };
+  auto put = [&](double* S, int q, double v) { S[off[q]] = v; };
 
   const double* x0 = a.x0 + (long long)b * kN;
   double* cur = S0;
   double* nxt = S1;
 #pragma unroll
   for (int q = 0; q < PPT; ++q)
-    if (off[q] >= 0) put(cur, q, x0[tid + 256 * q]);
+    if (off[q] >= 0) put(cur, q, x0[gix[q]]);
   __syncthreads();
 
-  const double* vals_b = a.obs_val + (long long)b * a.n_obs_times * a.n_obs;
+  const double* vals_b = a.obs_val + (long long)b * a.val_batch_stride;
   const long long* idx_b = a.obs_idx + (long long)b * a.idx_batch_stride;
 
+#ifdef DAB_BATCH_TIMING
+  long long bt_[6] = {0, 0, 0, 0, 0, 0}, bt_tick = clock64();
+#endif
   for (int c = 0; c < a.n_cycles; ++c) {
+    BT_TICK(5);
     // ---- observations of this window -> centred Yb^T tile and innovations
     for (int r = tid; r < nyp; r += 256) {
       const int s = r / a.n_obs, o = r - s * a.n_obs;
@@ -91,6 +120,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       dv[r] = loc >= 0 ? y - ybar : 0.0;
     }
     __syncthreads();
+    BT_TICK(0);
     // ---- C = Y'^T Rinv Y',  g = Y'^T Rinv d
     for (int e = tid; e < k * k + k; e += 256) {
       double s = 0.0;
@@ -104,6 +134,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       stats[e] = s * r_inv;
     }
     __syncthreads();
+    BT_TICK(1);
     // ---- k x k transform matrix T (shared memory): Newton-Schulz inverse square root on the tensor
     //      core; the Jacobi eigensolver for the empty-R branch, ill-conditioned or non-finite statistics
     if (a.empty_R || a.force_jacobi || !ns_small_body(stats, k, rho, Tm, nullptr, ew)) {
@@ -112,6 +143,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       else eig_small_body<4>(stats, k, rho, a.empty_R, Tm, nullptr, nullptr, ew);
     }
     __syncthreads();
+    BT_TICK(2);
     // ---- Xa = Xb T for this thread's points
     double x[PPT], acc[PPT];
 #pragma unroll
@@ -127,7 +159,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       double* oa = a.out_analysis + ((long long)b * a.n_cycles + c) * kN;
 #pragma unroll
       for (int q = 0; q < PPT; ++q)
-        if (off[q] >= 0) oa[tid + 256 * q] = x[q];
+        if (off[q] >= 0) oa[gix[q]] = x[q];
     }
 #pragma unroll
     for (int q = 0; q < PPT; ++q)
@@ -142,34 +174,82 @@ etkf_batched_kernel(const BatchedArgs a) {
         om[i] = s * inv_k;
       }
     }
-    // ---- RK4 window: stage inputs ping-pong through shared memory, x / acc stay in registers
+    BT_TICK(3);
+    // ---- RK4 window: stage values ping-pong through shared memory; the per-step bases
+    //      xh = x + h/2 F, xd = x + h F and the weighted sum stay in registers (x = analysis now)
+    double xh[PPT], xd[PPT];
+    const double h2F = h2 * F, dtF = dt * F;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) { xh[q] = x[q] + h2F; xd[q] = x[q] + dtF; }
+    if (BLOCKED) {
+      // the thread's points live in registers; per stage: 3 neighbour loads, PPT stores
+      double s[PPT];
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) s[q] = x[q];
+      const int h_l2 = o_m2[0], h_l1 = o_m1[0], h_r = npts > 0 ? o_p1[npts - 1] : 0;
+      for (int step = 0; step < a.n_steps; ++step) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+          const double L2 = cur[h_l2], L1 = cur[h_l1], R = cur[h_r];
+          double v[PPT];
+#pragma unroll
+          for (int q = 0; q < PPT; ++q) {
+            const double sm2 = q >= 2 ? s[q - 2] : (q == 1 ? L1 : L2);
+            const double sm1 = q >= 1 ? s[q - 1] : L1;
+            const double sp1 = (q + 1 < PPT && q + 1 < npts) ? s[q + 1 < PPT ? q + 1 : q] : R;
+            const double t = fma(sp1 - sm2, sm1, -s[q]);
+            if (st == 0) { acc[q] = fma(h6, t, xd[q]); v[q] = fma(h2, t, xh[q]); }
+            else if (st == 1) { acc[q] = fma(h3, t, acc[q]); v[q] = fma(h2, t, xh[q]); }
+            else if (st == 2) { acc[q] = fma(h3, t, acc[q]); v[q] = fma(dt, t, xd[q]); }
+            else { v[q] = fma(h6, t, acc[q]); xh[q] = v[q] + h2F; xd[q] = v[q] + dtF; }
+          }
+#pragma unroll
+          for (int q = 0; q < PPT; ++q) {
+            s[q] = v[q];
+            if (q < npts) nxt[off[q]] = v[q];
+          }
+          __syncthreads();
+          { double* t_ = cur; cur = nxt; nxt = t_; }
+        }
+      }
+    } else {
     for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
-        const double ca = (st == 2) ? dt : h2;
-        const double cw = (st == 0 || st == 3) ? h6 : h3;
+        // all loads first, all stores last: `cur` and `nxt` are plain pointers into the same array,
+        // so a store between the loads would serialise the points of a thread
+        double v[PPT];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
-          if (off[q] >= 0) {
-            const int o = off[q];
-            const double kk = fma(cur[o + 1] - cur[o - 2], cur[o - 1], F - cur[o]);
-            acc[q] = (st == 0) ? fma(cw, kk, x[q]) : fma(cw, kk, acc[q]);
-            double v;
-            if (st < 3) v = fma(ca, kk, x[q]);
-            else { x[q] = acc[q]; v = acc[q]; }
-            put(nxt, q, v);
-          }
+          const int o = off[q] >= 0 ? off[q] : 0;
+          const double t = fma(cur[off[q] >= 0 ? o_p1[q] : 0] - cur[off[q] >= 0 ? o_m2[q] : 0],
+                               cur[off[q] >= 0 ? o_m1[q] : 0], -cur[o]);
+          if (st == 0) { acc[q] = fma(h6, t, xd[q]); v[q] = fma(h2, t, xh[q]); }
+          else if (st == 1) { acc[q] = fma(h3, t, acc[q]); v[q] = fma(h2, t, xh[q]); }
+          else if (st == 2) { acc[q] = fma(h3, t, acc[q]); v[q] = fma(dt, t, xd[q]); }
+          else { v[q] = fma(h6, t, acc[q]); xh[q] = v[q] + h2F; xd[q] = v[q] + dtF; }
         }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+          if (off[q] >= 0) nxt[off[q]] = v[q];
         __syncthreads();
         { double* t_ = cur; cur = nxt; nxt = t_; }
       }
     }
+    }
   }
+  BT_TICK(4);
+#ifdef DAB_BATCH_TIMING
+  if (b == 0 && tid == 0)
+    printf("batched k=%d N=%d cycles=%d, clocks per cycle: obs %lld stats %lld K4 %lld transform+out %lld rk4 %lld\n", k, N,
+           a.n_cycles, bt_[0] / a.n_cycles, bt_[1] / a.n_cycles, bt_[2] / a.n_cycles, bt_[3] / a.n_cycles,
+           (bt_[4] + bt_[5]) / a.n_cycles);
+#endif
   if (a.out_final != nullptr) {
     double* of = a.out_final + (long long)b * kN;
 #pragma unroll
     for (int q = 0; q < PPT; ++q)
-      if (off[q] >= 0) of[tid + 256 * q] = cur[off[q]];
+      if (off[q] >= 0) of[gix[q]] = cur[off[q]];
   }
 }
 
@@ -183,17 +263,25 @@ size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs) {
 
 cudaError_t batched_launch(const BatchedArgs& a, int batch, cudaStream_t st) {
   const size_t smem = batched_smem_bytes(a.k, a.N, a.t_pad, a.n_obs);
-  const int ppt = (a.k * a.N + 255) / 256;
-#define DAB_B_CASE(P)                                                                                 \
+#define DAB_B_CASE(P, B)                                                                              \
   {                                                                                                   \
-    cudaFuncSetAttribute(etkf_batched_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    etkf_batched_kernel<P><<<batch, 256, smem, st>>>(a);                                              \
+    cudaFuncSetAttribute(etkf_batched_kernel<P, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    etkf_batched_kernel<P, B><<<batch, 256, smem, st>>>(a);                                           \
+    return cudaGetLastError();                                                                        \
   }
-  if (ppt <= 4) DAB_B_CASE(4)
-  else if (ppt <= 8) DAB_B_CASE(8)
-  else DAB_B_CASE(16)
+  // blocked mapping with the fewest points per thread that fits 256 threads
+  for (int p = 4; p <= 16; p *= 2) {
+    if ((long long)a.k * ((a.N + p - 1) / p) <= 256) {
+      if (p == 4) DAB_B_CASE(4, true)
+      if (p == 8) DAB_B_CASE(8, true)
+      DAB_B_CASE(16, true)
+    }
+  }
+  const int ppt = (a.k * a.N + 255) / 256;          // ragged shapes: round-robin mapping
+  if (ppt <= 4) DAB_B_CASE(4, false)
+  if (ppt <= 8) DAB_B_CASE(8, false)
+  DAB_B_CASE(16, false)
 #undef DAB_B_CASE
-  return cudaGetLastError();
 }
 
 }  // namespace dab

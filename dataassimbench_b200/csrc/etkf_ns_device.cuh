@@ -10,19 +10,20 @@
 
 namespace dab {
 
-constexpr int kNsSmallKP = 32;                 // padded size (identity on the padding)
-constexpr int kNsSmallLD = 36;                 // row stride: DMMA fragments conflict-free both ways
 constexpr double kNsSmallMaxCond = 1e7;
 
-__host__ __device__ inline int ns_small_smem_doubles() { return 3 * kNsSmallKP * kNsSmallLD + 6 * kNsSmallKP + 8; }
+// padded size KP = 16, 24 or 32 (identity on the padding): the work goes with KP^3
+__host__ __device__ inline int ns_small_kp(int k) { return k <= 16 ? 16 : (k <= 24 ? 24 : 32); }
+__host__ __device__ inline int ns_small_smem_doubles() { return 3 * 32 * 36 + 6 * 32 + 8; }   // the KP = 32 case
 
 // stats: [k*k] C row-major then [k] g (global or shared).  Tout: [k][k] row-major (global or shared).
 // Returns false (uniformly over the CTA, nothing written) when the statistics are not finite or the
 // bound on cond(A') exceeds kNsSmallMaxCond: the caller then runs the Jacobi eigensolver.
 // Must be called by every thread of the CTA; blockDim.x == 256 (returns false otherwise).
-static __device__ __noinline__ bool ns_small_body(const double* stats, int k, double rho, double* Tout,
-                                              int* info_out, double* sm) {
-  constexpr int KP = kNsSmallKP, LD = kNsSmallLD;
+template <int KP>
+static __device__ __noinline__ bool ns_small_body_kp(const double* stats, int k, double rho, double* Tout,
+                                                     int* info_out, double* sm) {
+  constexpr int LD = KP + 4;                   // row stride: DMMA fragments conflict-free both ways
   double* Y = sm;                              // Y_k          [KP][LD]
   double* Z = Y + KP * LD;                     // Z_k
   double* Tm = Z + KP * LD;                    // T_k = c1 I + c2 Z Y
@@ -41,7 +42,7 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
   double delta_k = k > 1 ? tr / ((double)(k - 1) * (double)k) : 0.0;
   if (!(delta_k >= 0.0)) delta_k = 0.0;
   for (int i = warp; i < KP; i += nwarp) {     // one warp per row, one column per lane
-    const int j = lane;
+    const int j = lane;                        // lanes >= KP idle (KP <= 32)
     double a = (i == j) ? 1.0 : 0.0;           // identity on the padding (scaled below)
     const bool in = i < k && j < k;
     if (in) a = stats[i * k + j] + delta_k + (i == j ? shift : 0.0);
@@ -52,12 +53,14 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
       ab += __shfl_xor_sync(0xffffffffu, ab, o);
       di += __shfl_xor_sync(0xffffffffu, di, o);
     }
-    Y[i * LD + j] = a;                         // unscaled for now
-    Z[i * LD + j] = (i == j) ? 1.0 : 0.0;
+    if (j < KP) {
+      Y[i * LD + j] = a;                       // unscaled for now
+      Z[i * LD + j] = (i == j) ? 1.0 : 0.0;
+    }
     if (lane == 0) { r_sq[i] = sq; r_abs[i] = ab; r_g[i] = i < k ? 2.0 * di - ab : 1e300; }
   }
   __syncthreads();
-  double fro2 = r_sq[lane], rmax = r_abs[lane], gmin = r_g[lane];
+  double fro2 = lane < KP ? r_sq[lane] : 0.0, rmax = lane < KP ? r_abs[lane] : 0.0, gmin = lane < KP ? r_g[lane] : 1e300;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     fro2 += __shfl_xor_sync(0xffffffffu, fro2, o);
@@ -82,38 +85,50 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
   double l = sqrt(lower * inv_s) * (1.0 - 1e-6);
   int iters = 0;
   constexpr int NT = KP / 8;                   // 8 x 8 tiles per side
+  constexpr int TPW = (NT * NT + 7) / 8;       // tiles per warp (8 warps)
   for (; iters < 40; ++iters) {
     const double al2 = 3.0 / (1.0 + l + l * l), al = sqrt(al2);
     const double c1 = 1.5 * al, c2 = -0.5 * al * al2;
+    double m0[TPW], m1[TPW];                                  // T tiles (ti, tj) of this warp: all loads, then the stores
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {                             // T tiles (ti, tj) of this warp
+    for (int c = 0; c < TPW; ++c) {
       const int t = warp + 8 * c, ti = t / NT, tj = t - ti * NT;
-      double m0 = 0.0, m1 = 0.0;
-#pragma unroll 4
-      for (int ks = 0; ks < KP / 4; ++ks)
-        dmma884(m0, m1, Z[(8 * ti + fm) * LD + 4 * ks + fr], Y[(4 * ks + fr) * LD + 8 * tj + fm]);
+      m0[c] = 0.0; m1[c] = 0.0;
+      if (t < NT * NT) {                                      // warp-uniform
+#pragma unroll
+        for (int ks = 0; ks < KP / 4; ++ks)
+          dmma884(m0[c], m1[c], Z[(8 * ti + fm) * LD + 4 * ks + fr], Y[(4 * ks + fr) * LD + 8 * tj + fm]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < TPW; ++c) {
+      const int t = warp + 8 * c, ti = t / NT, tj = t - ti * NT;
+      if (t >= NT * NT) continue;
       const int row = 8 * ti + fm, col = 8 * tj + 2 * fr;
-      Tm[row * LD + col] = fma(c2, m0, row == col ? c1 : 0.0);
-      Tm[row * LD + col + 1] = fma(c2, m1, row == col + 1 ? c1 : 0.0);
+      Tm[row * LD + col] = fma(c2, m0[c], row == col ? c1 : 0.0);
+      Tm[row * LD + col + 1] = fma(c2, m1[c], row == col + 1 ? c1 : 0.0);
     }
     __syncthreads();
     // both products of a tile position in one pass; results held until every warp has read Y and Z
-    double y0[2], y1[2], z0[2], z1[2];
+    double y0[TPW], y1[TPW], z0[TPW], z1[TPW];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < TPW; ++c) {
       const int t = warp + 8 * c, ti = t / NT, tj = t - ti * NT;
       double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll 4
-      for (int ks = 0; ks < KP / 4; ++ks) {
-        dmma884(a0, a1, Y[(8 * ti + fm) * LD + 4 * ks + fr], Tm[(4 * ks + fr) * LD + 8 * tj + fm]);   // Y T
-        dmma884(b0, b1, Tm[(8 * ti + fm) * LD + 4 * ks + fr], Z[(4 * ks + fr) * LD + 8 * tj + fm]);   // T Z
+      if (t < NT * NT) {
+#pragma unroll
+        for (int ks = 0; ks < KP / 4; ++ks) {
+          dmma884(a0, a1, Y[(8 * ti + fm) * LD + 4 * ks + fr], Tm[(4 * ks + fr) * LD + 8 * tj + fm]);   // Y T
+          dmma884(b0, b1, Tm[(8 * ti + fm) * LD + 4 * ks + fr], Z[(4 * ks + fr) * LD + 8 * tj + fm]);   // T Z
+        }
       }
       y0[c] = a0; y1[c] = a1; z0[c] = b0; z1[c] = b1;
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < TPW; ++c) {
       const int t = warp + 8 * c, ti = t / NT, tj = t - ti * NT;
+      if (t >= NT * NT) continue;
       const int row = 8 * ti + fm, col = 8 * tj + 2 * fr;
       Y[row * LD + col] = y0[c]; Y[row * LD + col + 1] = y1[c];
       Z[row * LD + col] = z0[c]; Z[row * LD + col + 1] = z1[c];
@@ -128,7 +143,7 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
   for (int j = tid; j < KP; j += nthr) gs[j] = j < k ? stats[k * k + j] : 0.0;
   __syncthreads();
   for (int i = warp; i < KP; i += nwarp) {     // u_i = Z[i,:] g and cs_i = sum_{r<k} Z[r][i]
-    double u = Z[i * LD + lane] * gs[lane];
+    double u = lane < KP ? Z[i * LD + lane] * gs[lane] : 0.0;
     double c = lane < k ? Z[lane * LD + i] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
@@ -137,7 +152,7 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
   __syncthreads();
   const double inv_k = 1.0 / (double)k;
   for (int i = warp; i < KP; i += nwarp) {
-    double w = Z[i * LD + lane] * us[lane];
+    double w = lane < KP ? Z[i * LD + lane] * us[lane] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
     if (lane == 0) was[i] = w * inv_s;
@@ -155,6 +170,13 @@ static __device__ __noinline__ bool ns_small_body(const double* stats, int k, do
   if (info_out && tid == 0) *info_out = iters;
   __syncthreads();
   return true;
+}
+
+static __device__ __forceinline__ bool ns_small_body(const double* stats, int k, double rho, double* Tout,
+                                                     int* info_out, double* sm) {
+  if (k <= 16) return ns_small_body_kp<16>(stats, k, rho, Tout, info_out, sm);
+  if (k <= 24) return ns_small_body_kp<24>(stats, k, rho, Tout, info_out, sm);
+  return ns_small_body_kp<32>(stats, k, rho, Tout, info_out, sm);
 }
 
 }  // namespace dab

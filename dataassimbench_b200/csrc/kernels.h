@@ -75,6 +75,7 @@ struct BatchedArgs {
   const double* obs_val;       // [batch][n_obs_times][n_obs] (NaN = padded slot)
   const long long* obs_idx;    // [batch or 1][n_obs_times][n_obs]
   long long idx_batch_stride;  // 0 when the index set is shared by all experiments
+  long long val_batch_stride;  // 0 when the observed values are shared by all experiments
   const long long* padded;     // [n_cycles][t_pad], shared
   const double* rho;           // [batch]
   double* out_analysis;        // nullable [batch][n_cycles][k][N]

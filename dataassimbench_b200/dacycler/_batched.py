@@ -36,7 +36,7 @@ def cycle_batched(cyclers, input_states, start_time, obs_vectors, n_cycles, obs_
     rho = np.ascontiguousarray([p['cfg'].rho for p in plans], dtype=np.float64)
     x0 = np.ascontiguousarray(np.stack([p['X0'] for p in plans]))
     if shared_obs:
-        vals = np.ascontiguousarray(np.broadcast_to(plans[0]['vals'], (B,) + plans[0]['vals'].shape))
+        vals = plans[0]['vals']                    # one observation set, uploaded once (flag bits 0 and 1)
         idx = plans[0]['sysidx']
     else:
         vals = np.ascontiguousarray(np.stack([p['vals'] for p in plans]))
@@ -45,8 +45,8 @@ def cycle_batched(cyclers, input_states, start_time, obs_vectors, n_cycles, obs_
     dim = plans[0]['state_dim']
     if return_mean_only:
         mean = np.empty((B, n_cycles, N))
-        H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, shared_obs, plans[0]['padded'], None, mean, None)
+        H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, 3 if shared_obs else 0, plans[0]['padded'], None, mean, None)
         return _xr.new_dataset({'x_mean': (('experiment', 'cycle', dim), mean)})
     out = np.empty((B, n_cycles, k, N))
-    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, shared_obs, plans[0]['padded'], out, None, None)
+    H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, 3 if shared_obs else 0, plans[0]['padded'], out, None, None)
     return _xr.new_dataset({'x': (('experiment', 'cycle', 'ensemble', dim), out)})

@@ -177,8 +177,10 @@ DAB_API int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, 
  * independent DACycler.cycle() experiments, one CTA each, the whole experiment in ONE launch.
  * cfg gives the per-experiment shape (rho ignored; k <= 32, k*N <= 4096, t_pad*n_obs*k <= 8192).
  * All pointers are HOST memory: rho [batch]; x0 [batch][k][N]; obs_values
- * [batch][n_obs_times][n_obs] (NaN = padded slot); system_index [batch][n_obs_times][n_obs], or
- * [n_obs_times][n_obs] when shared_index != 0; padded_time_idx [n_cycles][t_pad] (shared).
+ * [batch][n_obs_times][n_obs] (NaN = padded slot), or [n_obs_times][n_obs] when bit 1 of
+ * shared_index is set (one observation set for all experiments); system_index
+ * [batch][n_obs_times][n_obs], or [n_obs_times][n_obs] when bit 0 of shared_index is set;
+ * padded_time_idx [n_cycles][t_pad] (shared).
  * Outputs (each nullable): out_analysis [batch][n_cycles][k][N]; out_mean [batch][n_cycles][N]
  * (ensemble-mean analysis); out_final [batch][k][N] (background after the last forecast). */
 DAB_API int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int batch,

@@ -30,8 +30,10 @@ def run_batch(H, cases, rhos, N, k, n_cycles, S, dt, sd, stationary, shared_inde
     out = np.empty((B, n_cycles, k, N))
     mean = np.empty((B, n_cycles, N))
     fin = np.empty((B, k, N))
-    H.etkf_cycle_batched(cfg, B, np.ascontiguousarray(rhos, dtype=np.float64), x0, vals,
-                         np.ascontiguousarray(idx[0]) if shared_index else idx, shared_index, padded,
+    # shared_index: bit 0 = one index set, bit 1 = one set of observed values for all experiments
+    H.etkf_cycle_batched(cfg, B, np.ascontiguousarray(rhos, dtype=np.float64), x0,
+                         np.ascontiguousarray(vals[0]) if int(shared_index) & 2 else vals,
+                         np.ascontiguousarray(idx[0]) if int(shared_index) & 1 else idx, int(shared_index), padded,
                          out, mean, fin)
     return out, mean, fin
 
@@ -43,6 +45,8 @@ def run_batch(H, cases, rhos, N, k, n_cycles, S, dt, sd, stationary, shared_inde
     (40, 20, 40, 20, 5, True, None),        # converged regime
     (64, 32, 24, 5, 10, True, 5),           # k = 32 (largest), two obs times per window
     (5, 8, 3, 5, 10, True, None),           # the reference test's tiny shape
+    (100, 20, 30, 3, 8, True, None),        # 16 consecutive points per thread (7 threads per member, ragged)
+    (132, 31, 12, 2, 5, True, None),        # k * ceil(N/16) > 256: the round-robin point mapping
 ])
 def test_batched_equals_oracle_per_experiment(N, k, n_obs, n_cycles, S, stationary, obs_every):
     sd, dt = 1.0, 0.01
@@ -75,6 +79,9 @@ def test_batched_inflation_sweep_shared_index_matches_unbatched_gpu():
         ref, ref_fin, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, float(rho), True)
         assert rel_err(out[b], ref) < 1e-10
         assert rel_err(fin[b], ref_fin) < 1e-9
+    # one upload of the observed values for the whole sweep (flag bit 1): the same bits
+    out3, _, fin3 = run_batch(H, [case] * len(rhos), rhos, N, k, n_cycles, S, 0.01, sd, True, shared_index=3)
+    assert np.array_equal(out3, out) and np.array_equal(fin3, fin)
     H.close()
 
 

@@ -14,7 +14,7 @@ _, truth = o_l96.rk4_forecast(truth0, n_cycles * S, dt, return_traj=True)
 tidx = np.arange(0, n_cycles * S + 1, S)
 locs = rng.choice(N, n_obs, replace=False, shuffle=False)
 vals1 = truth[tidx][:, locs] + sd * rng.standard_normal((len(tidx), n_obs))
-vals = np.ascontiguousarray(np.broadcast_to(vals1, (B,) + vals1.shape))
+vals1 = np.ascontiguousarray(vals1)          # one observation set for the whole sweep (shared_index = 3)
 idx = np.ascontiguousarray(np.tile(locs, (len(tidx), 1)).astype(np.int64))
 x0 = np.ascontiguousarray(truth[0] + rng.standard_normal((B, k, N)))
 rho = np.linspace(1.0, 1.5, B)
@@ -24,9 +24,9 @@ cfg = _native.CycleConfig(system_dim=N, ensemble_dim=k, n_steps=S, model_dt=dt, 
                           n_cycles=n_cycles, t_pad=1, rank=0, world=1)
 H = _native.Handle(0)
 mean = np.empty((B, n_cycles, N))
-H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)     # warm-up
+H.etkf_cycle_batched(cfg, B, rho, x0, vals1, idx, 3, padded, None, mean, None)     # warm-up
 t0 = time.perf_counter()
-H.etkf_cycle_batched(cfg, B, rho, x0, vals, idx, True, padded, None, mean, None)
+H.etkf_cycle_batched(cfg, B, rho, x0, vals1, idx, 3, padded, None, mean, None)
 t1 = time.perf_counter()
 rmse = np.sqrt(((mean - truth[tidx[:n_cycles]][None]) ** 2).mean(axis=2))[:, 50:].mean(axis=1)
 # oracle on 2 experiments
