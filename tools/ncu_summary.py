@@ -36,8 +36,8 @@ def launches(src, dst):
     tot = sum(v[1] for v in agg.values())
     with open(dst, 'w') as f:
         f.write('# ncu launch list summary (%s)\n\n' % os.path.basename(src))
-        f.write('`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 20 '
-                '--warmup 10 --no-cpu-baseline`; per-launch times are cold-cache and serialised: compare SHARES.\n\n')
+        f.write('`ncu --metrics gpu__time_duration.sum --clock-control none` over a short `python bench.py '
+                '--no-cpu-baseline` run (see tools/evidence_r01.sh); per-launch times are cold-cache and serialised: compare SHARES.\n\n')
         f.write('| kernel | block | grid | launches | avg us | share |\n|---|---|---|---|---|---|\n')
         for (name, blk, grd), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %s | %s | %d | %.1f | %.3f |\n' % (name[:80], blk, grd, v[0], v[1] / v[0], v[1] / tot))
