@@ -34,6 +34,7 @@
 // takes over: for k <= 64 inside this kernel (CTA 0 has exactly its geometry), for k > 64 through
 // a flag in the scratch header that the eigensolver kernel enqueued behind this one checks.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "etkf_eig_device.cuh"
@@ -90,31 +91,14 @@ struct NsCfg {
 
 }  // namespace
 
-// ws: [16 ints header][2 parities][Z | Yt][KP*KP] doubles.
-template <int KP, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ ws,
-                    double* __restrict__ Tout, int* __restrict__ info_out) {
-  using C = NsCfg<KP, NW>;
-  constexpr int ROWS = C::ROWS, MT = C::MT, LDS = C::LDS, NT = NW * 32;
-  extern __shared__ __align__(16) double sm[];
-  double* Zs = sm;                               // own rows of Z        [ROWS][LDS]
-  double* Yts = Zs + ROWS * LDS;                 // own rows of Y^T
-  double* Ts0 = Yts + ROWS * LDS;                // T[R,:]
-  double* Ts1 = Ts0 + ROWS * LDS;                // T[:,R]^T
-  __shared__ double red_sq[KP], red_abs[KP];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fm = lane >> 2, q = lane & 3;
-  const int rank = (int)cluster_cta_rank();
-  const int R0 = ROWS * rank;
-  int* flags = reinterpret_cast<int*>(ws);
-  double* mats = ws + 2;                         // 16-byte header
-  const double shift = (double)(k - 1) / rho;
-#ifdef DAB_NS_TIMING
-  long long ns_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ns_tick = clock64();
-#endif
-
+// Deflation and bounds, shared by the two cluster kernels.  Returns delta/k, the scale s and the
+// lower bound of the spectrum of A' in the out-parameters; `ok` = statistics finite and the bound on
+// cond(A') within kNsMaxCond.  Every thread of every CTA computes the same values.
+template <int KP, int NT>
+__device__ __forceinline__ bool ns_bounds(const double* __restrict__ stats, int k, double shift,
+                                          double* red_sq, double* red_abs, double* red_g,
+                                          double& delta_k_out, double& s_out, double& lower_out) {
+  const int tid = threadIdx.x, lane = tid & 31;
   // ---- deflation and scale.  1 is an eigenvector of A with eigenvalue lambda_min = shift, and T only
   // needs A^{-1/2} on its orthogonal complement ((I-U) U = 0 and g is orthogonal to 1), so the
   // iteration runs on  A' = A + delta U  with  delta = tr(C)/(k-1): the known smallest eigenvalue is
@@ -124,7 +108,6 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   //   spectrum(A') in [max(shift, min_i(a'_ii - sum_{j != i} |a'_ij|)), min(|A'|_F, |A'|_inf)].
   // C3's first cycle: cond bound 640 -> 2.5, 8 steps -> 5.  Non-finite statistics poison |A'|_F.
   // TPR threads per row, interleaved columns (all loads in flight at once, sectors fully used).
-  __shared__ double red_g[KP];
   double delta_k = 0.0;
   {
     constexpr int TPR = NT / KP, CPT = KP / TPR;
@@ -192,7 +175,38 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   const double fro = sqrt(fro2);
   const double s = fro < rmax ? fro : rmax;
   const double lower = gmin > shift ? gmin : shift;          // A' >= A >= shift I (delta >= 0)
-  const bool ok = (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * lower);
+  delta_k_out = delta_k; s_out = s; lower_out = lower;
+  return (fro2 < 1e300) && (s > 0.0) && (s <= kNsMaxCond * lower);
+}
+
+// ws: [16 ints header][2 parities][Z | Yt][KP*KP] doubles.
+template <int KP, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ ws,
+                    double* __restrict__ Tout, int* __restrict__ info_out) {
+  using C = NsCfg<KP, NW>;
+  constexpr int ROWS = C::ROWS, MT = C::MT, LDS = C::LDS, NT = NW * 32;
+  extern __shared__ __align__(16) double sm[];
+  double* Zs = sm;                               // own rows of Z        [ROWS][LDS]
+  double* Yts = Zs + ROWS * LDS;                 // own rows of Y^T
+  double* Ts0 = Yts + ROWS * LDS;                // T[R,:]
+  double* Ts1 = Ts0 + ROWS * LDS;                // T[:,R]^T
+  __shared__ double red_sq[KP], red_abs[KP];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, q = lane & 3;
+  const int rank = (int)cluster_cta_rank();
+  const int R0 = ROWS * rank;
+  int* flags = reinterpret_cast<int*>(ws);
+  double* mats = ws + 2;                         // 16-byte header
+  const double shift = (double)(k - 1) / rho;
+#ifdef DAB_NS_TIMING
+  long long ns_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ns_tick = clock64();
+#endif
+
+  __shared__ double red_g[KP];
+  double delta_k, s, lower;
+  const bool ok = ns_bounds<KP, NT>(stats, k, shift, red_sq, red_abs, red_g, delta_k, s, lower);
   if (!ok) {                                     // uniform over the cluster: same inputs, same code
     if (KP == 64) {                              // k <= 64: CTA 0 IS the Jacobi eigensolver's CTA (8 warps, 64 columns)
       if (rank == 0) {
@@ -440,6 +454,260 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k <= 64: the same iteration with the two full matrices RESIDENT in every CTA's shared memory.
+// The step of the kernel above is latency-bound on pulling 128 KB of B fragments from L2 (eight
+// SMs reading the same lines) behind a cluster barrier.  Here every CTA writes its two new 4 KB
+// strips to the global scratch and issues TWO bulk copies (cp.async.bulk ... multicast::cluster)
+// that deliver them into the double-buffered shared memory of all eight CTAs and count their bytes
+// on the destination CTAs' mbarriers; a CTA starts its next step when its own mbarrier has seen all
+// sixteen strips (64 KB) -- no cluster barrier, every byte crosses L2 -> SM once, and the DMMA
+// fragments of both phases come from shared memory (16-byte chunks XOR-swizzled per row so that the
+// row-wise and the column-wise fragment loads are both conflict-free).  A buffer is safe to overwrite
+// when the strips of the step in between have arrived: their senders finished reading it first.
+namespace {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+// a peer that never delivers is a bug or a dead SM: trap after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(a, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void bulk_multicast(unsigned dst, const void* src, unsigned bytes, unsigned mbar,
+                                               unsigned short mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+               "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(mask) : "memory");
+}
+// element (r, j) of a 64 x 64 matrix: rows of 512 bytes, the 16-byte chunk index XORed with f(r)
+__device__ __forceinline__ int swz64(int r, int j) {
+  const int f = ((r & 1) << 2) ^ (((r >> 1) & 3) << 1);
+  return r * 64 + ((((j >> 1) ^ f)) << 1) + (j & 1);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1)
+ns_mc_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ ws,
+                       double* __restrict__ Tout, int* __restrict__ info_out) {
+  constexpr int KP = 64, ROWS = 8, NT = 256, NW = 8, LDT = KP + 8, MAT = KP * KP;
+  extern __shared__ __align__(128) double sm[];
+  double* Bz = sm;                               // [2][MAT]  Z, swizzled, double-buffered
+  double* Byt = sm + 2 * MAT;                    // [2][MAT]  Y^T
+  double* Ts0 = sm + 4 * MAT;                    // T[R,:]     [ROWS][LDT]
+  double* Ts1 = Ts0 + ROWS * LDT;                // T[:,R]^T
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(Ts1 + ROWS * LDT);   // [2]
+  __shared__ double red_sq[KP], red_abs[KP], red_g[KP];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, q = lane & 3;
+  const int rank = (int)cluster_cta_rank();
+  const int R0 = ROWS * rank;
+  int* flags = reinterpret_cast<int*>(ws);
+  double* mats = ws + 2;                         // [2 parities][Z | Yt][MAT], swizzled row images
+  const double shift = (double)(k - 1) / rho;
+#ifdef DAB_NS_TIMING
+  long long ns_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ns_tick = clock64();
+#endif
+
+  double delta_k, s, lower;
+  const bool ok = ns_bounds<KP, NT>(stats, k, shift, red_sq, red_abs, red_g, delta_k, s, lower);
+  if (!ok) {                                     // uniform over the cluster
+    if (rank == 0) {
+      if (tid == 0) flags[0] = 0;
+      eig_block_body<8>(stats, k, 64, rho, Tout, nullptr, info_out, 0, sm);
+    }
+    return;
+  }
+  const double inv_s = 1.0 / s;
+  const unsigned mb0 = smem_u32(mbar), mb1 = mb0 + 8;
+  if (tid == 0) {
+    mbar_init(mb0, 1); mbar_init(mb1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- Z0 = I, Y0 = A'/s: own strips to the global scratch (parity 0)
+  for (int e = tid; e < ROWS * KP; e += NT) {
+    const int r = e / KP, j = e - r * KP, i = R0 + r;
+    const double z = (i == j) ? 1.0 : 0.0;
+    double y = z;
+    if (i < k && j < k) y = (stats[i * k + j] + delta_k + (i == j ? shift : 0.0)) * inv_s;
+    mats[swz64(i, j)] = z;
+    mats[MAT + swz64(i, j)] = y;
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  cluster_sync_all();                            // every CTA's mbarriers exist before any copy lands
+  // publish the strips of parity `p`: 2 x 4 KB to all eight CTAs
+  auto publish = [&](int p) {
+    if (tid == 0) {
+      const unsigned mb = p ? mb1 : mb0;
+      mbar_expect_tx(mb, 2u * 8u * ROWS * KP * 8u);
+      const double* src = mats + (size_t)p * 2 * MAT + R0 * KP;
+      bulk_multicast(smem_u32(Bz + p * MAT + R0 * KP), src, ROWS * KP * 8, mb, 0xFF);
+      bulk_multicast(smem_u32(Byt + p * MAT + R0 * KP), src + MAT, ROWS * KP * 8, mb, 0xFF);
+    }
+  };
+  publish(0);
+  NS_TICK(0);
+
+  double l = sqrt(lower * inv_s) * (1.0 - 1e-6);
+  int par = 0, iters = 0;
+  unsigned ph[2] = {0u, 0u};                     // phase parity of the two mbarriers
+  for (; iters < kNsMaxIter; ++iters) {
+    const double al2 = 3.0 / (1.0 + l + l * l);
+    const double al = sqrt(al2);
+    const double c1 = 1.5 * al, c2 = -0.5 * al * al2;
+    mbar_wait(par ? mb1 : mb0, ph[par]);
+    ph[par] ^= 1u;
+    NS_TICK(1);
+    const double* Z = Bz + par * MAT;
+    const double* Yt = Byt + par * MAT;
+
+    // ---- phase 1: warp w -> tile w of M[R,:] = Z[R,:] Y and of M[:,R]^T = Yt[R,:] Z^T
+    double m0[2] = {0.0, 0.0}, m1[2] = {0.0, 0.0};
+    {
+      const int rb = 8 * warp + fm;              // B row (transposed access): column 8w+fm of the product
+      const int fa = (((R0 + fm) & 1) << 2) ^ ((((R0 + fm) >> 1) & 3) << 1);
+      const int fb = ((rb & 1) << 2) ^ (((rb >> 1) & 3) << 1);
+      const double* a0p = Z + (R0 + fm) * KP;    // A = Z[R,:],  B[j][n] = Yt[n][j]
+      const double* a1p = Yt + (R0 + fm) * KP;   // A = Yt[R,:], B[j][n] = Z[n][j]
+      const double* b0p = Yt + rb * KP;
+      const double* b1p = Z + rb * KP;
+#pragma unroll
+      for (int kk = 0; kk < KP / 8; ++kk) {
+        const int c = 4 * kk + q;
+        const double2 a0 = *reinterpret_cast<const double2*>(a0p + ((c ^ fa) << 1));
+        const double2 b0 = *reinterpret_cast<const double2*>(b0p + ((c ^ fb) << 1));
+        const double2 a1 = *reinterpret_cast<const double2*>(a1p + ((c ^ fa) << 1));
+        const double2 b1 = *reinterpret_cast<const double2*>(b1p + ((c ^ fb) << 1));
+        dmma884(m0[0], m1[0], a0.x, b0.x); dmma884(m0[1], m1[1], a1.x, b1.x);
+        dmma884(m0[0], m1[0], a0.y, b0.y); dmma884(m0[1], m1[1], a1.y, b1.y);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {                // T = c1 I + c2 M
+      double* Ts = g == 0 ? Ts0 : Ts1;
+      const int row = R0 + fm, col = 8 * warp + 2 * q;
+      double2 t;
+      t.x = fma(c2, m0[g], row == col ? c1 : 0.0);
+      t.y = fma(c2, m1[g], row == col + 1 ? c1 : 0.0);
+      *reinterpret_cast<double2*>(Ts + fm * LDT + col) = t;
+    }
+    __syncthreads();
+    NS_TICK(2);
+
+    // ---- phase 2: warps 0-3 -> Z'[R,:] = T[R,:] Z, warps 4-7 -> Y'^T[R,:] = T[:,R]^T Yt; a warp
+    //      takes the interleaved pair of 8-column tiles t (columns 16t+2i and 16t+2i+1)
+    const int prod = warp >> 2, t = warp & 3;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    {
+      const double* As = prod == 0 ? Ts0 : Ts1;
+      const double* B = prod == 0 ? Z : Yt;
+#pragma unroll
+      for (int kk = 0; kk < KP / 8; ++kk) {
+        const double2 a = *reinterpret_cast<const double2*>(As + fm * LDT + 8 * kk + 2 * q);
+        const int j0 = 8 * kk + 2 * q, j1 = j0 + 1, c = 8 * t + fm;
+        const int f0 = ((j0 & 1) << 2) ^ (((j0 >> 1) & 3) << 1), f1 = ((j1 & 1) << 2) ^ (((j1 >> 1) & 3) << 1);
+        const double2 b0 = *reinterpret_cast<const double2*>(B + j0 * KP + ((c ^ f0) << 1));
+        const double2 b1 = *reinterpret_cast<const double2*>(B + j1 * KP + ((c ^ f1) << 1));
+        dmma884(acc[0][0], acc[0][1], a.x, b0.x); dmma884(acc[1][0], acc[1][1], a.x, b0.y);
+        dmma884(acc[0][0], acc[0][1], a.y, b1.x); dmma884(acc[1][0], acc[1][1], a.y, b1.y);
+      }
+    }
+#ifdef DAB_NS_TIMING
+    if (acc[0][0] == -1.2345e300) ns_t[7] -= 1;
+#endif
+    NS_TICK(3);
+    // new strip rows -> global scratch of the other parity (swizzled), then the multicast
+    {
+      double* Sg = mats + (size_t)(par ^ 1) * 2 * MAT + (prod == 0 ? 0 : MAT);
+      const int r = R0 + fm, cch = 8 * t + 2 * q;           // chunks cch, cch+1 = columns 16t+4q .. +3
+      const int f = ((r & 1) << 2) ^ (((r >> 1) & 3) << 1);
+      *reinterpret_cast<double2*>(Sg + r * KP + ((cch ^ f) << 1)) = make_double2(acc[0][0], acc[1][0]);
+      *reinterpret_cast<double2*>(Sg + r * KP + (((cch + 1) ^ f) << 1)) = make_double2(acc[0][1], acc[1][1]);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    par ^= 1;
+    l = 0.5 * al * l * (3.0 - al2 * l * l);
+    const bool done = 1.0 - l < 1e-12;
+    publish(par);                                 // also after the last step: the final stage reads Z from it
+    NS_TICK(4);
+    if (done) { ++iters; break; }
+  }
+
+  // ---- T = U + (I-U)(wa 1^T + Wa),  Wa = sqrt((k-1)/s) Z,  wa = Z (Z g) / s; rows R of T
+  mbar_wait(par ? mb1 : mb0, ph[par]);
+  {
+    const double* Z = Bz + par * MAT;
+    double* gs = Ts0;                            // reuse the T strips: g, u, column sums, wa
+    double* us = gs + KP;
+    double* cs = us + KP;
+    double* was = cs + KP;
+    for (int j = tid; j < KP; j += NT) gs[j] = j < k ? stats[k * k + j] : 0.0;
+    __syncthreads();
+    {
+      constexpr int TPR = NT / KP, CPT = KP / TPR;         // 4 threads per row / column
+      const int i = tid / TPR, c = tid % TPR;
+      double u0 = 0.0, s0 = 0.0;
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        const int j = c + TPR * m;
+        u0 = fma(Z[swz64(i, j)], gs[j], u0);
+        s0 += j < k ? Z[swz64(j, i)] : 0.0;
+      }
+#pragma unroll
+      for (int o = TPR / 2; o > 0; o >>= 1) {
+        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      }
+      if (c == 0) { us[i] = u0; cs[i] = s0; }
+    }
+    __syncthreads();
+    const double inv_k = 1.0 / (double)k;
+    {
+      const int r = warp;                        // one warp per own row
+      double a0 = fma(Z[swz64(R0 + r, lane)], us[lane], Z[swz64(R0 + r, lane + 32)] * us[lane + 32]);
+      double mm = fma(cs[lane], us[lane], cs[lane + 32] * us[lane + 32]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        mm += __shfl_xor_sync(0xffffffffu, mm, o);
+      }
+      if (lane == 0) was[r] = a0 * inv_s;
+      if (tid == 0) was[ROWS] = mm * inv_s * inv_k;
+    }
+    __syncthreads();
+    const double cw = sqrt((double)(k - 1) * inv_s);
+    const double wmean = was[ROWS];
+    for (int e = tid; e < ROWS * KP; e += NT) {
+      const int r = e / KP, j = e - r * KP, i = R0 + r;
+      if (i < k && j < k) Tout[i * k + j] = inv_k + (was[r] - wmean) + cw * (Z[swz64(i, j)] - cs[j] * inv_k);
+    }
+  }
+  NS_TICK(6);
+  if (rank == 0 && tid == 0) {
+    flags[0] = 0;
+    if (info_out) *info_out = iters;
+#ifdef DAB_NS_TIMING
+    printf("ns_mc k=%d iters=%d cycles: prologue %lld | wait for strips %lld phase1+sync %lld phase2 %lld store+fence+publish %lld | final %lld\n",
+           k, iters, ns_t[0], ns_t[1], ns_t[2], ns_t[3], ns_t[4], ns_t[6]);
+#endif
+  }
+  cluster_sync_all();                            // no CTA leaves while copies into it may be in flight
+}
+
 size_t ns_ws_bytes(int k) {
   const size_t kp = k <= 64 ? 64 : 128;
   return 16 + sizeof(double) * 4 * kp * kp;
@@ -470,8 +738,28 @@ cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, doub
 }
 }  // namespace
 
+static cudaError_t ns_mc_launch(const double* stats, int k, double rho, double* ws, double* T, int* info_out,
+                                cudaStream_t st) {
+  const size_t smem = sizeof(double) * (4 * 64 * 64 + 2 * 8 * 72) + 64;
+  cudaError_t e = cudaFuncSetAttribute(ns_mc_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(8);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ns_mc_transform_kernel, stats, k, rho, ws, T, info_out);
+}
+
 cudaError_t ns_transform_launch(const double* stats, int k, double rho, double* ws, double* T,
                                 int* info_out, cudaStream_t st) {
+  static int use_mc = -1;                        // DAB_NS_MC=0: the L2-streaming kernel for k <= 64 too
+  if (use_mc < 0) { const char* ev = getenv("DAB_NS_MC"); use_mc = ev ? atoi(ev) : 1; }
+  if (k <= 64 && use_mc) return ns_mc_launch(stats, k, rho, ws, T, info_out, st);
   if (k <= 64) return ns_launch_t<64, 8>(stats, k, rho, ws, T, info_out, st);
   return ns_launch_t<128, 8>(stats, k, rho, ws, T, info_out, st);
 }
