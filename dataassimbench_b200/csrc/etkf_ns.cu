@@ -16,7 +16,10 @@
 //   alpha^2 = 3/(1 + l + l^2),  l <- alpha l (3 - alpha^2 l^2)/2
 //   (4-5 steps on the bench workloads; 9 at cond 1e3, 12 at cond 3e6)
 // Everything is k x k x k GEMM work, so -- unlike Jacobi, whose rotation chain is serial -- it
-// spreads over a thread-block cluster:
+// spreads over a thread-block cluster.  Two kernels share the scheme: `ns_transform_kernel` below
+// streams the B operands from L2 (any k <= 128), `ns_mc_transform_kernel` further down keeps both
+// matrices in shared memory and exchanges the strips by multicast bulk copies (k <= 64, the default
+// there).  The common structure:
 //   * a cluster of 8 CTAs; CTA r owns rows R = [ROWS r, ROWS (r+1)) of Z and of Y^T (= columns
 //     of Y), ROWS = KP/8;
 //   * per step every CTA forms FOUR row-strip products on the FP64 tensor core (DMMA.8x8x4):
