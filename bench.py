@@ -362,8 +362,6 @@ def run_product(args):
         n_loc = hi - lo
         x0 = torch.from_numpy(np.ascontiguousarray(w["X0"][:, lo:hi])).pin_memory()
         out_host = torch.empty((BLOCK, k, n_loc), dtype=torch.float64).pin_memory()
-        out_dev = torch.empty((BLOCK, k, n_loc), dtype=torch.float64, device="cuda")
-        copy_stream = torch.cuda.Stream()
         reps = max(1, min(K, 200) // BLOCK)
 
         def one_block():
@@ -373,13 +371,7 @@ def run_product(args):
                     H.cycler_stats(c)
                     if not cyc.device_exchange:
                         dist.all_reduce(cyc.stats)
-                    H.cycler_update(c, out_dev[c])
-                    ev = torch.cuda.Event()
-                    ev.record(stream)
-                    copy_stream.wait_event(ev)
-                    with torch.cuda.stream(copy_stream):
-                        out_host[c].copy_(out_dev[c], non_blocking=True)
-            copy_stream.synchronize()
+                    H.cycler_update_host(c, out_host[c])      # D2H on the handle's copy stream
             H.sync()
 
         one_block()                                                     # warm-up

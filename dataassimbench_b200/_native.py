@@ -67,6 +67,7 @@ _SIGNATURES = {
     "dab_cycler_stats_exchange": (C.c_int, [_P]),
     "dab_cycler_stats_ptr": (_P, [_P]),
     "dab_cycler_update": (C.c_int, [_P, C.c_int, _P]),
+    "dab_cycler_update_host": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_export": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dab_cycler_buffer_ptr": (_P, [_P, C.c_int]),
@@ -201,6 +202,10 @@ class Handle:
 
     def cycler_update(self, cycle, out_analysis_dev=None):
         self._check(self._lib.dab_cycler_update(self._h, cycle, _ptr(out_analysis_dev)))
+
+    def cycler_update_host(self, cycle, out_analysis_host=None):
+        """As cycler_update, the slab of the analysis going to (pinned) host memory on the copy stream."""
+        self._check(self._lib.dab_cycler_update_host(self._h, cycle, _ptr(out_analysis_host)))
 
     def cycler_ipc_export(self, which):
         buf = C.create_string_buffer(IPC_HANDLE_BYTES)

@@ -772,6 +772,13 @@ int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev) {
   return cycler_update(h, cycle, nullptr, out_analysis_dev, nullptr);
 }
 
+int dab_cycler_update_host(dab_handle* h, int cycle, double* out_analysis_host) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready);
+  DAB_ARG(h, cycle >= 0 && cycle < h->cyc.cfg.n_cycles);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  return cycler_update(h, cycle, out_analysis_host, nullptr, nullptr);
+}
+
 int dab_cycler_run(dab_handle* h, int c0, int c1, double* out_analysis, double* out_traj) {
   DAB_ARG(h, h != nullptr && h->cyc.ready);
   Cycler& c = h->cyc;

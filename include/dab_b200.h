@@ -146,6 +146,9 @@ DAB_API int dab_cycler_stats(dab_handle* h, int cycle);
 DAB_API int dab_cycler_stats_exchange(dab_handle* h);
 DAB_API double* dab_cycler_stats_ptr(dab_handle* h);            /* dev, k*k+k doubles */
 DAB_API int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev /* nullable [k][N/world] */);
+/* Same, with this rank's slab of the analysis copied to (pinned) HOST memory on the handle's copy
+ * stream, overlapped with the following cycle; dab_sync() waits for it. */
+DAB_API int dab_cycler_update_host(dab_handle* h, int cycle, double* out_analysis_host /* nullable [k][N/world] */);
 /* Peer plumbing for the fused halo exchange and the statistics exchange (CUDA IPC, one process per
  * GPU): which = 0/1 selects the two background (Xb) buffers, which = 2 the statistics exchange buffer. */
 DAB_API int dab_cycler_ipc_export(dab_handle* h, int which, void* handle_out /* 64 bytes */);
