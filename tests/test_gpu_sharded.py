@@ -17,7 +17,7 @@ from test_gpu_kernels import cycler_case, run_gpu_cycler, rel_err
 from oracle import windows as o_win
 
 
-def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchange="host"):
+def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchange="host", host_out=False):
     S, dt = case['S'], case['dt']
     times = o_win.get_all_times(case['start'], case['window'], n_cycles)
     padded = np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, case['obs_times'], case['window'])))
@@ -46,6 +46,7 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchang
     stats = [torch.as_tensor(Dev(h.cycler_stats_ptr(), k * k + k), device='cuda') for h in hs]
     out = torch.empty((n_cycles, k, N), dtype=torch.float64, device='cuda')
     slab = [torch.empty((k, n_loc), dtype=torch.float64, device='cuda') for _ in range(world)]
+    slab_host = [torch.empty((k, n_loc), dtype=torch.float64).pin_memory() for _ in range(world)]
     for c in range(n_cycles):
         for h in hs:
             h.cycler_stats(c)
@@ -57,10 +58,13 @@ def run_emulated_ranks(case, N, k, n_cycles, sd, rho, stationary, world, exchang
                 s.copy_(total)
             torch.cuda.synchronize()
         for r, h in enumerate(hs):
-            h.cycler_update(c, slab[r])
+            if host_out:
+                h.cycler_update_host(c, slab_host[r])      # D2H on the handle's copy stream
+            else:
+                h.cycler_update(c, slab[r])
         for r, h in enumerate(hs):
             h.sync()
-            out[c, :, r * n_loc:(r + 1) * n_loc] = slab[r]
+            out[c, :, r * n_loc:(r + 1) * n_loc] = slab_host[r].cuda() if host_out else slab[r]
     final = np.empty((k, N))
     for r, h in enumerate(hs):
         part = np.empty((k, n_loc))
@@ -89,3 +93,13 @@ def test_sharded_equals_single_gpu(N, k, n_obs, n_cycles, S, stationary, world, 
     # same kernels, only the summation order of the k*k+k statistics differs between 1 and G ranks
     assert rel_err(out, ref) < 1e-10
     assert rel_err(final, ref_final) < 1e-9
+
+
+def test_sharded_update_host_returns_the_same_slabs():
+    """dab_cycler_update_host: the per-rank slab of every analysis copied to pinned host memory on the
+    copy stream gives the same bits as the device output of dab_cycler_update."""
+    N, k, n_obs, n_cycles, S, world = 4096, 16, 1200, 4, 20, 2
+    case = cycler_case(N, k, n_obs, n_cycles, S, 1.0, 1.02, True, seed=5)
+    out_d, fin_d = run_emulated_ranks(case, N, k, n_cycles, 1.0, 1.02, True, world, "device")
+    out_h, fin_h = run_emulated_ranks(case, N, k, n_cycles, 1.0, 1.02, True, world, "device", host_out=True)
+    assert np.array_equal(out_d, out_h) and np.array_equal(fin_d, fin_h)
