@@ -141,7 +141,7 @@ __device__ __forceinline__ void eig_small_body(const double* stats, int k, doubl
   double* G = sm;                              // ncol * LD, column-major
   double* aux = G + ncol * LD;                 // 6 * ncol
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inv_k = 1.0 / (double)k;
 
   if (empty_R) {                               // reference zero branch: T = U

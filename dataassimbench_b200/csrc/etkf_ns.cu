@@ -189,7 +189,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
                     double* __restrict__ Tout, int* __restrict__ info_out) {
   using C = NsCfg<KP, NW>;
   constexpr int ROWS = C::ROWS, MT = C::MT, LDS = C::LDS, NT = NW * 32;
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(128) double sm[];
   double* Zs = sm;                               // own rows of Z        [ROWS][LDS]
   double* Yts = Zs + ROWS * LDS;                 // own rows of Y^T
   double* Ts0 = Yts + ROWS * LDS;                // T[R,:]
@@ -505,7 +505,7 @@ __device__ __forceinline__ int swz64(int r, int j) {
 __global__ void __launch_bounds__(256, 1)
 ns_mc_transform_kernel(const double* __restrict__ stats, int k, double rho, double* __restrict__ ws,
                        double* __restrict__ Tout, int* __restrict__ info_out) {
-  constexpr int KP = 64, ROWS = 8, NT = 256, NW = 8, LDT = KP + 8, MAT = KP * KP;
+  constexpr int KP = 64, ROWS = 8, NT = 256, LDT = KP + 8, MAT = KP * KP;
   extern __shared__ __align__(128) double sm[];
   double* Bz = sm;                               // [2][MAT]  Z, swizzled, double-buffered
   double* Byt = sm + 2 * MAT;                    // [2][MAT]  Y^T
