@@ -68,6 +68,7 @@ _SIGNATURES = {
     "dab_cycler_stats_ptr": (_P, [_P]),
     "dab_cycler_update": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_update_host": (C.c_int, [_P, C.c_int, _P]),
+    "dab_cycler_set_truth": (C.c_int, [_P, _P, _P]),
     "dab_cycler_ipc_export": (C.c_int, [_P, C.c_int, _P]),
     "dab_cycler_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dab_cycler_buffer_ptr": (_P, [_P, C.c_int]),
@@ -202,6 +203,10 @@ class Handle:
 
     def cycler_update(self, cycle, out_analysis_dev=None):
         self._check(self._lib.dab_cycler_update(self._h, cycle, _ptr(out_analysis_dev)))
+
+    def cycler_set_truth(self, truth_dev, sse_out_dev):
+        """Score every analysis on the device: sse_out_dev[cycle] = sum_e (ensemble mean - truth[cycle])^2."""
+        self._check(self._lib.dab_cycler_set_truth(self._h, _ptr(truth_dev), _ptr(sse_out_dev)))
 
     def cycler_update_host(self, cycle, out_analysis_host=None):
         """As cycler_update, the slab of the analysis going to (pinned) host memory on the copy stream."""

@@ -54,6 +54,10 @@ struct Cycler {
   // statistics exchange over peer memory (world > 1): [2 parities][kMaxRanks] flags (256 bytes), then
   // [2 parities][world][k*k+k] slots; rank r writes slot r of every rank (stats_reduce_kernel)
   DevBuf xchg, xchg_ctr;
+  // optional on-device score of every analysis (dab_cycler_set_truth)
+  const double* truth = nullptr;           // [n_cycles][n_loc], device, caller-owned
+  double* sse_out = nullptr;               // [n_cycles], device, caller-owned
+  DevBuf sse_partial;
   unsigned long long xchg_seq = 0;
   cudaEvent_t ev_xa[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool copied_pending[2] = {false, false};
@@ -153,7 +157,7 @@ static void cycler_free(dab_handle* h) {
   c.xb_bytes = 0;
   c.obs_loc.release(); c.obs_val.release(); c.seg.release(); c.partial.release();
   c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
-  c.xchg.release(); c.xchg_ctr.release();
+  c.xchg.release(); c.xchg_ctr.release(); c.sse_partial.release();
   c.ready = false;
 }
 
@@ -547,6 +551,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     DAB_CUDA(h, cudaMemsetAsync(c.xchg_ctr.p, 0, c.xchg_ctr.bytes, h->stream));
   }
   c.xchg_seq = 0;
+  c.truth = nullptr; c.sse_out = nullptr;
   DAB_CUDA(h, cudaStreamSynchronize(h->stream));               // host vectors go out of scope
   // ---- measure, don't guess: pick the forecast kernel's CTA width for this shape with CUDA events
   c.l96_T = 0;
@@ -710,6 +715,11 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   prof_mark(h, PROF_TRANSFORM);
   h->launches += 2;
   const double* xa = c.ext[eb].as<double>() + c.halo_l;
+  if (c.truth != nullptr && c.sse_out != nullptr) {          // score this analysis on the device
+    DAB_CUDA(h, mean_sqerr_launch(xa, c.ld_e, k, c.n_loc, c.truth + (size_t)cycle * c.n_loc,
+                                  c.sse_partial.as<double>(), c.sse_out + cycle, h->stream));
+    h->launches += 2;
+  }
   if (out_host) {
     DAB_CUDA(h, cudaEventRecord(c.ev_xa[eb], h->stream));
     DAB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, c.ev_xa[eb], 0));
@@ -770,6 +780,16 @@ int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev) {
   DAB_ARG(h, cycle >= 0 && cycle < h->cyc.cfg.n_cycles);
   DAB_CUDA(h, cudaSetDevice(h->device));
   return cycler_update(h, cycle, nullptr, out_analysis_dev, nullptr);
+}
+
+int dab_cycler_set_truth(dab_handle* h, const double* truth_dev, double* sse_out_dev) {
+  DAB_ARG(h, h != nullptr && h->cyc.ready);
+  DAB_ARG(h, (truth_dev == nullptr) == (sse_out_dev == nullptr));
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  if (truth_dev != nullptr) DAB_CUDA(h, h->cyc.sse_partial.reserve(sizeof(double) * 512));
+  h->cyc.truth = truth_dev;
+  h->cyc.sse_out = sse_out_dev;
+  return 0;
 }
 
 int dab_cycler_update_host(dab_handle* h, int cycle, double* out_analysis_host) {

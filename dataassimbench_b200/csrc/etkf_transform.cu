@@ -103,6 +103,56 @@ transform_kernel(const TransformArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// On-device score of an analysis (the step after the path, SURVEY.md 8f: dabench.metrics rmse/mse
+// of the ensemble mean, dabench/metrics/_deterministic.py:43-72, evaluated without copying the
+// analysis to the host): sse = sum over this rank's columns of (mean_j Xa[j][e] - truth[e])^2.
+// Two fixed-order stages (per-CTA partials, then one warp): bit-reproducible, no atomics.
+constexpr int kSseCtas = 296;
+
+__global__ void __launch_bounds__(256)
+mean_sqerr_kernel(const double* __restrict__ xa, long long ld, int k, long long n, const double* __restrict__ truth,
+                  double* __restrict__ partial) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const double inv_k = 1.0 / (double)k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    double m = 0.0;
+    for (int j = 0; j < k; ++j) m += xa[(long long)j * ld + e];
+    const double d = m * inv_k - truth[e];
+    acc = fma(d, d, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) *out = t;
+}
+
+cudaError_t mean_sqerr_launch(const double* xa, long long ld, int k, long long n, const double* truth,
+                              double* partial /* kSseCtas doubles */, double* out, cudaStream_t st) {
+  long long g = (n + 255) / 256;
+  if (g > kSseCtas) g = kSseCtas;
+  if (g < 1) g = 1;
+  mean_sqerr_kernel<<<(unsigned)g, 256, 0, st>>>(xa, ld, k, n, truth, partial);
+  sum_partials_kernel<<<1, 32, 0, st>>>(partial, (int)g, out);
+  return cudaGetLastError();
+}
+
 cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st) {
   const int k8 = (a.k + 7) / 8 <= 2 ? 2 : ((a.k + 7) / 8 <= 4 ? 4 : ((a.k + 7) / 8 <= 8 ? 8 : 16));
   const long long n_cols = a.n_loc + a.halo_l + a.halo_r;

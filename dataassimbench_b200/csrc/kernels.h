@@ -68,6 +68,9 @@ struct TransformArgs {
   int halo_l, halo_r, k, rank;
 };
 cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st);
+// sum over the columns of (ensemble mean - truth)^2, fixed summation order; partial: 296 doubles
+cudaError_t mean_sqerr_launch(const double* xa, long long ld, int k, long long n, const double* truth,
+                              double* partial, double* out, cudaStream_t st);
 
 // etkf_batched.cu: one CTA per experiment, whole experiment in one launch
 struct BatchedArgs {

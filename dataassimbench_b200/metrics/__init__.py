@@ -2,7 +2,7 @@
 used to evaluate the 1 % time-mean-RMSE parity criterion."""
 import numpy as np
 
-__all__ = ['pearson_r', 'rmse', 'mse', 'mae']
+__all__ = ['pearson_r', 'rmse', 'mse', 'mae', 'rmse_from_sse']
 
 
 def mse(predictions, targets):
@@ -22,3 +22,9 @@ def pearson_r(predictions, targets):
     p = np.asarray(predictions) - np.mean(predictions)
     t = np.asarray(targets) - np.mean(targets)
     return np.sum(t * p) / (np.sqrt(np.sum(t * t)) * np.sqrt(np.sum(p * p)))
+
+
+def rmse_from_sse(sse, n):
+    """RMSE from the per-cycle sums of squared errors the cycler accumulates on the device
+    (`dab_cycler_set_truth`; summed over the ranks first when the grid is sharded)."""
+    return np.sqrt(np.asarray(sse, dtype=np.float64) / n)

@@ -146,6 +146,14 @@ DAB_API int dab_cycler_stats(dab_handle* h, int cycle);
 DAB_API int dab_cycler_stats_exchange(dab_handle* h);
 DAB_API double* dab_cycler_stats_ptr(dab_handle* h);            /* dev, k*k+k doubles */
 DAB_API int dab_cycler_update(dab_handle* h, int cycle, double* out_analysis_dev /* nullable [k][N/world] */);
+/* Optional on-device score of every analysis (the step after the path: dabench.metrics mse/rmse of
+ * the ensemble mean, dabench/metrics/_deterministic.py:43-72, without copying analyses to the
+ * host): with truth_dev [n_cycles][N/world] (this rank's columns of the truth at the analysis
+ * times) registered, every update also writes
+ *   sse_out_dev[cycle] = sum over this rank's columns of (mean_j Xa[j][e] - truth[cycle][e])^2
+ * (fixed summation order).  rmse = sqrt(sum over ranks / N).  Both NULL switches it off; the
+ * pointers must stay valid until then (dab_cycler_setup also switches it off). */
+DAB_API int dab_cycler_set_truth(dab_handle* h, const double* truth_dev, double* sse_out_dev);
 /* Same, with this rank's slab of the analysis copied to (pinned) HOST memory on the handle's copy
  * stream, overlapped with the following cycle; dab_sync() waits for it. */
 DAB_API int dab_cycler_update_host(dab_handle* h, int cycle, double* out_analysis_host /* nullable [k][N/world] */);

@@ -415,3 +415,30 @@ def test_cycle_host_entry_point(H):
                       np.ascontiguousarray(case['sysidx']), padded, out)
     assert rel_err(out, ref) < 1e-9
     assert H.kernel_launches() == 5 * n_cycles
+
+
+@pytest.mark.parametrize("N,k", [(4096, 16), (1000, 33)])
+def test_cycler_scores_analyses_on_device(H, N, k):
+    """dab_cycler_set_truth: the sum of squared errors of the ensemble-mean analysis against a
+    device-resident truth, per cycle, equals dabench.metrics-style mse of the returned analyses."""
+    from dataassimbench_b200 import metrics
+    n_cycles, S, sd, rho = 5, 20, 1.0, 1.02
+    case = cycler_case(N, k, N // 3, n_cycles, S, sd, rho, True, seed=N)
+    times = o_win.get_all_times(case['start'], case['window'], n_cycles)
+    padded = np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, case['obs_times'], case['window'])))
+    cfg = _native.CycleConfig(system_dim=N, ensemble_dim=k, n_steps=S, model_dt=case['dt'], forcing=8.0, rho=rho,
+                              obs_error_sd=sd, n_obs_times=case['vals'].shape[0], n_obs=case['vals'].shape[1],
+                              stationary=1, n_cycles=n_cycles, t_pad=padded.shape[1], rank=0, world=1)
+    H.cycler_setup(cfg, np.ascontiguousarray(case['vals']), np.ascontiguousarray(case['sysidx']), padded)
+    H.cycler_set_state(np.ascontiguousarray(case['X0']), True)
+    truth = np.ascontiguousarray(case['truth'][::S][:n_cycles])            # truth at the analysis times
+    truth_dev = dev(truth)
+    sse = torch.full((n_cycles,), float('nan'), dtype=torch.float64, device='cuda')
+    H.cycler_set_truth(truth_dev, sse)
+    out = torch.empty((n_cycles, k, N), dtype=torch.float64).pin_memory()
+    H.cycler_run(0, n_cycles, out)
+    H.sync()
+    H.cycler_set_truth(None, None)
+    got = metrics.rmse_from_sse(sse.cpu().numpy(), N)
+    ref = np.array([metrics.rmse(out[c].numpy().mean(axis=0), truth[c]) for c in range(n_cycles)])
+    assert np.max(np.abs(got - ref) / ref) < 1e-12
