@@ -142,3 +142,39 @@ def test_mini_dataset_surface():
     s = _xr.MiniDataset({'x': (('cycle', 'ensemble', 'cycle_timestep', 'index'), np.zeros((2, 3, 5, 4)))})
     st = s.stack(time=['cycle', 'cycle_timestep']).transpose('time', ...)
     assert st['x'].shape == (10, 3, 4)
+
+
+def test_cycle_batched_marshalling(monkeypatch):
+    """cycle_batched hands the C ABI one observation set for a sweep (flag bits 0 and 1 of
+    shared_index) and per-experiment arrays otherwise; no kernel runs here (fake handle)."""
+    from dataassimbench_b200 import _runtime
+    from dataassimbench_b200.dacycler import cycle_batched
+    N, k, n_cycles, S = 8, 4, 5, 10
+    ds, obs, model, init = _experiment(N, k, n_cycles, S)
+    calls = []
+
+    class Fake:
+        def etkf_cycle_batched(self, cfg, batch, rho, x0, vals, idx, shared, padded, out, mean, fin):
+            calls.append(dict(batch=batch, rho=np.array(rho), x0=x0.shape, vals=vals.shape, idx=idx.shape,
+                              shared=shared, out=None if out is None else out.shape,
+                              mean=None if mean is None else mean.shape))
+            for a in (out, mean):
+                if a is not None:
+                    a[...] = 0.0
+    monkeypatch.setattr(_runtime, 'handle', lambda: Fake())
+    rhos = [1.0, 1.1, 1.3]
+    cyclers = [dab.dacycler.ETKF(N, 0.01, model, ensemble_dim=k, multiplicative_inflation=r) for r in rhos]
+    res = cycle_batched(cyclers, init, 0.0, obs, n_cycles, analysis_window=0.1)            # one obs set
+    assert res['x'].shape == (3, n_cycles, k, N)
+    c = calls[-1]
+    assert c['shared'] == 3 and c['vals'] == (n_cycles + 1, 3) and c['idx'] == (n_cycles + 1, 3)
+    assert c['batch'] == 3 and np.allclose(c['rho'], rhos) and c['x0'] == (3, k, N)
+    res = cycle_batched(cyclers, [init] * 3, 0.0, [obs] * 3, n_cycles, analysis_window=0.1,
+                        return_mean_only=True)                                              # a list of obs sets
+    assert res['x_mean'].shape == (3, n_cycles, N)
+    c = calls[-1]
+    assert c['shared'] == 0 and c['vals'] == (3, n_cycles + 1, 3) and c['idx'] == (3, n_cycles + 1, 3)
+    with pytest.raises(ValueError):                       # experiments of a batch must share their shape
+        other = dab.dacycler.ETKF(N, 0.02, dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.02)),
+                                  ensemble_dim=k)
+        cycle_batched([cyclers[0], other], init, 0.0, obs, n_cycles, analysis_window=0.1)
