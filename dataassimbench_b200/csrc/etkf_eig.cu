@@ -90,7 +90,7 @@ cudaError_t eig_transform_launch(const double* stats, int k, double rho, int emp
     if (method != kEigJacobi && lam_out == nullptr && ns_ws != nullptr) {
       cudaError_t e = ns_transform_launch(stats, k, rho, ns_ws, T, info_out, st);
       if (e != cudaSuccess) return e;
-      if (k <= 64) return cudaGetLastError();    // the fallback for k <= 64 lives inside that kernel
+      if (ns_fallback_in_kernel(k)) return cudaGetLastError();    // the fallback for k <= 64 lives inside that kernel
       run_flag = reinterpret_cast<const int*>(ns_ws);
     }
     const int threads = 32 * (((k + 7) & ~7) / 8);

@@ -12,7 +12,7 @@
 // KNOWN interval [l0^2, 1], the coupled Newton-Schulz iteration (Higham, Functions of Matrices,
 // eq. 6.35 -- the numerically stable ordering Y <- Y T, Z <- T Z) with the optimal interval
 // scaling of Chen & Chow (2014) converges in a number of steps that is known in advance:
-//   M = Z Y,  T = (alpha/2)(3 I - alpha^2 M),  Y <- Y T,  Z <- T Z,   Z -> (A'/s)^{-1/2}
+//   M = Z Y,  T = (alpha/2)(3 I - alpha^2 M),  Y <- Y T^T,  Z <- T Z,   Z -> (A'/s)^{-1/2}
 //   alpha^2 = 3/(1 + l + l^2),  l <- alpha l (3 - alpha^2 l^2)/2
 //   (4-5 steps on the bench workloads; 9 at cond 1e3, 12 at cond 3e6)
 // Everything is k x k x k GEMM work, so -- unlike Jacobi, whose rotation chain is serial -- it
@@ -22,11 +22,13 @@
 // there).  The common structure:
 //   * a cluster of 8 CTAs; CTA r owns rows R = [ROWS r, ROWS (r+1)) of Z and of Y^T (= columns
 //     of Y), ROWS = KP/8;
-//   * per step every CTA forms FOUR row-strip products on the FP64 tensor core (DMMA.8x8x4):
-//       M[R,:] = Z[R,:] Y          and  M[:,R]^T = Y^T[R,:] Z^T        (phase 1)
-//       Z'[R,:] = T[R,:] Z         and  Y'^T[R,:] = T[:,R]^T Y^T       (phase 2)
-//     (both the row AND the column strip of M are computed: using M[R,:]^T for M[:,R] is the
-//     unstable T Y ordering -- measured divergence at cond >= 1e5);
+//   * per step every CTA forms THREE row-strip products on the FP64 tensor core (DMMA.8x8x4):
+//       M[R,:] = Z[R,:] Y,   T[R,:] = c1 I + c2 M[R,:]                 (phase 1)
+//       Z'[R,:] = T[R,:] Z   and   Y'^T[R,:] = T[R,:] Y^T              (phase 2)
+//     i.e. Z <- T Z and Y <- Y T^T, so that M = Z Y goes to T M T^T -- a congruence, the property
+//     that makes the coupled iteration stable (Y <- T Y instead, M -> T Z T Y, diverges at cond
+//     >= 1e5; tests/test_ns_algorithm_cpu.py).  Storing Y transposed makes both updates
+//     left-multiplications by the SAME row strip of T;
 //   * the A operand of every product is the CTA's own strip in shared memory; the B operand is
 //     the full matrix, streamed as DMMA fragments straight from L2 (ld.global.cg, 16-byte loads,
 //     every fetched sector fully used) and prefetched into registers a whole unit ahead;
@@ -80,7 +82,7 @@ struct NsCfg {
   static constexpr int LDS = KP + 8;             // strip stride: LDS.128 fragments conflict-free
   static constexpr int NT8 = KP / 8;             // 8-column tiles across
   static constexpr int NT16 = KP / 16;           // interleaved tile pairs across
-  static constexpr int J1 = 2 * NT8 / NW;        // phase-1 jobs per warp (product, tile)
+  static constexpr int J1 = NT8 / NW;            // phase-1 jobs per warp (tiles of M[R,:])
   static constexpr int V1 = KP / 8;              // 16-byte B loads per phase-1 job
   static constexpr int J2 = 2 * NT16 / NW;       // phase-2 jobs per warp (product, tile pair)
   static constexpr int V2 = KP / 4;              // 16-byte B loads per phase-2 job
@@ -211,14 +213,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
   double delta_k, s, lower;
   const bool ok = ns_bounds<KP, NT>(stats, k, shift, red_sq, red_abs, red_g, delta_k, s, lower);
   if (!ok) {                                     // uniform over the cluster: same inputs, same code
-    if (KP == 64) {                              // k <= 64: CTA 0 IS the Jacobi eigensolver's CTA (8 warps, 64 columns)
-      if (rank == 0) {
-        if (tid == 0) flags[0] = 0;
-        eig_block_body<8>(stats, k, 64, rho, Tout, nullptr, info_out, 0, sm);
-      }
-    } else if (rank == 0 && tid == 0) {
-      flags[0] = 1;                              // k > 64: the eigensolver kernel enqueued behind this one runs
-    }
+    if (rank == 0 && tid == 0) flags[0] = 1;     // the eigensolver kernel enqueued behind this one runs
     return;
   }
   const double inv_s = 1.0 / s;
@@ -334,7 +329,7 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
       for (int v = 0; v < C::UV; v += 2) {
         const int g = C::UV * u + v, ji = g / C::V2, ks = g % C::V2;
         const int jg = warp + NW * ji, prod = jg / C::NT16;
-        const double* As = prod == 0 ? Ts0 : Ts1;
+        const double* As = Ts0;                  // T[R,:] serves both products
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           const double2 a = *reinterpret_cast<const double2*>(As + (8 * m + fm) * LDS + 8 * (ks >> 1) + 2 * q);
@@ -577,45 +572,42 @@ ns_mc_transform_kernel(const double* __restrict__ stats, int k, double rho, doub
     const double* Z = Bz + par * MAT;
     const double* Yt = Byt + par * MAT;
 
-    // ---- phase 1: warp w -> tile w of M[R,:] = Z[R,:] Y and of M[:,R]^T = Yt[R,:] Z^T
-    double m0[2] = {0.0, 0.0}, m1[2] = {0.0, 0.0};
+    // ---- phase 1: warp w -> tile w of M[R,:] = Z[R,:] Y  (B[j][n] = Yt[n][j]: row-wise access of Yt)
+    double m0 = 0.0, m1 = 0.0;
     {
-      const int rb = 8 * warp + fm;              // B row (transposed access): column 8w+fm of the product
+      const int rb = 8 * warp + fm;              // row of Yt = column 8w+fm of the product
       const int fa = (((R0 + fm) & 1) << 2) ^ ((((R0 + fm) >> 1) & 3) << 1);
       const int fb = ((rb & 1) << 2) ^ (((rb >> 1) & 3) << 1);
-      const double* a0p = Z + (R0 + fm) * KP;    // A = Z[R,:],  B[j][n] = Yt[n][j]
-      const double* a1p = Yt + (R0 + fm) * KP;   // A = Yt[R,:], B[j][n] = Z[n][j]
-      const double* b0p = Yt + rb * KP;
-      const double* b1p = Z + rb * KP;
+      const double* ap = Z + (R0 + fm) * KP;
+      const double* bp = Yt + rb * KP;
+      double e0 = 0.0, e1 = 0.0;                 // two accumulation chains (even / odd 8-column groups)
 #pragma unroll
-      for (int kk = 0; kk < KP / 8; ++kk) {
-        const int c = 4 * kk + q;
-        const double2 a0 = *reinterpret_cast<const double2*>(a0p + ((c ^ fa) << 1));
-        const double2 b0 = *reinterpret_cast<const double2*>(b0p + ((c ^ fb) << 1));
-        const double2 a1 = *reinterpret_cast<const double2*>(a1p + ((c ^ fa) << 1));
-        const double2 b1 = *reinterpret_cast<const double2*>(b1p + ((c ^ fb) << 1));
-        dmma884(m0[0], m1[0], a0.x, b0.x); dmma884(m0[1], m1[1], a1.x, b1.x);
-        dmma884(m0[0], m1[0], a0.y, b0.y); dmma884(m0[1], m1[1], a1.y, b1.y);
+      for (int kk = 0; kk < KP / 8; kk += 2) {
+        const int c = 4 * kk + q, d = c + 4;
+        const double2 a0 = *reinterpret_cast<const double2*>(ap + ((c ^ fa) << 1));
+        const double2 b0 = *reinterpret_cast<const double2*>(bp + ((c ^ fb) << 1));
+        const double2 a1 = *reinterpret_cast<const double2*>(ap + ((d ^ fa) << 1));
+        const double2 b1 = *reinterpret_cast<const double2*>(bp + ((d ^ fb) << 1));
+        dmma884(m0, m1, a0.x, b0.x); dmma884(e0, e1, a1.x, b1.x);
+        dmma884(m0, m1, a0.y, b0.y); dmma884(e0, e1, a1.y, b1.y);
       }
+      m0 += e0; m1 += e1;
     }
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {                // T = c1 I + c2 M
-      double* Ts = g == 0 ? Ts0 : Ts1;
+    {                                            // T[R,:] = c1 I + c2 M[R,:]
       const int row = R0 + fm, col = 8 * warp + 2 * q;
       double2 t;
-      t.x = fma(c2, m0[g], row == col ? c1 : 0.0);
-      t.y = fma(c2, m1[g], row == col + 1 ? c1 : 0.0);
-      *reinterpret_cast<double2*>(Ts + fm * LDT + col) = t;
+      t.x = fma(c2, m0, row == col ? c1 : 0.0);
+      t.y = fma(c2, m1, row == col + 1 ? c1 : 0.0);
+      *reinterpret_cast<double2*>(Ts0 + fm * LDT + col) = t;
     }
     __syncthreads();
-    NS_TICK(2);
 
-    // ---- phase 2: warps 0-3 -> Z'[R,:] = T[R,:] Z, warps 4-7 -> Y'^T[R,:] = T[:,R]^T Yt; a warp
+    // ---- phase 2: warps 0-3 -> Z'[R,:] = T[R,:] Z, warps 4-7 -> Y'^T[R,:] = T[R,:] Y^T; a warp
     //      takes the interleaved pair of 8-column tiles t (columns 16t+2i and 16t+2i+1)
     const int prod = warp >> 2, t = warp & 3;
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     {
-      const double* As = prod == 0 ? Ts0 : Ts1;
+      const double* As = Ts0;
       const double* B = prod == 0 ? Z : Yt;
 #pragma unroll
       for (int kk = 0; kk < KP / 8; ++kk) {
@@ -712,7 +704,8 @@ ns_mc_transform_kernel(const double* __restrict__ stats, int k, double rho, doub
 }
 
 size_t ns_ws_bytes(int k) {
-  const size_t kp = k <= 64 ? 64 : 128;
+  (void)k;
+  const size_t kp = 128;                       // room for the padded-to-128 streaming kernel in every case
   return 16 + sizeof(double) * 4 * kp * kp;
 }
 
@@ -724,7 +717,6 @@ cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, doub
   size_t strips = sizeof(double) * 4 * C::ROWS * C::LDS;
   size_t fin = sizeof(double) * ((size_t)KP * C::LDF + 4 * KP + C::ROWS + 8);
   size_t smem = strips > fin ? strips : fin;
-  if (KP == 64 && smem < eig_smem_bytes(64)) smem = eig_smem_bytes(64);   // in-kernel Jacobi fallback
   auto kern = ns_transform_kernel<KP, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -740,6 +732,16 @@ cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, doub
   return cudaLaunchKernelEx(&cfg, kern, stats, k, rho, ws, T, info_out);
 }
 }  // namespace
+
+// DAB_NS_MC=0: the L2-streaming kernel (padded to 128) for k <= 64 too
+static int ns_use_mc() {
+  static int use_mc = -1;
+  if (use_mc < 0) { const char* ev = getenv("DAB_NS_MC"); use_mc = ev ? (atoi(ev) != 0) : 1; }
+  return use_mc;
+}
+
+// true when the Jacobi fallback runs inside the Newton-Schulz kernel (no second launch needed)
+bool ns_fallback_in_kernel(int k) { return k <= 64 && ns_use_mc() == 1; }
 
 static cudaError_t ns_mc_launch(const double* stats, int k, double rho, double* ws, double* T, int* info_out,
                                 cudaStream_t st) {
@@ -760,11 +762,8 @@ static cudaError_t ns_mc_launch(const double* stats, int k, double rho, double* 
 
 cudaError_t ns_transform_launch(const double* stats, int k, double rho, double* ws, double* T,
                                 int* info_out, cudaStream_t st) {
-  static int use_mc = -1;                        // DAB_NS_MC=0: the L2-streaming kernel for k <= 64 too
-  if (use_mc < 0) { const char* ev = getenv("DAB_NS_MC"); use_mc = ev ? atoi(ev) : 1; }
-  if (k <= 64 && use_mc) return ns_mc_launch(stats, k, rho, ws, T, info_out, st);
-  if (k <= 64) return ns_launch_t<64, 8>(stats, k, rho, ws, T, info_out, st);
-  return ns_launch_t<128, 8>(stats, k, rho, ws, T, info_out, st);
+  if (k <= 64 && ns_use_mc()) return ns_mc_launch(stats, k, rho, ws, T, info_out, st);
+  return ns_launch_t<128, 8>(stats, k, rho, ws, T, info_out, st);   // k <= 64 padded to 128 with DAB_NS_MC=0
 }
 
 }  // namespace dab

@@ -54,6 +54,7 @@ cudaError_t eig_transform_launch(const double* stats, int k, double rho, int emp
                                  double* lam_out, int* info_out, double* ns_ws, int method,
                                  cudaStream_t st);
 size_t ns_ws_bytes(int k);
+bool ns_fallback_in_kernel(int k);
 cudaError_t ns_transform_launch(const double* stats, int k, double rho, double* ws, double* T,
                                 int* info_out, cudaStream_t st);
 
