@@ -468,7 +468,8 @@ def run_product(args):
                          "between reuses" % (N * k * 8 / 1e6),
                    "experiment": "%d-cycle run from a fresh ensemble, repeated; reset copy inside the "
                                  "timed region" % BLOCK,
-                   "parallelism": "grid-sharded x%d" % world if world > 1 else "single GPU"},
+                   "parallelism": "grid-sharded x%d" % world if world > 1 else "single GPU",
+                   "forecast_shape": dict(zip(("code", "launches_per_window"), H.cycler_forecast_shape()))},
         "member_steps_per_s": cps * k * S,
         "point_steps_per_s": cps * k * S * N,
         "all_finite": final,

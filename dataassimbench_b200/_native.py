@@ -76,6 +76,7 @@ _SIGNATURES = {
     "dab_cycler_stream": (_P, [_P]),
     "dab_cycler_background_ptr": (_P, [_P]),
     "dab_cycler_kernel_launches": (C.c_int, [_P]),
+    "dab_cycler_forecast_shape": (C.c_int, [_P]),
     "dab_cycler_set_profiling": (C.c_int, [_P, C.c_int]),
     "dab_cycler_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "dab_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -200,6 +201,11 @@ class Handle:
 
     def cycler_stats_ptr(self):
         return self._lib.dab_cycler_stats_ptr(self._h)
+
+    def cycler_forecast_shape(self):
+        """(shape code, launches per window) the autotuner picked for the forecast kernel."""
+        v = self._lib.dab_cycler_forecast_shape(self._h)
+        return v // 10, v % 10
 
     def cycler_update(self, cycle, out_analysis_dev=None):
         self._check(self._lib.dab_cycler_update(self._h, cycle, _ptr(out_analysis_dev)))

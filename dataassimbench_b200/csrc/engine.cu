@@ -682,6 +682,7 @@ double* dab_cycler_stats_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cy
 void* dab_cycler_stream(dab_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 double* dab_cycler_background_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.xb[h->cyc.cur] : nullptr; }
 int dab_cycler_kernel_launches(dab_handle* h) { return h ? (int)h->launches : 0; }
+int dab_cycler_forecast_shape(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.l96_T * 10 + h->cyc.l96_chunks : 0; }
 
 // eig (K4) + transform (K5, fused halo exchange) + forecast (K1).  The analysis of this cycle is
 // left in ext[cycle & 1]; out_host / out_dev optionally receive its slab part.

@@ -168,7 +168,11 @@ DAB_API int dab_cycler_set_peer(dab_handle* h, int peer_rank, int which, const d
 DAB_API void* dab_cycler_stream(dab_handle* h);                  /* cudaStream_t the cycler enqueues on */
 /* device pointers of the current background / last analysis (extended layout) for tests */
 DAB_API double* dab_cycler_background_ptr(dab_handle* h);
-DAB_API int dab_cycler_kernel_launches(dab_handle* h);           /* kernels launched since setup */
+DAB_API int dab_cycler_kernel_launches(dab_handle* h);
+/* What the setup-time autotuner picked for the forecast kernel: 10 * shape code + launches per window
+ * (shape code: CTA width for 8 points per thread, 1000 * c + width with c = 12/16/17 for 12 / 16 /
+ * 16-in-170-registers points per thread; 0 = untuned heuristic). */
+DAB_API int dab_cycler_forecast_shape(dab_handle* h);           /* kernels launched since setup */
 
 /* Measurement aids (bench.py): per-kernel CUDA-event timing on the cycler's stream.
  * ms_out[5]/count_out[5]: contraction, reduction, eigensolver, transform, forecast. */
