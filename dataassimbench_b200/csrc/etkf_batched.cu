@@ -28,6 +28,10 @@ namespace dab {
 #define BT_TICK(i) do { } while (0)
 #endif
 
+__host__ __device__ inline int batched_state_doubles(int k, int N, int ppt, bool blocked) {
+  return blocked ? ppt * 256 : k * (N + 3);
+}
+
 // PPT points per thread.  BLOCKED: a thread owns PPT CONSECUTIVE points of one member
 // (ceil(N/PPT) threads per member, k * ceil(N/PPT) <= 256) and keeps them in registers through the
 // RK4 window, so a stage reads only 3 neighbour values from shared memory.  Otherwise (shapes that do
@@ -37,14 +41,23 @@ template <int PPT, bool BLOCKED>
 __global__ void __launch_bounds__(256)
 etkf_batched_kernel(const BatchedArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int k = a.k, N = a.N, NP = N + 3;              // member row stride (3 spare slots: odd strides spread the banks)
-  const int kN = k * N, nyp = a.t_pad * a.n_obs;
+  const int k = a.k, N = a.N, NP = N + 3;
+  const int kN = k * N, nyp = a.t_pad * a.n_obs, nys = nyp | 1;   // odd row stride of Ys: conflict-free columns
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
-  double* S0 = sm;                                      // k*NP  state / RK stage buffers (ping-pong)
-  double* S1 = S0 + k * NP;
-  double* Ys = S1 + k * NP;                             // k*nyp centred Yb^T
-  double* dv = Ys + k * nyp;                            // nyp   innovations
+  const int tpm = (N + PPT - 1) / PPT;                  // BLOCKED: threads per member
+  // State layout in shared memory.  BLOCKED: thread-major -- point q of thread t at q*256 + t, so
+  // that the stores of a stage and the three neighbour loads are conflict-free (member-major rows
+  // put consecutive threads PPT doubles apart: 4-way conflicts, 2.1e9 excess wavefronts in the
+  // first ncu capture).  Otherwise member-major rows of N + 3.
+  auto sidx = [&](int j, int i) -> int {
+    return BLOCKED ? (i % PPT) * 256 + j * tpm + i / PPT : j * NP + 2 + i;
+  };
+  const int state_doubles = batched_state_doubles(k, N, PPT, BLOCKED);
+  double* S0 = sm;                                      // state / RK stage buffers (ping-pong)
+  double* S1 = S0 + state_doubles;
+  double* Ys = S1 + state_doubles;                      // k*nyp centred Yb^T
+  double* dv = Ys + k * nys;                            // nyp   innovations
   double* stats = dv + nyp;                             // k*k + k
   double* Tm = stats + k * k + k;                       // k*k
   double* ew = Tm + k * k;                              // eigensolver workspace
@@ -59,7 +72,6 @@ etkf_batched_kernel(const BatchedArgs a) {
   // and the offsets of its three stencil neighbours on the periodic ring (computed once: the RK4
   // stage below is then 4 loads, the 17-instruction arithmetic of l96_forecast.cu and 1 store)
   int off[PPT], mem[PPT], col[PPT], gix[PPT], o_m2[PPT], o_m1[PPT], o_p1[PPT];
-  const int tpm = (N + PPT - 1) / PPT;                  // BLOCKED: threads per member
   int npts = 0;                                         // BLOCKED: valid points of this thread
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
@@ -75,11 +87,10 @@ etkf_batched_kernel(const BatchedArgs a) {
       j = valid ? p / N : 0; i = p - j * N;
     }
     if (!valid) { j = 0; i = 0; }
-    const int base = j * NP + 2;
-    mem[q] = j; col[q] = i; gix[q] = j * N + i; off[q] = valid ? base + i : -1;
-    o_m2[q] = base + (i >= 2 ? i - 2 : i - 2 + N);
-    o_m1[q] = base + (i >= 1 ? i - 1 : N - 1);
-    o_p1[q] = base + (i + 1 < N ? i + 1 : 0);
+    mem[q] = j; col[q] = i; gix[q] = j * N + i; off[q] = valid ? sidx(j, i) : -1;
+    o_m2[q] = sidx(j, i >= 2 ? i - 2 : i - 2 + N);
+    o_m1[q] = sidx(j, i >= 1 ? i - 1 : N - 1);
+    o_p1[q] = sidx(j, i + 1 < N ? i + 1 : 0);
   }
   auto put = [&](double* S, int q, double v) { S[off[q]] = v; };
 
@@ -111,12 +122,12 @@ etkf_batched_kernel(const BatchedArgs a) {
       }
       double sum = 0.0;
       for (int j = 0; j < k; ++j) {
-        const double v = loc >= 0 ? cur[j * NP + 2 + loc] : 0.0;
-        Ys[j * nyp + r] = v;
+        const double v = loc >= 0 ? cur[sidx(j, loc)] : 0.0;
+        Ys[j * nys + r] = v;
         sum += v;
       }
       const double ybar = sum * inv_k;
-      for (int j = 0; j < k; ++j) Ys[j * nyp + r] = loc >= 0 ? Ys[j * nyp + r] - ybar : 0.0;
+      for (int j = 0; j < k; ++j) Ys[j * nys + r] = loc >= 0 ? Ys[j * nys + r] - ybar : 0.0;
       dv[r] = loc >= 0 ? y - ybar : 0.0;
     }
     __syncthreads();
@@ -126,10 +137,10 @@ etkf_batched_kernel(const BatchedArgs a) {
       double s = 0.0;
       if (e < k * k) {
         const int p = e / k, q = e - p * k;
-        for (int r = 0; r < nyp; ++r) s = fma(Ys[p * nyp + r], Ys[q * nyp + r], s);
+        for (int r = 0; r < nyp; ++r) s = fma(Ys[p * nys + r], Ys[q * nys + r], s);
       } else {
         const int p = e - k * k;
-        for (int r = 0; r < nyp; ++r) s = fma(Ys[p * nyp + r], dv[r], s);
+        for (int r = 0; r < nyp; ++r) s = fma(Ys[p * nys + r], dv[r], s);
       }
       stats[e] = s * r_inv;
     }
@@ -151,7 +162,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       double v = 0.0;
       if (off[q] >= 0) {
         const int j = mem[q], i = col[q];
-        for (int m = 0; m < k; ++m) v = fma(Tm[m * k + j], cur[m * NP + 2 + i], v);
+        for (int m = 0; m < k; ++m) v = fma(Tm[m * k + j], cur[sidx(m, i)], v);
       }
       x[q] = v;
     }
@@ -170,7 +181,7 @@ etkf_batched_kernel(const BatchedArgs a) {
       double* om = a.out_mean + ((long long)b * a.n_cycles + c) * N;
       for (int i = tid; i < N; i += 256) {
         double s = 0.0;
-        for (int j = 0; j < k; ++j) s += cur[j * NP + 2 + i];
+        for (int j = 0; j < k; ++j) s += cur[sidx(j, i)];
         om[i] = s * inv_k;
       }
     }
@@ -253,9 +264,21 @@ etkf_batched_kernel(const BatchedArgs a) {
   }
 }
 
+// the point mapping the launch will use: blocked with the fewest points per thread that fits 256
+// threads, else round-robin
+static void batched_mapping(int k, int N, int* ppt, bool* blocked) {
+  for (int p = 4; p <= 16; p *= 2)
+    if ((long long)k * ((N + p - 1) / p) <= 256) { *ppt = p; *blocked = true; return; }
+  const int r = (k * N + 255) / 256;
+  *ppt = r <= 4 ? 4 : (r <= 8 ? 8 : 16);
+  *blocked = false;
+}
+
 size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs) {
   const int nyp = t_pad * n_obs;
-  size_t d = 2 * (size_t)k * (N + 3) + (size_t)k * nyp + nyp + ((size_t)k * k + k) + (size_t)k * k +
+  int ppt; bool blocked;
+  batched_mapping(k, N, &ppt, &blocked);
+  size_t d = 2 * (size_t)batched_state_doubles(k, N, ppt, blocked) + (size_t)k * (nyp | 1) + nyp + ((size_t)k * k + k) + (size_t)k * k +
              (size_t)(eig_small_smem_doubles(k) > ns_small_smem_doubles() ? eig_small_smem_doubles(k)
                                                                           : ns_small_smem_doubles());
   return d * sizeof(double) + 16;
@@ -269,17 +292,15 @@ cudaError_t batched_launch(const BatchedArgs& a, int batch, cudaStream_t st) {
     etkf_batched_kernel<P, B><<<batch, 256, smem, st>>>(a);                                           \
     return cudaGetLastError();                                                                        \
   }
-  // blocked mapping with the fewest points per thread that fits 256 threads
-  for (int p = 4; p <= 16; p *= 2) {
-    if ((long long)a.k * ((a.N + p - 1) / p) <= 256) {
-      if (p == 4) DAB_B_CASE(4, true)
-      if (p == 8) DAB_B_CASE(8, true)
-      DAB_B_CASE(16, true)
-    }
+  int ppt; bool blocked;
+  batched_mapping(a.k, a.N, &ppt, &blocked);
+  if (blocked) {
+    if (ppt == 4) DAB_B_CASE(4, true)
+    if (ppt == 8) DAB_B_CASE(8, true)
+    DAB_B_CASE(16, true)
   }
-  const int ppt = (a.k * a.N + 255) / 256;          // ragged shapes: round-robin mapping
-  if (ppt <= 4) DAB_B_CASE(4, false)
-  if (ppt <= 8) DAB_B_CASE(8, false)
+  if (ppt == 4) DAB_B_CASE(4, false)
+  if (ppt == 8) DAB_B_CASE(8, false)
   DAB_B_CASE(16, false)
 #undef DAB_B_CASE
 }
