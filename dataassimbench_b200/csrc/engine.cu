@@ -570,10 +570,14 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
                               l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
                               l96_shape_code(17, 160), l96_shape_code(17, 192),
                               l96_shape_code(12, 128), l96_shape_code(12, 160), l96_shape_code(12, 192)};
-    const int cand_chunks[3] = {1, 2, 4};
+    // splitting the window into 2 or 4 launches (forecast_ext, DAB_L96_CHUNKS) was measured at C3/C4 and
+    // never won (shorter halos lose to the extra pass), so the tuner no longer tries it: that also keeps
+    // the two extended scratch buffers it needs unallocated
+    const int cand_chunks[3] = {1, 0, 0};
     float best_ms = 1e30f;
     for (int cc = 0; cc < 3; ++cc) {
       const int chunks = cand_chunks[cc];
+      if (chunks < 1) continue;
       if (chunks > 1 && c.first_steps < 2 * chunks) continue;
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
