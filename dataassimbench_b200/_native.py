@@ -54,6 +54,7 @@ _SIGNATURES = {
     "dab_sync": (C.c_int, [_P]),
     "dab_last_error": (C.c_char_p, [_P]),
     "dab_set_eig_method": (C.c_int, [_P, C.c_int]),
+    "dab_set_pdl": (C.c_int, [C.c_int]),
     "dab_l96_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, _P]),
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
@@ -170,6 +171,10 @@ class Handle:
     def set_eig_method(self, method):
         """K4 solver for 32 < k <= 128: EIG_AUTO (cluster Newton-Schulz, Jacobi fallback) or EIG_JACOBI."""
         self._check(self._lib.dab_set_eig_method(self._h, int(method)))
+
+    def set_pdl(self, on):
+        """Programmatic dependent launch between the kernels of a cycle (process-wide switch)."""
+        self._check(self._lib.dab_set_pdl(int(bool(on))))
 
     def etkf_transform_matrix(self, stats, k, rho, empty_R, T, lam=None, sweeps=None, stream=None):
         self._check(self._lib.dab_etkf_transform_matrix_f64(self._h, _ptr(stats), k, rho, int(empty_R),

@@ -25,4 +25,32 @@ __device__ __forceinline__ long long pmod(long long a, long long n) {
   return r < 0 ? r + n : r;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------
+// The five kernels of a cycle run back to back on one stream and each is short (8-130 us), so
+// the drain -> launch -> ramp gap at every boundary is a visible share of the cycle.  A kernel
+// launched through `launch_chain` may become resident while its predecessor is still running;
+// it does whatever does not depend on the predecessor (index tables, barrier set-up), then
+// `pdl_wait()` blocks until the predecessor has completed and its writes are visible.  Every
+// kernel calls `pdl_launch_dependents()` only AFTER its own wait, so that at most two kernels
+// share the machine and "my predecessor finished" implies "everything before it finished":
+// reads and writes after the wait keep plain stream-order semantics.  Both instructions are
+// no-ops in a kernel launched without the attribute (DAB_PDL=0, or an ordinary <<<>>> launch).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // engine.cu: DAB_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(bool chain, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (chain && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace dab

@@ -14,6 +14,16 @@
 
 using namespace dab;
 
+namespace dab {
+static int g_pdl = -1;      // -1: not decided yet (DAB_PDL, default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) { const char* e = getenv("DAB_PDL"); g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return g_pdl == 1;
+}
+}  // namespace dab
+
+int dab_set_pdl(int on) { dab::g_pdl = on ? 1 : 0; return 0; }
+
 namespace {
 
 struct DevBuf {
@@ -337,7 +347,7 @@ static int stats_from_arrays(dab_handle* h, const double* X, const double* y, co
   const long long seg[3] = {0, n_y, 0};
   DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
   DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
-                              h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, st));
+                              h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, false, st));
   DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, 1.0 / (sd * sd), stats, nullptr, st));
   h->launches += (n_y > 0 ? 1 : 0) + 2;
   return 0;
@@ -648,7 +658,7 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
   prof_mark(h, PROF_START);
   DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
                               c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
-                              c.partial.as<double>(), grid, h->stream));
+                              c.partial.as<double>(), grid, true, h->stream));
   prof_mark(h, PROF_CONTRACT);
   const double r_inv = 1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd);
   if (stats_exchange_ready(c)) {

@@ -77,6 +77,9 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
     fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + RB + tid, r_end, nloc, nval);
   }
   __syncthreads();
+  // everything above read the observation tables only; the state is the previous kernel's output
+  pdl_wait();
+  pdl_launch_dependents();
   double v[8];
   int loc = s_loc[0][lane];
 #pragma unroll
@@ -163,6 +166,8 @@ stats_reduce_kernel(const double* __restrict__ partial, int n_part, int kp, int 
   const int slice = threadIdx.x >> 5;
   const int n_el = k * k + k;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  pdl_wait();
+  pdl_launch_dependents();
   if (el < n_el) {
     const int src = el < k * k ? (el / k) * kp + (el % k) : kp * kp + (el - k * k);
     const long long stride = (long long)kp * kp + kp;
@@ -226,6 +231,10 @@ stats_gather_kernel(const unsigned long long* flags, unsigned long long seq, con
     __threadfence_system();
   }
   __syncthreads();
+  // the flags (this rank's own included) are what this kernel really depends on, so the polling
+  // above may overlap the tail of the reduction kernel; the wait keeps the stream-order chain
+  pdl_wait();
+  pdl_launch_dependents();
   const int el = blockIdx.x * blockDim.x + threadIdx.x;
   if (el < n_el) {
     double s = 0.0;
@@ -250,13 +259,13 @@ int contract_grid(long long n_rows, int sms) {
 
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
                             const double* obs_val, const long long* seg, int n_seg,
-                            long long n_rows, double* partial, int grid, cudaStream_t st) {
+                            long long n_rows, double* partial, int grid, bool chain, cudaStream_t st) {
   const int k8 = contract_k8(k);
   switch (k8) {
-    case 2: contract_kernel<2><<<grid, 64, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
-    case 4: contract_kernel<4><<<grid, 128, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
-    case 8: contract_kernel<8><<<grid, 256, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
-    default: contract_kernel<16><<<grid, 512, 0, st>>>(X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial); break;
+    case 2: return launch_chain(chain, contract_kernel<2>, dim3(grid), dim3(64), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
+    case 4: return launch_chain(chain, contract_kernel<4>, dim3(grid), dim3(128), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
+    case 8: return launch_chain(chain, contract_kernel<8>, dim3(grid), dim3(256), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
+    default: return launch_chain(chain, contract_kernel<16>, dim3(grid), dim3(512), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
   }
   return cudaGetLastError();
 }
@@ -266,16 +275,15 @@ cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double
   const int n_el = k * k + k;
   StatsPush none{};
   none.world = 1;
-  stats_reduce_kernel<<<(n_el + 31) / 32, 512, 0, st>>>(partial, n_part, 8 * contract_k8(k), k, r_inv, stats,
-                                                         push ? *push : none);
-  return cudaGetLastError();
+  return launch_chain(true, stats_reduce_kernel, dim3((n_el + 31) / 32), dim3(512), 0, st, partial, n_part,
+                      8 * contract_k8(k), k, r_inv, stats, push ? *push : none);
 }
 
 cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,
                                 int k, int world, double* stats, cudaStream_t st) {
   const int n_el = k * k + k;
-  stats_gather_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(flags, seq, slots, n_el, world, stats);
-  return cudaGetLastError();
+  return launch_chain(true, stats_gather_kernel, dim3((n_el + 255) / 256), dim3(256), 0, st, flags, seq, slots,
+                      n_el, world, stats);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -211,6 +211,8 @@ ns_transform_kernel(const double* __restrict__ stats, int k, double rho, double*
 
   __shared__ double red_g[KP];
   double delta_k, s, lower;
+  pdl_wait();                                    // the statistics are the previous kernel's output
+  pdl_launch_dependents();
   const bool ok = ns_bounds<KP, NT>(stats, k, shift, red_sq, red_abs, red_g, delta_k, s, lower);
   if (!ok) {                                     // uniform over the cluster: same inputs, same code
     if (rank == 0 && tid == 0) flags[0] = 1;     // the eigensolver kernel enqueued behind this one runs
@@ -521,6 +523,8 @@ ns_mc_transform_kernel(const double* __restrict__ stats, int k, double rho, doub
 #endif
 
   double delta_k, s, lower;
+  pdl_wait();                                    // the statistics are the previous kernel's output
+  pdl_launch_dependents();
   const bool ok = ns_bounds<KP, NT>(stats, k, shift, red_sq, red_abs, red_g, delta_k, s, lower);
   if (!ok) {                                     // uniform over the cluster
     if (rank == 0) {
@@ -725,10 +729,12 @@ cudaError_t ns_launch_t(const double* stats, int k, double rho, double* ws, doub
   cfg.blockDim = dim3(NW * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, stats, k, rho, ws, T, info_out);
 }
 }  // namespace
@@ -753,10 +759,12 @@ static cudaError_t ns_mc_launch(const double* stats, int k, double rho, double* 
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, ns_mc_transform_kernel, stats, k, rho, ws, T, info_out);
 }
 

@@ -29,14 +29,6 @@ transform_kernel(const TransformArgs a) {
   const int fm = lane >> 2, fr = lane & 3;
   const int k = a.k;
 
-  // A fragments of T^T for this warp's 8 output members: A[jrow][m] = T[m][8*warp + jrow]
-  double af[2 * K8];
-#pragma unroll
-  for (int ks = 0; ks < 2 * K8; ++ks) {
-    const int m = 4 * ks + fr, j = 8 * warp + fm;
-    af[ks] = (m < k && j < k) ? a.T[m * k + j] : 0.0;
-  }
-
   // Balanced split: the extended row is cut into 8-column DMMA tiles and every CTA takes the same
   // number of them (+-1) as ONE contiguous range, walked in chunks of up to TC columns -- no
   // last-round stragglers (1028 64-column tiles on 592 CTAs used to leave 26 % of the second round idle).
@@ -70,7 +62,19 @@ transform_kernel(const TransformArgs a) {
       v[it] = (sp != nullptr && m < k) ? sp[(long long)m * a.src_ld] : 0.0;
     }
   };
+  // The background ensemble was finished two kernels ago (see pdl_wait in common.cuh: this CTA can
+  // only be resident once the kernel that made T has passed its own wait), so the first chunk is
+  // fetched while T is still being computed; T itself is read after the wait.
   fetch(t_begin);
+  pdl_wait();
+  pdl_launch_dependents();
+  // A fragments of T^T for this warp's 8 output members: A[jrow][m] = T[m][8*warp + jrow]
+  double af[2 * K8];
+#pragma unroll
+  for (int ks = 0; ks < 2 * K8; ++ks) {
+    const int m = 4 * ks + fr, j = 8 * warp + fm;
+    af[ks] = (m < k && j < k) ? a.T[m * k + j] : 0.0;
+  }
   for (long long t0 = t_begin; t0 < t_end; t0 += TC / 8) {
     const int tiles_here = (int)(t_end - t0 < TC / 8 ? t_end - t0 : TC / 8);
     const long long e0 = e_lo + t0 * 8;
@@ -160,6 +164,7 @@ cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st) {
   const size_t smem = (size_t)8 * k8 * XLD * sizeof(double);
   long long g = n_tiles;                       // small problems: one 64-column chunk per CTA
   static int occ_cache[17] = {0};              // resident CTAs per SM of transform_kernel<K8>
+  cudaError_t launch_err = cudaSuccess;
 #define DAB_TR_CASE(K)                                                                              \
   {                                                                                                 \
     if (occ_cache[K] == 0) {                                                                        \
@@ -171,7 +176,7 @@ cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st) {
     const long long cap = (long long)sms * occ_cache[K];   /* every resident slot gets an equal share */ \
     if (g > cap) g = cap;                                                                           \
     if (g < 1) g = 1;                                                                               \
-    transform_kernel<K><<<(unsigned)g, 32 * K, smem, st>>>(a);                                      \
+    launch_err = launch_chain(true, transform_kernel<K>, dim3((unsigned)g), dim3(32 * K), smem, st, a);    \
   }
   switch (k8) {
     case 2: DAB_TR_CASE(2) break;
@@ -180,7 +185,7 @@ cudaError_t transform_launch(const TransformArgs& a, int sms, cudaStream_t st) {
     default: DAB_TR_CASE(16) break;
   }
 #undef DAB_TR_CASE
-  return cudaGetLastError();
+  return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
 
 }  // namespace dab

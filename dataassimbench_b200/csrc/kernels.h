@@ -26,7 +26,9 @@ int contract_grid(long long n_rows, int sms);
 size_t contract_partial_doubles(int k, int n_cta);
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
                             const double* obs_val, const long long* seg, int n_seg,
-                            long long n_rows, double* partial, int grid, cudaStream_t st);
+                            long long n_rows, double* partial, int grid,
+                            bool chain /* obs tables are not the previous kernel's output: PDL allowed */,
+                            cudaStream_t st);
 // Multi-rank statistics exchange fused into the reduction (etkf_contract.cu): where this rank's
 // reduced k*k+k values go on every rank, and the flags that announce them.
 struct StatsPush {

@@ -72,6 +72,8 @@ l96_rk4_window_kernel(const L96Args a) {
 #ifdef DAB_L96_TRACE
   if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * blockIdx.x + 4] = smid();
 #endif
+  pdl_wait();                 // the input is the previous kernel's output (transform or forecast chunk)
+  pdl_launch_dependents();
 
   // ---- coalesced load into padded shared memory
 #pragma unroll
@@ -206,12 +208,11 @@ static cudaError_t launch_pb(const L96Args& a, int k, int T, bool periodic, cuda
   dim3 grid((unsigned)((long long)a.tiles_per_member * k));
   if (periodic) {
     cudaFuncSetAttribute(l96_rk4_window_kernel<P, true, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    l96_rk4_window_kernel<P, true, MAXT, MINB><<<grid, T, smem, st>>>(a);
+    return launch_chain(true, l96_rk4_window_kernel<P, true, MAXT, MINB>, grid, dim3(T), smem, st, a);
   } else {
     cudaFuncSetAttribute(l96_rk4_window_kernel<P, false, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    l96_rk4_window_kernel<P, false, MAXT, MINB><<<grid, T, smem, st>>>(a);
+    return launch_chain(true, l96_rk4_window_kernel<P, false, MAXT, MINB>, grid, dim3(T), smem, st, a);
   }
-  return cudaGetLastError();
 }
 
 // CTAs of <= 256 threads use the register-capped build (<= 80 registers: three CTAs per SM, so

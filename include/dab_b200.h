@@ -58,6 +58,12 @@ DAB_API const char* dab_last_error(const dab_handle* h);   /* h may be NULL: las
 #define DAB_EIG_NEWTON_SCHULZ 2
 DAB_API int dab_set_eig_method(dab_handle* h, int method);
 
+/* Programmatic dependent launch between the kernels of a cycle (process-wide; default on, or the
+ * environment variable DAB_PDL=0|1 read at the first launch).  With it a kernel becomes resident
+ * while its predecessor drains, fetches what does not depend on it, and blocks on
+ * griddepcontrol.wait before touching its output; results are bit-identical either way. */
+DAB_API int dab_set_pdl(int on);
+
 /* ---- K1: Lorenz-96 RK4 ensemble forecast -----------------------------------------------
  * Replaces ETKF._step_forecast (dabench/dacycler/_etkf.py:64-80) -> Model.forecast ->
  * Data.generate (dabench/data/_data.py:86-211) -> integrate (dabench/data/_utils.py:16-57)

@@ -386,6 +386,25 @@ def test_cycler_matches_oracle_rk4(H, N, k, n_obs, n_cycles, S, stationary, obs_
     assert rel_err(gpu_traj[:, :, :S - 1, :], ref[:, :, 1:, :]) < 1e-9
 
 
+@pytest.mark.parametrize("N,k,n_obs", [(36, 10, 18), (6000, 64, 1800), (3000, 128, 3000)])
+def test_cycler_dependent_launch_is_bit_identical(H, N, k, n_obs):
+    """Programmatic dependent launch (dab_set_pdl) only moves where a kernel waits for its
+    predecessor: the analyses of a multi-cycle run must not change by a single bit, run after run."""
+    n_cycles, S, sd, rho = 10, 20, 1.0, 1.03
+    case = cycler_case(N, k, n_obs, n_cycles, S, sd, rho, True, seed=N + 3 * k)
+    try:
+        H.set_pdl(False)
+        base, base_final, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, True)
+        H.set_pdl(True)
+        for _ in range(3):
+            out, final, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, True)
+            assert np.array_equal(out, base)
+            assert np.array_equal(final, base_final)
+    finally:
+        H.set_pdl(True)
+    assert np.all(np.isfinite(base))
+
+
 def test_cycler_long_window_chunked(H):
     """n_steps above the per-launch limit exercises the chunked forecast path."""
     N, k, n_cycles, S = 512, 6, 3, 70
