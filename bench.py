@@ -44,18 +44,60 @@ BLOCK = 10          # cycles per experiment (fresh ensemble every BLOCK cycles)
 FLOPS_PER_POINT_STEP = 29.0
 
 
-def make_workload(name, seed=42):
+def oracle_generators():
+    """(forecast, padded_table) built on the CPU oracle: the reference arm, the cpu_baseline leg and
+    the offline tools.  The product arm never calls this (see device_generators)."""
+    from oracle import l96 as o_l96, windows as o_win
+
+    def forecast(x, n, dt, return_traj=False):
+        return o_l96.rk4_forecast(x, n, dt, return_traj=return_traj)
+
+    def padded_table(obs_times, window, n_cycles):
+        times = o_win.get_all_times(0.0, window, n_cycles)
+        return np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, obs_times, window)))
+
+    return forecast, padded_table
+
+
+def device_generators(H):
+    """The same two functions made of the package itself: the nature run comes from the forecast
+    kernel (dab_l96_forecast_f64) and the window table from the host mirror of the reference's
+    bookkeeping, so the product arm's synthetic inputs involve nothing under oracle/."""
+    import torch
+    from dataassimbench_b200.dacycler import _windows
+
+    def forecast(x, n, dt, return_traj=False):
+        x = np.asarray(x, dtype=np.float64)
+        a = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(x))).cuda()
+        b = torch.empty_like(a)
+        tr = torch.empty((int(n),) + tuple(a.shape), dtype=torch.float64, device="cuda") if return_traj else None
+        H.l96_forecast(a, b, tr, a.shape[1], a.shape[0], int(n), dt, 8.0)
+        torch.cuda.synchronize()
+        last = b.cpu().numpy().reshape(x.shape)
+        if not return_traj:
+            return last
+        full = np.concatenate([np.atleast_2d(x)[None], tr.cpu().numpy()], axis=0)
+        return last, full.reshape((int(n) + 1,) + x.shape)
+
+    def padded_table(obs_times, window, n_cycles):
+        centres = _windows.window_centres(0.0, window, n_cycles)
+        return np.ascontiguousarray(_windows.padded_time_table(obs_times, centres, window))
+
+    return forecast, padded_table
+
+
+def make_workload(name, seed=42, generators=None):
     """Synthetic experiment: truth spun up with RK4, ensemble = truth + N(0,1),
     one observation time per window placed at the analysis time, stationary random locations
     drawn like Observer does (default_rng.choice(N, n_obs, replace=False, shuffle=False))."""
-    from oracle import l96 as o_l96, windows as o_win
+    rk4, padded_table = generators if generators is not None else oracle_generators()
     w = dict(WORKLOADS[name])
     N, k, S, dt = w["N"], w["k"], w["S"], w["dt"]
     rng = np.random.default_rng(seed)
     truth = 8.0 + rng.standard_normal(N)
     # spin-up onto the attractor (local decorrelation takes a few time units); bounded so that the
     # CPU-side generation of the multi-million-point workloads stays within a minute
-    truth = o_l96.rk4_forecast(truth, int(max(100, min(500, 6.0e7 / N))), dt)
+    truth = rk4(truth, int(max(100, min(500, 6.0e7 / N))), dt)
     n_obs = int(round(w["obs_frac"] * N))
     locs = np.sort(rng.choice(N, n_obs, replace=False, shuffle=False)) if n_obs == N else \
         rng.choice(N, n_obs, replace=False, shuffle=False)
@@ -65,10 +107,9 @@ def make_workload(name, seed=42):
     for c in range(BLOCK):
         vals[c] = x[locs] + w["sd"] * rng.standard_normal(n_obs)
         if c + 1 < BLOCK:
-            x = o_l96.rk4_forecast(x, S, dt)
+            x = rk4(x, S, dt)
     obs_times = np.arange(BLOCK) * (S * dt)
-    times = o_win.get_all_times(0.0, S * dt, BLOCK)
-    padded = np.ascontiguousarray(o_win.pad_time_indices(o_win.get_obs_indices(times, obs_times, S * dt)))
+    padded = padded_table(obs_times, S * dt, BLOCK)
     w.update(n_obs=n_obs, X0=np.ascontiguousarray(X0), vals=np.ascontiguousarray(vals),
              sysidx=np.ascontiguousarray(np.tile(locs, (BLOCK, 1)).astype(np.int64)), padded=padded,
              name=name)
@@ -231,11 +272,11 @@ def run_c2_batched(H, B=4096, n_cycles=50):
     """4096 independent Lorenz-96 N=40, k=20 ETKF experiments (inflation sweep 1.0..1.5), S=20,
     through dab_etkf_cycle_batched_f64 with host buffers; wall clock of the second call."""
     from dataassimbench_b200 import _native
-    from oracle import l96 as o_l96
+    rk4, _ = device_generators(H)
     N, k, S, n_obs, sd, dt = 40, 20, 20, 20, 1.0, 0.01
     rng = np.random.default_rng(1)
-    truth0 = o_l96.rk4_forecast(8 + rng.standard_normal(N), 1000, dt)
-    _, truth = o_l96.rk4_forecast(truth0, n_cycles * S, dt, return_traj=True)
+    truth0 = rk4(8 + rng.standard_normal(N), 1000, dt)
+    _, truth = rk4(truth0, n_cycles * S, dt, return_traj=True)
     tidx = np.arange(0, n_cycles * S + 1, S)
     locs = rng.choice(N, n_obs, replace=False, shuffle=False)
     vals1 = truth[tidx][:, locs] + sd * rng.standard_normal((len(tidx), n_obs))
@@ -276,9 +317,9 @@ def run_product(args):
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
                          % (args.gpus, world))
 
-    w = make_workload(args.workload)
-    N, k, S = w["N"], w["k"], w["S"]
     H = _native.Handle(local_rank)
+    w = make_workload(args.workload, generators=device_generators(H))
+    N, k, S = w["N"], w["k"], w["S"]
     from dataassimbench_b200.sharded import ShardedCycler
     cyc = ShardedCycler(H, w, BLOCK, rank, world)
 

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "dab_set_pdl": (C.c_int, [C.c_int]),
     "dab_l96_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, _P]),
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
+    "dab_observe_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, C.c_int, _P, _I64, _P, _P, _P]),
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
     "dab_etkf_transform_matrix_f64": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
@@ -161,6 +162,13 @@ class Handle:
     def obs_gather(self, X, idx, mask, Yb, N, k, n_y, stream=None):
         self._check(self._lib.dab_obs_gather_f64(self._h, _ptr(X), _ptr(idx), _ptr(mask), _ptr(Yb),
                                                  N, k, n_y, _ptr(stream)))
+
+    def observe(self, state, N, n_state_times, time_pos, n_t, loc, stationary, count, n_obs, errors, values,
+                stream=None):
+        """Observer.observe sampling on the device: values = state[time_pos][loc] + errors (NaN tails)."""
+        self._check(self._lib.dab_observe_f64(self._h, _ptr(state), N, n_state_times, _ptr(time_pos), n_t,
+                                              _ptr(loc), int(bool(stationary)), _ptr(count), n_obs,
+                                              _ptr(errors), _ptr(values), _ptr(stream)))
 
     def etkf_stats(self, X, y, idx, mask, sd, N, k, n_y, stats, stream=None):
         self._check(self._lib.dab_etkf_stats_f64(self._h, _ptr(X), _ptr(y), _ptr(idx), _ptr(mask),

@@ -257,6 +257,13 @@ def var_array(ds, name):
     return np.asarray(v.values if hasattr(v, "values") else v)
 
 
+def var_data(ds, name):
+    """The array object behind a data variable as it was stored (a NumPy array, or a device tensor
+    kept by the stand-in Dataset); no conversion."""
+    v = ds[name]
+    return v.data if hasattr(v, "data") else v
+
+
 def var_dims(ds, name):
     return tuple(ds[name].dims)
 

@@ -92,6 +92,7 @@ struct dab_handle {
   std::string err;
   long launches = 0;
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
+  DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   int eig_method = kEigAuto;
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
@@ -252,7 +253,7 @@ int dab_destroy(dab_handle* h) {
   cudaDeviceSynchronize();
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_seg.release();
-  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release();
+  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
   h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -330,6 +331,31 @@ int dab_obs_gather_f64(dab_handle* h, const double* X, const int64_t* idx, const
   DAB_CUDA(h, gather_launch(X, N, k, reinterpret_cast<const long long*>(idx), mask, n_y, Yb,
                             static_cast<cudaStream_t>(stream)));
   if (n_y > 0) h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------- Observer.observe sampling
+int dab_observe_f64(dab_handle* h, const double* state, int64_t N, int64_t n_state_times,
+                    const int64_t* time_pos, int64_t n_t, const int64_t* loc, int stationary,
+                    const int64_t* count, int64_t n_obs, const double* errors, double* values,
+                    void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, N >= 1 && n_state_times >= 1 && n_t >= 0 && n_obs >= 0);
+  DAB_ARG(h, n_t * n_obs == 0 || (state != nullptr && time_pos != nullptr && loc != nullptr && values != nullptr));
+  if (n_t * n_obs == 0) return 0;
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DAB_CUDA(h, h->s_flag.reserve(sizeof(int)));
+  DAB_CUDA(h, cudaMemsetAsync(h->s_flag.p, 0, sizeof(int), st));
+  DAB_CUDA(h, observe_launch(state, N, n_state_times, reinterpret_cast<const long long*>(time_pos), n_t,
+                             reinterpret_cast<const long long*>(loc), stationary,
+                             reinterpret_cast<const long long*>(count), n_obs, errors, values,
+                             h->s_flag.as<int>(), h->sms, st));
+  h->launches++;
+  int bad = 0;
+  DAB_CUDA(h, cudaMemcpyAsync(&bad, h->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, -1, "dab_observe_f64: a time_pos or loc entry of a valid slot is out of range");
   return 0;
 }
 

@@ -307,6 +307,51 @@ cudaError_t gather_launch(const double* X, long long ld, int k, const long long*
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Observer.observe sampling (the step before the path; dabench/observer/_observer.py:290-316,
+// 346-363): values[t][j] = state[time_pos[t]][loc[t][j]] + errors[t][j] for j < count[t]; the
+// ragged tail of a row is NaN (the reference pads with NaN, and NaN + error stays NaN).  The
+// index draws stay on the host (they must consume NumPy's PCG64 stream in the reference's order);
+// this is the part that touches the trajectory, so a device-resident nature run never has to be
+// copied out: 8 B read (one 32 B sector) + 8 B index + 8 B error + 8 B write per observation.
+// An index outside [0, N) yields NaN and raises *bad (checked by the host wrapper).
+__global__ void __launch_bounds__(256)
+observe_kernel(const double* __restrict__ state, long long N, long long n_state_times,
+               const long long* __restrict__ time_pos, long long n_t, const long long* __restrict__ loc, int stationary,
+               const long long* __restrict__ count, long long n_obs, const double* __restrict__ errors,
+               double* __restrict__ values, int* __restrict__ bad) {
+  const long long total = n_t * n_obs;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / n_obs, j = i - t * n_obs;
+    double v = nan;
+    if (count == nullptr || j < count[t]) {
+      const long long l = loc[stationary ? j : i], tp = time_pos[t];
+      if (l >= 0 && l < N && tp >= 0 && tp < n_state_times) {
+        v = state[tp * N + l];
+        if (errors != nullptr) v += errors[i];
+      } else {
+        *bad = 1;
+      }
+    }
+    values[i] = v;
+  }
+}
+
+cudaError_t observe_launch(const double* state, long long N, long long n_state_times, const long long* time_pos, long long n_t,
+                           const long long* loc, int stationary, const long long* count, long long n_obs,
+                           const double* errors, double* values, int* bad, int sms, cudaStream_t st) {
+  const long long total = n_t * n_obs;
+  if (total <= 0) return cudaSuccess;
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)sms * 8;          // 8 resident 256-thread CTAs per SM, grid-stride beyond
+  if (g > cap) g = cap;
+  observe_kernel<<<(unsigned)g, 256, 0, st>>>(state, N, n_state_times, time_pos, n_t, loc, stationary, count, n_obs, errors,
+                                              values, bad);
+  return cudaGetLastError();
+}
+
 // Build a compact (loc, val) list on device from reference-style arrays (used by the
 // single-analysis entry point): rows with mask == 0 are kept as loc = -1 (contribute nothing).
 __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigned char* __restrict__ mask,

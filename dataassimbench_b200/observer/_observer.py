@@ -4,7 +4,10 @@ Mirrors `dabench.observer.Observer` (dabench/observer/_observer.py:89-366) for s
 1-D states (Lorenz-96).  Index sets must be bit-compatible with the reference, so the one
 `numpy.random.default_rng(random_seed)` stream is consumed in the reference's order: times
 (:192-207), then locations (:209-271), then ONE normal draw covering every slot (:346-348).
-Host-side NumPy; the sampled arrays feed the device through `dab_cycler_setup`.
+The draws are host-side NumPy.  The sampling itself -- `state_vec.sel(time=...).sel(locations)`,
+pad, `+ errors` (:290-316, 361-363) -- runs on the device (`dab_observe_f64`) when the trajectory
+is a CUDA tensor, e.g. a nature run produced by `dab_l96_forecast_f64`: only the sampled values
+leave HBM.  With a NumPy trajectory it is plain indexing.
 """
 import numpy as np
 
@@ -38,7 +41,10 @@ class Observer:
         return int(np.sum(rng.binomial(1, p=self.random_location_density, size=n)))
 
     def observe(self):
-        traj = _xr.var_array(self.state_vec, 'x')
+        traj = _xr.var_data(self.state_vec, 'x')
+        on_device = _is_cuda_tensor(traj)
+        if not on_device:
+            traj = _xr.var_array(self.state_vec, 'x')
         traj_t = _xr.var_array(self.state_vec, 'time')
         n_t, n_sys = traj.shape
         index = np.arange(n_sys)
@@ -64,7 +70,7 @@ class Observer:
                 locs = np.asarray(_loc_array(self.locations), dtype=np.int64)
             self.location_dim = len(locs)
             sysidx = np.tile(locs, (self.time_dim, 1)).astype(np.int64)
-            clean = traj[pos][:, locs]
+            counts = None
         else:
             if self.locations is None:
                 if self.random_location_count is not None:
@@ -78,21 +84,59 @@ class Observer:
             self._location_counts = counts
             self.location_dim = int(np.max(counts)) if len(counts) else 0
             sysidx = np.zeros((self.time_dim, self.location_dim), dtype=np.int64)
-            clean = np.full((self.time_dim, self.location_dim), np.nan)
             for i, l in enumerate(per_time):
                 sysidx[i, :len(l)] = l
-                clean[i, :len(l)] = traj[pos[i], l]
 
         errors = rng.normal(loc=self.error_bias, scale=self.error_sd,
                             size=(1, self.time_dim, self.location_dim))
         if self.error_positive_only:
             errors[errors < 0.] = 0.
+        if on_device:
+            values = self._sample_on_device(traj, pos, sysidx, counts, errors[0])
+        else:
+            if counts is None:
+                clean = traj[pos][:, sysidx[0]] if self.time_dim else np.empty((0, self.location_dim))
+            else:
+                clean = np.full((self.time_dim, self.location_dim), np.nan)
+                for i, c in enumerate(counts):
+                    clean[i, :c] = traj[pos[i], sysidx[i, :c]]
+            values = clean + errors[0]
         return _xr.new_dataset(
-            {'x': (('time', 'observations'), clean + errors[0]),
+            {'x': (('time', 'observations'), values),
              'system_index': (('variable', 'time', 'observations'), sysidx[None]),
              'errors': (('variable', 'time', 'observations'), errors)},
             coords={'time': self.times, 'variable': np.array(['x'])},
             attrs={'stationary_observers': self.stationary_observers, 'error_sd': self.error_sd})
+
+    def _sample_on_device(self, traj, pos, sysidx, counts, errors):
+        """values[t][j] = traj[pos[t]][sysidx[t][j]] + errors[t][j], NaN beyond counts[t]: one
+        `dab_observe_f64` launch on the trajectory's device; the index tables and the errors go up,
+        only the sampled values come back."""
+        import torch
+        from .._runtime import handle
+        if traj.dtype != torch.float64 or not traj.is_contiguous():
+            raise TypeError("a device trajectory must be a contiguous float64 tensor [time, index]")
+        dev = traj.device
+        n_t, n_obs = sysidx.shape
+        if n_t * n_obs == 0:
+            return np.empty((n_t, n_obs))
+        H = handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        stationary = counts is None
+        d_pos = up(np.asarray(pos, dtype=np.int64))
+        d_loc = up(sysidx[0] if stationary else sysidx)
+        d_cnt = None if stationary else up(np.asarray(counts, dtype=np.int64))
+        d_err = up(np.asarray(errors, dtype=np.float64))
+        d_val = torch.empty((n_t, n_obs), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream()
+            H.observe(traj, traj.shape[1], traj.shape[0], d_pos, n_t, d_loc, stationary, d_cnt, n_obs,
+                      d_err, d_val, stream=stream.cuda_stream)
+        return d_val.cpu().numpy()
+
+
+def _is_cuda_tensor(a):
+    return type(a).__module__.split('.')[0] == 'torch' and bool(getattr(a, 'is_cuda', False))
 
 
 def _loc_array(locations):

@@ -85,6 +85,24 @@ DAB_API int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_ou
 DAB_API int dab_obs_gather_f64(dab_handle* h, const double* X, const int64_t* idx, const uint8_t* mask,
                        double* Yb, int64_t N, int k, int64_t n_y, void* stream);
 
+/* ---- the step before the path: Observer.observe sampling on the device -------------------
+ * Replaces the `state_vec.sel(time=...).sel(locations)` / concat / pad / `+ errors` part of
+ * Observer.observe (dabench/observer/_observer.py:290-316, 346-363) for a trajectory that already
+ * lives in HBM (e.g. a nature run made by dab_l96_forecast_f64): only the sampled values leave the
+ * device.  The random draws (times, locations, errors) stay with the caller: they must consume
+ * numpy.random.default_rng in the reference's order to stay bit-compatible.
+ *   state    dev [n_state_times][N]
+ *   time_pos dev int64 [n_t]            row of `state` for every observation time
+ *   loc      dev int64 [n_obs] (stationary != 0) or [n_t][n_obs]
+ *   count    nullable dev int64 [n_t]   valid slots per time (ragged, non-stationary); the rest is NaN
+ *   errors   nullable dev [n_t][n_obs]
+ *   values   dev [n_t][n_obs]           = state[time_pos[t]][loc] + errors
+ * Synchronises the stream and returns -1 if a time_pos / loc entry in a valid slot is out of range. */
+DAB_API int dab_observe_f64(dab_handle* h, const double* state, int64_t N, int64_t n_state_times,
+                    const int64_t* time_pos, int64_t n_t, const int64_t* loc, int stationary,
+                    const int64_t* count, int64_t n_obs, const double* errors, double* values,
+                    void* stream);
+
 /* ---- K3+K4: statistics and transform matrix (exposed for tests and for rank-parallel use) -
  * stats = [C (k*k, row-major) | g (k)] with C = Yb'^T Rinv Yb', g = Yb'^T Rinv (y - ybar)
  * (dabench/dacycler/_etkf.py:137-146,154) for R = obs_error_sd^2 I

@@ -84,6 +84,53 @@ def test_obsop_gather_is_index_selection():
         dab.obsop.ObsOp.gather(X, [50])
 
 
+@pytest.mark.parametrize("stationary", [True, False])
+@pytest.mark.parametrize("N,n_times", [(40, 25), (5000, 12)])
+def test_observer_samples_a_device_trajectory_bit_for_bit(stationary, N, n_times):
+    """Observer.observe with the trajectory in HBM (dab_observe_f64) = the same call on the host copy:
+    same draws, same values to the bit, NaN in the ragged tails (observer/_observer.py:290-316, 346-363)."""
+    rng = np.random.default_rng(N + n_times)
+    traj = rng.standard_normal((n_times, N))
+    coords = {'time': np.arange(n_times) * 0.05, 'index': np.arange(N)}
+    kw = dict(random_time_density=0.5, random_location_density=0.3, error_sd=0.7, error_bias=0.05,
+              stationary_observers=stationary, random_seed=5)
+    host = dab.observer.Observer(_xr.new_dataset({'x': (('time', 'index'), traj)}, coords=coords), **kw).observe()
+    dev = dab.observer.Observer(_xr.new_dataset({'x': (('time', 'index'), torch.from_numpy(traj).cuda())},
+                                                coords=coords), **kw).observe()
+    for name in ('x', 'system_index', 'errors'):
+        a, b = np.asarray(host[name].values), np.asarray(dev[name].values)
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), name
+    assert np.array_equal(host['time'].values, dev['time'].values)
+    if not stationary:
+        assert np.isnan(np.asarray(dev['x'].values)).any()          # ragged rows were padded
+    # the reference's relation between the three fields
+    v, e, si = (np.asarray(dev[n].values) for n in ('x', 'errors', 'system_index'))
+    pos = np.searchsorted(coords['time'], dev['time'].values)
+    ok = ~np.isnan(v)
+    assert np.array_equal(v[ok], (traj[pos][np.arange(len(pos))[:, None], si[0]] + e[0])[ok])
+
+
+def test_observe_entry_point_rejects_bad_indices():
+    from dataassimbench_b200._runtime import handle
+    H = handle()
+    state = torch.arange(12, dtype=torch.float64, device='cuda').reshape(3, 4)
+    out = torch.empty((2, 3), dtype=torch.float64, device='cuda')
+    pos = torch.tensor([0, 2], dtype=torch.int64, device='cuda')
+    loc = torch.tensor([3, 0, 1], dtype=torch.int64, device='cuda')
+    H.observe(state, 4, 3, pos, 2, loc, True, None, 3, None, out)
+    assert np.array_equal(out.cpu().numpy(), np.array([[3., 0., 1.], [11., 8., 9.]]))
+    cnt = torch.tensor([1, 3], dtype=torch.int64, device='cuda')
+    loc2 = torch.tensor([[2, 99, 99], [1, 1, 0]], dtype=torch.int64, device='cuda')      # 99 sits in a padded slot
+    H.observe(state, 4, 3, pos, 2, loc2, False, cnt, 3, None, out)
+    assert np.array_equal(out.cpu().numpy(), np.array([[2., np.nan, np.nan], [9., 9., 8.]]), equal_nan=True)
+    with pytest.raises(RuntimeError, match="out of range"):
+        H.observe(state, 4, 3, pos, 2, torch.tensor([0, 4, 1], dtype=torch.int64, device='cuda'), True, None, 3,
+                  None, out)
+    with pytest.raises(RuntimeError, match="out of range"):
+        H.observe(state, 4, 3, torch.tensor([0, 3], dtype=torch.int64, device='cuda'), 2, loc, True, None, 3,
+                  None, out)
+
+
 @pytest.mark.parametrize("tag", ["c1", "c2", "c3s", "c5s"])
 def test_analysis_golden_fixture(tag):
     """Committed literal-formula vectors (tests/golden/make_golden.py): <= 1e-10."""
