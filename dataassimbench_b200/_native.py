@@ -56,6 +56,7 @@ _SIGNATURES = {
     "dab_set_eig_method": (C.c_int, [_P, C.c_int]),
     "dab_set_pdl": (C.c_int, [C.c_int]),
     "dab_l96_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, _P]),
+    "dab_l63_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
     "dab_observe_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, C.c_int, _P, _I64, _P, _P, _P]),
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
@@ -158,6 +159,10 @@ class Handle:
     def l96_forecast(self, x_in, x_out, traj, N, k, n_steps, dt, F, stream=None):
         self._check(self._lib.dab_l96_forecast_f64(self._h, _ptr(x_in), _ptr(x_out), _ptr(traj),
                                                    N, k, n_steps, dt, F, _ptr(stream)))
+
+    def l63_forecast(self, x_in, x_out, traj, k, n_steps, dt, sigma=10.0, rho=28.0, beta=8.0 / 3.0, stream=None):
+        self._check(self._lib.dab_l63_forecast_f64(self._h, _ptr(x_in), _ptr(x_out), _ptr(traj), k, n_steps,
+                                                   dt, sigma, rho, beta, _ptr(stream)))
 
     def obs_gather(self, X, idx, mask, Yb, N, k, n_y, stream=None):
         self._check(self._lib.dab_obs_gather_f64(self._h, _ptr(X), _ptr(idx), _ptr(mask), _ptr(Yb),

@@ -321,6 +321,20 @@ int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_out, doubl
   return forecast_plain(h, x_in, x_out, traj, N, k, n_steps, dt, F, st, tmp);
 }
 
+// Lorenz-63: members are [k][3]; in place (x_in == x_out) is allowed, every thread owns one member
+int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj, int64_t k,
+                         int n_steps, double dt, double sigma, double rho, double beta, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, k >= 0 && n_steps >= 0);
+  DAB_ARG(h, k == 0 || (x_in != nullptr && x_out != nullptr));
+  if (k == 0) return 0;
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, l63_forecast_launch(x_in, x_out, traj, k, n_steps, dt, sigma, rho, beta,
+                                  static_cast<cudaStream_t>(stream)));
+  h->launches++;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ K2
 int dab_obs_gather_f64(dab_handle* h, const double* X, const int64_t* idx, const uint8_t* mask,
                        double* Yb, int64_t N, int k, int64_t n_y, void* stream) {

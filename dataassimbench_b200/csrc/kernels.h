@@ -20,6 +20,10 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 long long traj_stride, int sms, int forced_T /* 0 = heuristic */,
                                 cudaStream_t st);
 
+// Lorenz-63 members [k][3]  l63_forecast.cu
+cudaError_t l63_forecast_launch(const double* x_in, double* x_out, double* traj, long long k, int n_steps,
+                                double dt, double sigma, double rho, double beta, cudaStream_t st);
+
 // K2/K3  etkf_contract.cu
 int contract_k8(int k);
 int contract_grid(long long n_rows, int sms);

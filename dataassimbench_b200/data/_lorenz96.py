@@ -45,6 +45,31 @@ class Data:
         self.var_names = ['x']
         self.x0 = x0
 
+    def generate(self, n_steps=None, t_final=None, x0=None, **kwargs):
+        """Trajectory of n_steps points at spacing delta_t, initial state included
+        (dabench/data/_data.py:121-125, dabench/data/_utils.py:44)."""
+        if n_steps is not None:
+            t_final = n_steps * self.delta_t
+        elif t_final is not None:
+            n_steps = int(t_final / self.delta_t)
+        else:
+            raise TypeError('Either n_steps or t_final must be supplied as an input argument.')
+        if x0 is None:
+            if self.x0 is None:
+                raise TypeError('Initial condition is None, x0 = {}. it must either be provided as an '
+                                'argument or set as an attribute in the model object.'.format(x0))
+            x0 = self.x0
+        t = np.arange(0.0, t_final - self.delta_t / 2, self.delta_t)
+        y = self._integrate(np.asarray(x0, dtype=np.float64).reshape(1, -1), len(t))[0]
+        return _xr.new_dataset(
+            {'x': (('time', 'index'), y)},
+            coords={'time': t, 'index': np.arange(self.system_dim)},
+            attrs={'store_as_jax': self.store_as_jax, 'system_dim': self.system_dim,
+                   'delta_t': self.delta_t})
+
+    def _integrate(self, X0, n_points):
+        raise NotImplementedError('a generator integrates on the GPU through its own forecast kernel')
+
 
 class Lorenz96(Data):
     def __init__(self, forcing_term=8., delta_t=0.05, x0=None, system_dim=36, values=None,
@@ -67,28 +92,6 @@ class Lorenz96(Data):
         x = np.asarray(x, dtype=np.float64)
         xm2, xm1, xp1 = np.roll(x, 2, -1), np.roll(x, 1, -1), np.roll(x, -1, -1)
         return (xp1 - xm2) * xm1 - x + self.forcing_term
-
-    def generate(self, n_steps=None, t_final=None, x0=None, **kwargs):
-        """Trajectory of n_steps points at spacing delta_t, initial state included
-        (dabench/data/_data.py:121-125, dabench/data/_utils.py:44)."""
-        if n_steps is not None:
-            t_final = n_steps * self.delta_t
-        elif t_final is not None:
-            n_steps = int(t_final / self.delta_t)
-        else:
-            raise TypeError('Either n_steps or t_final must be supplied as an input argument.')
-        if x0 is None:
-            if self.x0 is None:
-                raise TypeError('Initial condition is None, x0 = {}. it must either be provided as an '
-                                'argument or set as an attribute in the model object.'.format(x0))
-            x0 = self.x0
-        t = np.arange(0.0, t_final - self.delta_t / 2, self.delta_t)
-        y = self._integrate(np.asarray(x0, dtype=np.float64).reshape(1, -1), len(t))[0]
-        return _xr.new_dataset(
-            {'x': (('time', 'index'), y)},
-            coords={'time': t, 'index': np.arange(self.system_dim)},
-            attrs={'store_as_jax': self.store_as_jax, 'system_dim': self.system_dim,
-                   'delta_t': self.delta_t})
 
     def _integrate(self, X0, n_points):
         """[k, N] -> [k, n_points, N] on the GPU (K1 with trajectory output)."""

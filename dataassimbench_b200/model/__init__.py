@@ -1,3 +1,3 @@
-from ._model import Model, Lorenz96Model
+from ._model import Model, Lorenz96Model, Lorenz63Model
 
-__all__ = ["Model", "Lorenz96Model"]
+__all__ = ["Model", "Lorenz96Model", "Lorenz63Model"]

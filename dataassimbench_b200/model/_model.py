@@ -31,3 +31,18 @@ class Lorenz96Model(Model):
     def forecast(self, state_vec, n_steps):
         new_vec = self.model_obj.generate(x0=_xr.var_array(state_vec, 'x'), n_steps=n_steps)
         return new_vec.isel(time=-1), new_vec
+
+
+class Lorenz63Model(Model):
+    """Wraps a `data.Lorenz63` generator the same way (the wrapper the reference's model test defines
+    inline, tests/model_base_test.py:10-16, with the n_steps argument of the cyclers' contract)."""
+
+    def __init__(self, system_dim=None, delta_t=None, model_obj=None):
+        if model_obj is None:
+            from ..data import Lorenz63
+            model_obj = Lorenz63(delta_t=delta_t or 0.01)
+        super().__init__(system_dim=3, delta_t=delta_t or model_obj.delta_t, model_obj=model_obj)
+
+    def forecast(self, state_vec, n_steps=2):
+        new_vec = self.model_obj.generate(x0=_xr.var_array(state_vec, 'x'), n_steps=n_steps)
+        return new_vec.isel(time=-1), new_vec

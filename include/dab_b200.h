@@ -75,6 +75,12 @@ DAB_API int dab_set_pdl(int on);
 DAB_API int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj,
                          int64_t N, int k, int n_steps, double dt, double F, void* stream);
 
+/* Lorenz-63 members through the same plugin point (dabench/data/_lorenz63.py:70-90 rhs; defaults
+ * sigma = 10, rho = 28, beta = 8/3, :37-42), classical RK4 at dt.
+ *   x_in, x_out dev [k][3] (may alias); traj nullable dev [n_steps][k][3]: state after step 1..n_steps */
+DAB_API int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj, int64_t k,
+                         int n_steps, double dt, double sigma, double rho, double beta, void* stream);
+
 /* ---- K2: observation operator as a gather ----------------------------------------------
  * Replaces the dense one-hot H (DACycler._calc_default_H, dabench/dacycler/_dacycler.py:58-66),
  * its masking (dabench/dacycler/_etkf.py:202-203) and ETKF._apply_obsop `H @ Xb`

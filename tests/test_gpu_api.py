@@ -73,6 +73,29 @@ def test_generate_and_model_forecast_contract():
     assert np.array_equal(tr['x'].values[0], traj['x'].values[3])
 
 
+def test_lorenz63_model_forecast_reference_known_answer():
+    """/root/reference/tests/model_base_test.py:18-30 and tests/data_lorenz63_test.py:22-75 through
+    the API classes (RK4 at delta_t instead of the adaptive integrator: within the tests' allclose)."""
+    m = dab.model.Lorenz63Model(model_obj=dab.data.Lorenz63())
+    sv = _xr.new_dataset({'x': (('index',), m.model_obj.x0)})
+    new, traj = m.forecast(sv)
+    assert np.allclose(sv['x'].values, np.array([-10., -15., 21.3]))
+    assert not np.allclose(new['x'].values, sv['x'].values)
+    assert np.allclose(new['x'].values, np.array([-10.499835, -15.48437, 22.282299]))
+    assert traj['x'].shape == (2, 3)
+    g = dab.data.Lorenz63(system_dimension=3)
+    t1 = g.generate(t_final=1)
+    assert t1['x'].shape == (100, 3) and t1.attrs['system_dim'] == 3
+    assert np.array_equal(t1['x'].values, dab.data.Lorenz63().generate(t_final=1)['x'].values)
+    t2 = g.generate(t_final=1, x0=np.array([-2.2, -2.2, 19.1]))
+    assert not np.allclose(t1['x'].values, t2['x'].values, rtol=1e-5, atol=0)
+    assert not np.allclose(t2['x'].values[-1], np.array([-2.2, -2.2, 19.1]))
+    from oracle import l63 as o_l63
+    assert rel_err(t1['x'].values, o_l63.generate_rk4(o_l63.X0_DEFAULT, 100, 0.01)) < 1e-11
+    # against the reference's own integrator the fixed-step RK4 differs by its truncation error only
+    assert rel_err(t1['x'].values[:30], o_l63.generate_dopri5(o_l63.X0_DEFAULT, 30, 0.01)) < 1e-5
+
+
 def test_obsop_gather_is_index_selection():
     rng = np.random.default_rng(0)
     X = rng.standard_normal((6, 50))

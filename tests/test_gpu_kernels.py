@@ -40,6 +40,31 @@ def make_ensemble(N, k, seed=0, spinup=200):
     return x + rng.standard_normal((k, N)), x
 
 
+# ------------------------------------------------------------------------- Lorenz-63 members
+@pytest.mark.parametrize("k,steps,dt", [(1, 1, 0.01), (7, 25, 0.01), (1000, 100, 0.01), (300, 40, 0.005)])
+def test_l63_forecast_matches_oracle_rk4(H, k, steps, dt):
+    from oracle import l63 as o_l63
+    rng = np.random.default_rng(k + steps)
+    X = o_l63.X0_DEFAULT + rng.standard_normal((k, 3))
+    last, traj = o_l63.rk4_forecast(X, steps, dt, return_traj=True)
+    x_in = dev(X)
+    x_out = torch.empty_like(x_in)
+    tr = torch.empty((steps, k, 3), dtype=torch.float64, device='cuda')
+    H.l63_forecast(x_in, x_out, tr, k, steps, dt)
+    H.sync(); torch.cuda.synchronize()
+    # rounding differences (FMA contraction) are amplified by the chaotic dynamics: one ulp of noise per
+    # step ends at 2e-13 over 1000 members x 100 steps in the oracle itself; 1e-10 leaves room and is
+    # still five orders below the method's own truncation error
+    assert rel_err(x_out.cpu().numpy(), last) < 1e-10
+    assert rel_err(tr.cpu().numpy(), traj[1:]) < 1e-10
+    assert np.array_equal(tr[-1].cpu().numpy(), x_out.cpu().numpy())
+    # in place, no trajectory, non-default parameters
+    par = dict(sigma=9.0, rho=30.0, beta=2.5)
+    H.l63_forecast(x_in, x_in, None, k, steps, dt, **par)
+    torch.cuda.synchronize()
+    assert rel_err(x_in.cpu().numpy(), o_l63.rk4_forecast(X, steps, dt, **par)) < 1e-10
+
+
 # ------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("N,k,steps,dt", [
     (5, 8, 10, 0.05), (36, 10, 20, 0.01), (40, 20, 20, 0.01), (1000, 3, 7, 0.01),

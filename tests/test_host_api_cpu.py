@@ -8,7 +8,7 @@ import scipy.integrate
 import dataassimbench_b200 as dab
 from dataassimbench_b200 import _xr
 from dataassimbench_b200.dacycler import _windows
-from oracle import windows as o_win, l96 as o_l96, observer as o_obs
+from oracle import windows as o_win, l96 as o_l96, l63 as o_l63, observer as o_obs
 
 
 @pytest.mark.parametrize("start,w,n,obs_dt,n_obs_t", [
@@ -96,6 +96,25 @@ def _experiment(N=8, k=4, n_cycles=5, S=10):
     X0 = ds['x'].values[0] + np.random.default_rng(0).standard_normal((k, N))
     init = _xr.new_dataset({'x': (('ensemble', 'index'), X0)}, coords={'index': np.arange(N)})
     return ds, obs, model, init
+
+
+def test_lorenz63_generator_surface(capsys):
+    """Constructor contract of dabench.data.Lorenz63 (dabench/data/_lorenz63.py:37-68): defaults,
+    system_dim forced to 3 with the reference's warning, rhs and Jacobian."""
+    g = dab.data.Lorenz63(system_dimension=3)                 # the reference's tests pass this stray kwarg
+    assert (g.sigma, g.rho, g.beta, g.delta_t, g.system_dim) == (10., 28., 8. / 3., 0.01, 3)
+    assert np.array_equal(g.x0, [-10.0, -15.0, 21.3])
+    g5 = dab.data.Lorenz63(system_dim=5)
+    assert g5.system_dim == 3 and 'requires system_dim=3' in capsys.readouterr().out
+    x = np.array([1.5, -2.0, 20.0])
+    assert np.allclose(g.rhs(x), o_l63.rhs(x), rtol=0, atol=0)
+    eps = 1e-6
+    J = np.stack([(o_l63.rhs(x + eps * e) - o_l63.rhs(x - eps * e)) / (2 * eps) for e in np.eye(3)], axis=1)
+    assert np.allclose(g.Jacobian(x), J, atol=1e-7)
+    with pytest.raises(TypeError):
+        g.generate()                                          # neither n_steps nor t_final (dabench/data/_data.py:127-128)
+    m = dab.model.Lorenz63Model(model_obj=g)
+    assert m.system_dim == 3 and m.delta_t == 0.01 and callable(m.forecast)
 
 
 def test_cycle_plan_marshalling():

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import scipy.integrate
 
-from oracle import l96, etkf, observer, threefry, metrics, windows
+from oracle import l96, l63, etkf, observer, threefry, metrics, windows
 
 
 # ---------------------------------------------------------------- ETKF end-to-end golden
@@ -103,6 +103,21 @@ def test_l96_reference_trajectory():
     assert y.shape == L96_TRUE.shape
     assert np.allclose(y, L96_TRUE, rtol=0.01, atol=0)               # :135
     assert np.allclose(np.sum(y), np.sum(L96_TRUE), rtol=1e-3, atol=0)
+
+
+def test_l63_reference_known_answer():
+    """/root/reference/tests/model_base_test.py:18-30: Lorenz63().generate(x0, n_steps=2)[-1]."""
+    gold = np.array([-10.499835, -15.48437, 22.282299])
+    assert np.allclose(l63.X0_DEFAULT, np.array([-10., -15., 21.3]))
+    assert np.allclose(l63.generate_dopri5(l63.X0_DEFAULT, 2, 0.01)[-1], gold)
+    assert np.allclose(l63.generate_rk4(l63.X0_DEFAULT, 2, 0.01)[-1], gold)          # the kernel's integrator
+    # the restated adaptive integrator against an independent one
+    ref = scipy.integrate.solve_ivp(lambda t, y: l63.rhs(y), (0.0, 0.5), l63.X0_DEFAULT, rtol=1e-12,
+                                    atol=1e-12, t_eval=np.arange(50) * 0.01).y.T
+    assert np.max(np.abs(l63.generate_dopri5(l63.X0_DEFAULT, 50, 0.01) - ref)) < 5e-6
+    # an ensemble is advanced member-wise
+    X = l63.X0_DEFAULT + np.arange(12).reshape(4, 3) * 0.1
+    assert np.array_equal(l63.rk4_forecast(X, 5, 0.01)[2], l63.rk4_forecast(X[2], 5, 0.01))
 
 
 def test_rhs_matches_explicit_index_form():
