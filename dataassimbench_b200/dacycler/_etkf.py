@@ -15,6 +15,7 @@ from ._dacycler import DACycler
 class ETKF(DACycler):
     _in_4d = False
     _uses_ensemble = True
+    traj_block_bytes = 4 << 30      # device memory for return_forecast trajectories, per block of cycles
 
     def __init__(self, system_dim, delta_t, model_obj, B=None, R=None, H=None, h=None,
                  ensemble_dim=4, multiplicative_inflation=1.0):
@@ -86,13 +87,21 @@ class ETKF(DACycler):
         if not return_forecast:
             H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out)
             return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy().copy())})
+        # The trajectories are S*k*N*8 bytes per cycle (671 MB at N=65536, k=64): they are produced in
+        # blocks of cycles that fit `traj_block_bytes` of device memory and streamed to the host block
+        # by block, instead of materialising n_cycles of them in HBM (the reference builds the whole
+        # array inside its scan, dabench/dacycler/_dacycler.py:276-290).
         H.cycler_setup(cfg, p['vals'], p['sysidx'], p['padded'])
         H.cycler_set_state(p['X0'], True)
-        traj = torch.empty((n_cycles, max(S, 1), k, N), dtype=torch.float64, device='cuda')
-        H.cycler_run(0, n_cycles, out, traj if S > 0 else None)
-        H.sync()
         full = np.empty((n_cycles, k, max(S, 1), N))
+        per_cycle = max(S, 1) * k * N * 8
+        blk = int(max(1, min(n_cycles, self.traj_block_bytes // per_cycle)))
+        traj = torch.empty((blk, max(S, 1), k, N), dtype=torch.float64, device='cuda') if S > 0 else None
+        for c0 in range(0, n_cycles, blk):
+            c1 = min(n_cycles, c0 + blk)
+            H.cycler_run(c0, c1, out[c0:c1], traj[:c1 - c0] if S > 0 else None)
+            H.sync()
+            if S > 1:
+                full[c0:c1, :, 1:, :] = traj[:c1 - c0, :S - 1].permute(0, 2, 1, 3).cpu().numpy()
         full[:, :, 0, :] = out.numpy()
-        if S > 1:
-            full[:, :, 1:, :] = traj[:, :S - 1].permute(0, 2, 1, 3).cpu().numpy()
         return _xr.new_dataset({'x': (('cycle', 'ensemble', 'cycle_timestep', dim), full)})

@@ -54,6 +54,11 @@ def test_reference_etkf_test_recipe_through_the_api():
                      analysis_window=0.1, n_cycles=10)
     assert out_a['x'].shape == (10, 8, 5)
     assert np.array_equal(out_a['x'].values, out_sv['x'].values[:, :, 0, :])
+    # trajectories streamed to the host in blocks of cycles (3, 3, 3, 1 here) are the same array
+    dc.traj_block_bytes = 3 * (10 * 8 * 5 * 8) + 17
+    out_blk = dc.cycle(input_state=init, start_time=start_time, obs_vector=obs, obs_error_sd=1.5,
+                       analysis_window=0.1, n_cycles=10, return_forecast=True)
+    assert np.array_equal(out_blk['x'].values, out_sv['x'].values)
 
 
 def test_generate_and_model_forecast_contract():
