@@ -3,6 +3,8 @@ include/dab_b200.h declares, and fails loudly (no CPU fallback) without a CUDA d
 import ctypes
 import os
 import re
+import shutil
+import subprocess
 
 import pytest
 
@@ -44,3 +46,54 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(_native.DabError) as ei:
         _native.Handle(0)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+C_PROGRAM = r"""
+#include <stdio.h>
+#include <string.h>
+#include "dab_b200.h"
+
+int main(void) {
+  struct dab_cycle_config cfg;
+  dab_handle* h = (dab_handle*)0;
+  int rc;
+  memset(&cfg, 0, sizeof cfg);
+  printf("version %d sizeof_cfg %d max_ens %d max_ranks %d ipc %d\n", dab_version(), (int)sizeof cfg,
+         DAB_MAX_ENSEMBLE, DAB_MAX_RANKS, DAB_IPC_HANDLE_BYTES);
+  rc = dab_create(&h, 0);
+  if (rc != 0) {                       /* no GPU here: must fail loudly and leave no handle */
+    printf("create rc %d handle %s msg %s\n", rc, h ? "set" : "null", dab_last_error((dab_handle*)0));
+    return 0;
+  }
+  printf("create ok\n");
+  dab_set_pdl(1);
+  rc = dab_cycler_setup(h, &cfg, 0, 0, 0);       /* system_dim 0: argument error, not a crash */
+  printf("setup rc %d msg %s\n", rc, dab_last_error(h));
+  dab_destroy(h);
+  return 0;
+}
+"""
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="needs gcc")
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """The boundary is a C ABI: include/dab_b200.h compiles as strict C99 (no C++, no torch types), and a
+    C program linked against the in-tree library can call it; without a GPU dab_create returns an error
+    code and a message instead of a handle."""
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "use_dab.c"
+    src.write_text(C_PROGRAM)
+    exe = tmp_path / "use_dab"
+    libdir = os.path.dirname(_build.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-ldab_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    first = out.stdout.splitlines()[0].split()
+    assert int(first[1]) >= 100 and int(first[3]) == ctypes.sizeof(_native.CycleConfig)
+    import torch
+    if torch.cuda.is_available():
+        assert "create ok" in out.stdout and "setup rc -1" in out.stdout
+    else:
+        assert "create rc" in out.stdout and "handle null" in out.stdout
+        assert "no CPU fallback" in out.stdout or "CUDA" in out.stdout
