@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import scipy.integrate
 
-from oracle import l96, l63, etkf, observer, threefry, metrics, windows
+from oracle import l96, l63, etkf, var3d, observer, threefry, metrics, windows
 
 
 # ---------------------------------------------------------------- ETKF end-to-end golden
@@ -207,3 +207,44 @@ def test_get_all_times_keeps_reference_float_quirk():
     assert len(windows.get_all_times(0.0, 0.1, 10)) == 10
     with pytest.raises(ValueError):
         windows.get_all_times(0.0, 0.1, 12)
+
+
+def test_var3d_reference_golden():
+    """/root/reference/tests/dacycler_var3d_test.py:11-84 with the oracle: Lorenz-96 N=6, dt=0.05, 34 of 50
+    observation times (density 0.7, seed 94), 3 stationary locations, sd 0.7, 10 cycles of window 0.25.
+    The literal analysis (dense H/R/B, conjugate gradients as jax.scipy.sparse.linalg.cg) and the closed
+    form for the default operators both reproduce the two presaved vectors to the printed digits."""
+    x0 = l96.default_x0(6, 0.05)
+    nature = l96.generate_dopri5(x0, 50, 0.05)
+    times = l96.time_grid(50, 0.05)
+    obs = observer.observe(nature, times, random_time_density=0.7, random_location_count=3, error_bias=0.0,
+                           error_sd=0.7, random_seed=94, stationary_observers=True)
+    assert obs['values'].shape == (34, 3)
+    init = nature[0] + threefry.normal(42, (6,))
+    fc = lambda x, n: l96.generate_dopri5(x, n, 0.05)
+    first = np.array([-0.90632236, -1.20861455, 1.64865068, 5.11034063, 4.399881, -3.75779771])
+    last = np.array([3.92060079, 3.97290102, -0.763032, -1.5979558, -0.0086728, 2.60395146])
+    runs = []
+    for literal in (True, False):
+        out = var3d.cycle(init, times[0], obs['values'], obs['time'], obs['system_index'], 10, 0.7, fc, 0.05,
+                          analysis_window=0.25, literal=literal)
+        assert out.shape == (10, 6)
+        assert np.max(np.abs(out[0] - first)) < 2e-8 and np.max(np.abs(out[-1] - last)) < 1e-7
+        runs.append(out)
+    assert np.max(np.abs(runs[0] - runs[1])) < 1e-9          # CG on a diagonal system is exact in <= 3 steps
+
+
+def test_var3d_cg_matches_direct_solve():
+    rng = np.random.default_rng(3)
+    n, m = 40, 25
+    xb, y = rng.standard_normal(n), rng.standard_normal(m)
+    loc = rng.integers(0, n, m)                               # repeated locations on purpose
+    H = etkf.calc_default_H(m, n, loc[None])
+    H[::7] = 0.0                                              # masked rows
+    R = etkf.calc_default_R(m, 0.8)
+    xa = var3d.analysis_literal(xb, y, H, R)
+    A = np.identity(n) + H.T @ H / 0.64
+    assert np.max(np.abs(xa - np.linalg.solve(A, xb + H.T @ y / 0.64))) < 1e-4     # CG tolerance 1e-5
+    w = np.ones(m) / 0.64
+    w[::7] = 0.0
+    assert np.max(np.abs(var3d.analysis_diagonal(xb, y, loc, w) - np.linalg.solve(A, xb + H.T @ y / 0.64))) < 1e-13
