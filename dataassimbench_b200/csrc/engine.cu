@@ -373,6 +373,29 @@ int dab_observe_f64(dab_handle* h, const double* state, int64_t N, int64_t n_sta
   return 0;
 }
 
+// ------------------------------------------------------- 3D-Var analysis, default operators
+int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, int64_t N, const int64_t* loc,
+                           const double* val, int64_t n_rows, double obs_error_sd, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, N >= 1 && n_rows >= 0 && obs_error_sd > 0.0);
+  DAB_ARG(h, xb != nullptr && xa != nullptr && xb != xa);
+  DAB_ARG(h, n_rows == 0 || (loc != nullptr && val != nullptr));
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DAB_CUDA(h, h->s_flag.reserve(sizeof(int)));
+  DAB_CUDA(h, h->s_val.reserve(sizeof(double) * (size_t)N));          // the denominators
+  DAB_CUDA(h, cudaMemsetAsync(h->s_flag.p, 0, sizeof(int), st));
+  DAB_CUDA(h, var3d_analysis_launch(xb, xa, h->s_val.as<double>(), N, reinterpret_cast<const long long*>(loc),
+                                    val, n_rows, 1.0 / (obs_error_sd * obs_error_sd), h->s_flag.as<int>(),
+                                    h->sms, st));
+  h->launches += n_rows > 0 ? 3 : 2;
+  int bad = 0;
+  DAB_CUDA(h, cudaMemcpyAsync(&bad, h->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, -1, "dab_var3d_analysis_f64: an observation location is out of range");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------- K3 / K4
 static int stats_from_arrays(dab_handle* h, const double* X, const double* y, const int64_t* idx,
                              const uint8_t* mask, double sd, long long N, int k, long long n_y,

@@ -51,6 +51,9 @@ cudaError_t gather_launch(const double* X, long long ld, int k, const long long*
 cudaError_t observe_launch(const double* state, long long N, long long n_state_times, const long long* time_pos, long long n_t,
                            const long long* loc, int stationary, const long long* count, long long n_obs,
                            const double* errors, double* values, int* bad, int sms, cudaStream_t st);
+cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, long long n, const long long* loc,
+                                  const double* val, long long n_rows, double w, int* bad, int sms,
+                                  cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
                             long long n_y, int* loc, double* val, cudaStream_t st);
 

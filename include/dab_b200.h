@@ -109,6 +109,17 @@ DAB_API int dab_observe_f64(dab_handle* h, const double* state, int64_t N, int64
                     const int64_t* count, int64_t n_obs, const double* errors, double* values,
                     void* stream);
 
+/* ---- 3D-Var analysis with the default operators -------------------------------------------
+ * Replaces Var3D._cycle_obsop (dabench/dacycler/_var3d.py:52-112) when H is the default index gather
+ * (masked rows removed by the caller), R = obs_error_sd^2 I and B = I (DACycler._calc_default_B,
+ * dabench/dacycler/_dacycler.py:74-76): the system I + B H^T R^-1 H the reference hands to conjugate
+ * gradients is then diagonal and is solved exactly,
+ *   xa[i] = (xb[i] + sum_r val[r] / sd^2) / (1 + count_i / sd^2)   over rows r with loc[r] == i.
+ *   xb, xa dev [N] (distinct); loc dev int64 [n_rows]; val dev [n_rows].
+ * Synchronises the stream; returns -1 if a location is out of range. */
+DAB_API int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, int64_t N, const int64_t* loc,
+                           const double* val, int64_t n_rows, double obs_error_sd, void* stream);
+
 /* ---- K3+K4: statistics and transform matrix (exposed for tests and for rank-parallel use) -
  * stats = [C (k*k, row-major) | g (k)] with C = Yb'^T Rinv Yb', g = Yb'^T Rinv (y - ybar)
  * (dabench/dacycler/_etkf.py:137-146,154) for R = obs_error_sd^2 I

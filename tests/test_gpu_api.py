@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 import dataassimbench_b200 as dab
 from dataassimbench_b200 import _xr, _native
-from oracle import l96 as o_l96, etkf as o_etkf, threefry, metrics as o_metrics
+from oracle import l96 as o_l96, etkf as o_etkf, var3d as o_var3d, threefry, metrics as o_metrics
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -157,6 +157,66 @@ def test_observe_entry_point_rejects_bad_indices():
     with pytest.raises(RuntimeError, match="out of range"):
         H.observe(state, 4, 3, torch.tensor([0, 3], dtype=torch.int64, device='cuda'), 2, loc, True, None, 3,
                   None, out)
+
+
+def test_var3d_analysis_entry_point():
+    """dab_var3d_analysis_f64 = the closed form of the reference's CG system for default H / R / B
+    (oracle/var3d.py::analysis_diagonal, itself checked against the literal CG solve on CPU)."""
+    from dataassimbench_b200._runtime import handle
+    H = handle()
+    rng = np.random.default_rng(8)
+    N, sd = 5000, 0.7
+    xb = rng.standard_normal(N)
+    d_xb = torch.from_numpy(xb).cuda()
+    d_xa = torch.empty_like(d_xb)
+    # one observation per point: bit-exact
+    loc = rng.choice(N, 1500, replace=False, shuffle=False).astype(np.int64)
+    val = rng.standard_normal(1500)
+    H.var3d_analysis(d_xb, d_xa, N, torch.from_numpy(loc).cuda(), torch.from_numpy(val).cuda(), 1500, sd)
+    ref = o_var3d.analysis_diagonal(xb, val, loc, np.full(1500, 1.0 / sd ** 2))
+    assert np.array_equal(d_xa.cpu().numpy(), ref)
+    assert not np.array_equal(ref, xb) and np.array_equal(ref[np.setdiff1d(np.arange(N), loc)], xb[np.setdiff1d(np.arange(N), loc)])
+    # two observation times in the window hitting the same points, plus a triple: sums in any order
+    loc2 = np.concatenate([loc, loc[:700], loc[:5]])
+    val2 = np.concatenate([val, rng.standard_normal(705)])
+    H.var3d_analysis(d_xb, d_xa, N, torch.from_numpy(loc2).cuda(), torch.from_numpy(val2).cuda(), len(loc2), sd)
+    ref2 = o_var3d.analysis_diagonal(xb, val2, loc2, np.full(len(loc2), 1.0 / sd ** 2))
+    assert np.max(np.abs(d_xa.cpu().numpy() - ref2)) < 1e-14
+    # no observation: the analysis is the background
+    H.var3d_analysis(d_xb, d_xa, N, None, None, 0, sd)
+    assert np.array_equal(d_xa.cpu().numpy(), xb)
+    with pytest.raises(RuntimeError, match="out of range"):
+        H.var3d_analysis(d_xb, d_xa, N, torch.tensor([0, N], dtype=torch.int64, device='cuda'),
+                         torch.zeros(2, dtype=torch.float64, device='cuda'), 2, sd)
+
+
+def test_var3d_reference_recipe_through_the_api():
+    """The reference's Var3D test (tests/dacycler_var3d_test.py:11-84) written against this package: the first
+    analysis is its presaved vector; the run equals the oracle's literal cycle (dense H/R/B + conjugate
+    gradients) with the same fixed-step RK4 forecast."""
+    nature = dab.data.Lorenz96(system_dim=6, store_as_jax=True).generate(n_steps=50)
+    obs = dab.observer.Observer(nature, random_time_density=0.7, random_location_count=3, error_bias=0.0,
+                                error_sd=0.7, random_seed=94, stationary_observers=True).observe()
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=6, store_as_jax=True))
+    dc = dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model)
+    init = nature.isel(time=0)
+    x_init = init['x'].values + threefry.normal(42, (6,))
+    init = init.assign(x=(['index'], x_init.copy()))
+    t0 = nature['time'].values[0]
+    out = dc.cycle(input_state=init, start_time=t0, obs_vector=obs, n_cycles=10, analysis_window=0.25,
+                   return_forecast=False)
+    assert out['x'].shape == (10, 6)
+    assert np.allclose(out['x'].values[0], [-0.90632236, -1.20861455, 1.64865068, 5.11034063, 4.399881, -3.75779771])
+    assert np.array_equal(init['x'].values, x_init)                       # the caller's state is untouched
+    fc = lambda x, n: o_l96.generate_rk4(x, n, 0.05)
+    ref = o_var3d.cycle(x_init, t0, obs['x'].values, obs['time'].values, obs['system_index'].values[0], 10, 0.7,
+                        fc, 0.05, analysis_window=0.25, return_forecast=True, literal=True)
+    assert rel_err(out['x'].values, ref[:, 0]) < 1e-9
+    full = dc.cycle(input_state=init, start_time=t0, obs_vector=obs, n_cycles=10, analysis_window=0.25,
+                    return_forecast=True)
+    assert full['x'].shape == (10, 5, 6)
+    assert rel_err(full['x'].values, ref) < 1e-9
+    assert np.array_equal(full['x'].values[:, 0], out['x'].values)
 
 
 @pytest.mark.parametrize("tag", ["c1", "c2", "c3s", "c5s"])

@@ -8,7 +8,7 @@ import scipy.integrate
 import dataassimbench_b200 as dab
 from dataassimbench_b200 import _xr
 from dataassimbench_b200.dacycler import _windows
-from oracle import windows as o_win, l96 as o_l96, l63 as o_l63, observer as o_obs
+from oracle import windows as o_win, l96 as o_l96, l63 as o_l63, observer as o_obs, var3d as o_var3d, threefry
 
 
 @pytest.mark.parametrize("start,w,n,obs_dt,n_obs_t", [
@@ -197,3 +197,85 @@ def test_cycle_batched_marshalling(monkeypatch):
         other = dab.dacycler.ETKF(N, 0.02, dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.02)),
                                   ensemble_dim=k)
         cycle_batched([cyclers[0], other], init, 0.0, obs, n_cycles, analysis_window=0.1)
+
+
+def _var3d_reference_recipe():
+    """The set-up of /root/reference/tests/dacycler_var3d_test.py:11-66 with this package's classes (the
+    nature run comes from the oracle here: `generate()` needs the GPU)."""
+    nature_x = o_l96.generate_dopri5(o_l96.default_x0(6, 0.05), 50, 0.05)
+    times = o_l96.time_grid(50, 0.05)
+    nature = _xr.new_dataset({'x': (('time', 'index'), nature_x)}, coords={'time': times, 'index': np.arange(6)})
+    obs = dab.observer.Observer(nature, random_time_density=0.7, random_location_count=3, error_bias=0.0,
+                                error_sd=0.7, random_seed=94, stationary_observers=True).observe()
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=6, store_as_jax=True))
+    dc = dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model)
+    init = nature.isel(time=0)
+    init = init.assign(x=(['index'], init['x'].values + threefry.normal(42, (6,))))
+    return nature, obs, dc, init, times
+
+
+class _FakeVar3DHandle:
+    """The two device calls of Var3D.cycle answered by the oracle on CPU tensors."""
+
+    def var3d_analysis(self, xb, xa, N, loc, val, n_rows, sd, stream=None):
+        l = loc.numpy() if loc is not None else np.zeros(0, dtype=np.int64)
+        v = val.numpy() if val is not None else np.zeros(0)
+        assert len(l) == n_rows and xb.numel() == N
+        xa.numpy()[:] = o_var3d.analysis_diagonal(xb.numpy(), v, l, np.full(len(l), 1.0 / sd ** 2))
+
+    def l96_forecast(self, x_in, x_out, traj, N, k, n_steps, dt, F, stream=None):
+        last, tr = o_l96.rk4_forecast(x_in.numpy(), n_steps, dt, F, return_traj=True)
+        x_out.numpy()[:] = last
+        if traj is not None:
+            traj.numpy()[:n_steps] = tr[1:]
+
+
+def test_var3d_cycle_host_logic(monkeypatch):
+    """Var3D.cycle's bookkeeping (windows, valid rows, output assembly) against the oracle cycle, with the
+    two device calls replaced by their oracle equivalents; the first analysis is the reference's presaved
+    vector (tests/dacycler_var3d_test.py:70-77)."""
+    pytest.importorskip("torch")
+    nature, obs, dc, init, times = _var3d_reference_recipe()
+    monkeypatch.setattr(dab.dacycler.Var3D, '_device', 'cpu')
+    monkeypatch.setattr(dab.dacycler.Var3D, '_handle', lambda self: _FakeVar3DHandle())
+    out = dc.cycle(input_state=init, start_time=times[0], obs_vector=obs, n_cycles=10, analysis_window=0.25,
+                   return_forecast=False)
+    assert out['x'].shape == (10, 6) and _xr.var_dims(out, 'x') == ('cycle', 'index')
+    assert np.allclose(out['x'].values[0], [-0.90632236, -1.20861455, 1.64865068, 5.11034063, 4.399881, -3.75779771])
+    fc = lambda x, n: o_l96.generate_rk4(x, n, 0.05)
+    ref = o_var3d.cycle(init['x'].values, times[0], obs['x'].values, obs['time'].values,
+                        obs['system_index'].values[0], 10, 0.7, fc, 0.05, analysis_window=0.25,
+                        return_forecast=True, literal=True)
+    assert np.max(np.abs(out['x'].values - ref[:, 0])) < 1e-9
+    full = dc.cycle(input_state=init, start_time=times[0], obs_vector=obs, n_cycles=10, analysis_window=0.25,
+                    return_forecast=True)
+    assert full['x'].shape == (10, 5, 6) and _xr.var_dims(full, 'x') == ('cycle', 'cycle_timestep', 'index')
+    assert np.max(np.abs(full['x'].values - ref)) < 1e-9
+    assert np.array_equal(full['x'].values[:, 0], out['x'].values)
+
+
+def test_var3d_rows_of_cycle_masks():
+    """Two observation times in one window, moving observers with NaN padding, an empty window."""
+    p = dict(padded=np.array([[1, 2], [3, 0], [0, 0]], dtype=np.int64), stationary=False,
+             vals=np.array([[1.0, np.nan], [2.0, 3.0], [np.nan, np.nan]]),
+             sysidx=np.array([[4, 0], [1, 4], [0, 0]], dtype=np.int64))
+    loc, val = dab.dacycler.Var3D._rows_of_cycle(p, 0)
+    assert loc.tolist() == [4, 1, 4] and val.tolist() == [1.0, 2.0, 3.0]
+    loc, val = dab.dacycler.Var3D._rows_of_cycle(p, 1)
+    assert len(loc) == 0 and len(val) == 0                    # its only slot is all padding
+    loc, val = dab.dacycler.Var3D._rows_of_cycle(p, 2)
+    assert len(loc) == 0
+    p['stationary'] = True
+    loc, val = dab.dacycler.Var3D._rows_of_cycle(p, 0)
+    assert loc.tolist() == [4, 0, 1, 4] and np.isnan(val[1])  # stationary observers: all-true mask, as the reference
+
+
+def test_var3d_rejects_what_it_does_not_accelerate():
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=6))
+    nature, obs, dc, init, times = _var3d_reference_recipe()
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, B=np.eye(6)).cycle(init, 0.0, obs, 2)
+    with pytest.raises(ValueError):
+        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, h=lambda x: x).cycle(init, 0.0, obs, 2)
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.Var3D(system_dim=3, delta_t=0.01, model_obj=dab.model.Lorenz63Model()).cycle(init, 0.0, obs, 2)
