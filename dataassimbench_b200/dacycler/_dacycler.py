@@ -44,6 +44,20 @@ class DACycler:
         return dict(centres=centres, padded=padded, obs_times=obs_times,
                     stationary=bool(_xr.get_attr(obs_vector, 'stationary_observers', True)))
 
+    def _lorenz96_generator(self):
+        """The Lorenz-96 generator behind `model_obj`, or None.  The forecast plugin is recognised by
+        what it wraps: the native `Lorenz96Model`, or any `Model` subclass whose `model_obj` is a
+        `data.Lorenz96` -- e.g. the wrapper the reference's cycler tests define inline
+        (tests/dacycler_etkf_test.py:39-46: `forecast` = `model_obj.generate(x0, n_steps)`).  Its
+        `forecast()` body is then not called per member: the forecast kernel integrates that generator
+        (its delta_t and forcing_term) for the whole ensemble."""
+        from ..data import Lorenz96
+        from ..model import Model
+        gen = getattr(self.model_obj, 'model_obj', None)
+        if isinstance(self.model_obj, Model) and isinstance(gen, Lorenz96):
+            return gen
+        return None
+
     def cycle(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
               analysis_window=0.2, analysis_time_in_window=None, return_forecast=False):
         raise NotImplementedError('only the ETKF cycler is accelerated (dataassimbench_b200.dacycler.ETKF)')

@@ -29,16 +29,16 @@ class Var3D(DACycler):
     # ------------------------------------------------------------------ marshalling (CPU-testable)
     def _plan(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
               analysis_window=0.2, analysis_time_in_window=None):
-        from ..model import Lorenz96Model
         if self.h is not None and self.H is None:
             # dabench/dacycler/_dacycler.py:103-104
             raise ValueError('Only linear obs operators (H) are supported right now.')
         if self.H is not None or self.R is not None or self.B is not None:
             raise NotImplementedError('user-supplied H / R / B matrices are outside the accelerated path '
                                       '(default index-gather H, obs_error_sd**2 * I and identity B only)')
-        if not isinstance(self.model_obj, Lorenz96Model):
-            raise NotImplementedError('the accelerated Var3D.cycle() needs model_obj to be a '
-                                      'dataassimbench_b200.model.Lorenz96Model')
+        gen = self._lorenz96_generator()
+        if gen is None:
+            raise NotImplementedError('the accelerated Var3D.cycle() needs model_obj to be a Model wrapping a '
+                                      'dataassimbench_b200.data.Lorenz96 generator (e.g. model.Lorenz96Model)')
         w = self._prepare_cycle(input_state, start_time, obs_vector, n_cycles, obs_error_sd,
                                 analysis_window, analysis_time_in_window)
         if self._data_vars != ['x'] or self._observed_vars != ['x']:
@@ -52,7 +52,6 @@ class Var3D(DACycler):
         vals = np.ascontiguousarray(vals.reshape(len(w['obs_times']), -1))
         sysidx = np.asarray(_xr.var_array(obs_vector, 'system_index'))
         sysidx = np.ascontiguousarray(sysidx.reshape(vals.shape), dtype=np.int64)
-        gen = self.model_obj.model_obj
         return dict(x0=x0, vals=vals, sysidx=sysidx, padded=np.asarray(w['padded'], dtype=np.int64),
                     stationary=w['stationary'], n_steps=self.steps_per_window - 1,
                     model_dt=float(gen.delta_t), forcing=float(gen.forcing_term), sd=float(self.obs_error_sd),

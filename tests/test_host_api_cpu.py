@@ -131,6 +131,36 @@ def test_cycle_plan_marshalling():
     assert dc.steps_per_window == S + 1
 
 
+def test_inline_model_wrapper_of_the_reference_tests_is_recognised():
+    """The reference's cycler tests define their forecast plugin inline
+    (tests/dacycler_etkf_test.py:39-46, tests/dacycler_var3d_test.py:36-45): a Model subclass around a
+    Lorenz96 generator.  It is accepted as it is -- the plan takes delta_t and the forcing from the
+    generator -- while a Model around anything else is refused."""
+    N, k, n_cycles, S = 8, 4, 5, 10
+    ds, obs, _, init = _experiment(N, k, n_cycles, S)
+
+    class L96Model(dab.model.Model):
+        def forecast(self, state_vec, n_steps):
+            new_vec = self.model_obj.generate(x0=state_vec['x'].data, n_steps=n_steps)
+            return new_vec.isel(time=-1), new_vec
+
+    inline = L96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.02, forcing_term=7.5))
+    p = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, model_obj=inline, ensemble_dim=k)._plan(
+        init, 0.0, obs, n_cycles, analysis_window=0.1)
+    assert p['cfg'].model_dt == 0.02 and p['cfg'].forcing == 7.5 and p['cfg'].n_steps == S
+
+    class Other(dab.model.Model):
+        def forecast(self, state_vec, n_steps):
+            return state_vec, state_vec
+
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.ETKF(system_dim=N, delta_t=0.01, model_obj=Other(model_obj=object()), ensemble_dim=k)._plan(
+            init, 0.0, obs, n_cycles, analysis_window=0.1)
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.ETKF(system_dim=N, delta_t=0.01, model_obj=dab.data.Lorenz96(system_dim=N), ensemble_dim=k)._plan(
+            init, 0.0, obs, n_cycles, analysis_window=0.1)       # a bare generator is not a Model
+
+
 def test_cycle_rejects_what_it_does_not_accelerate():
     N, k = 8, 4
     ds, obs, model, init = _experiment(N, k)
