@@ -37,6 +37,10 @@ struct L96Args {
   long long traj_stride;     // doubles between consecutive trajectory steps
   int n_steps, halo_l, useful, tiles_per_member;
   double dt, F;
+  // RK4 coefficients, precomputed on the host so that the kernel takes them from the constant bank
+  // (uniform registers): a DFMA with three distinct REGISTER operands issues every 3 cycles (two
+  // register-file banks, tools/l96_probe2.cu: 65 % of the FP64 rate), with one uniform operand every 2.
+  double h2, h3, h6, h2F, dtF;
 };
 
 // -DDAB_L96_TRACE (debug builds, tools/build_timing.sh): every CTA records {start, loaded, computed,
@@ -99,13 +103,10 @@ l96_rk4_window_kernel(const L96Args a) {
   //   y_2 = xh + h/2 t_1,  y_3 = xh + h/2 t_2,  y_4 = xd + h t_3,    xh = x + h/2 F,  xd = x + h F
   //   x'  = xd + h/6 t_1 + h/3 t_2 + h/3 t_3 + h/6 t_4  (= x + h/6 (k_1 + 2 k_2 + 2 k_3 + k_4))
   double s[P], xh[P], xd[P], acc[P];
-  const double dt = a.dt, F = a.F;
-  const double h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
-  const double h2F = h2 * F, dtF = dt * F;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     s[i] = stage[phys<P>(t * P + i)];
-    xh[i] = s[i] + h2F; xd[i] = s[i] + dtF;
+    xh[i] = s[i] + a.h2F; xd[i] = s[i] + a.dtF;
   }
 
   const int tl = t > 0 ? t - 1 : 0;
@@ -127,8 +128,9 @@ l96_rk4_window_kernel(const L96Args a) {
       const double2 L = e_last2[buf * T + tl];
       const double R = e_first[buf * T + tr];
       buf ^= 1;
-      const double ca = (st == 2) ? dt : h2;                 // next-stage coefficient
-      const double cw = (st == 0 || st == 3) ? h6 : h3;      // RK4 weight
+      // next-stage coefficient ca and RK4 weight cw: uniform operands (see L96Args)
+#define L96_CA (st == 2 ? a.dt : a.h2)
+#define L96_CW ((st == 0 || st == 3) ? a.h6 : a.h3)
       double kk[P];
       // edge points first so the next stage's edges can be published early
       kk[0] = fma((P > 1 ? s[1] : R) - L.x, L.y, -s[0]);
@@ -136,15 +138,15 @@ l96_rk4_window_kernel(const L96Args a) {
       if (P > 2) kk[P - 1] = fma(R - s[P - 3], s[P - 2], -s[P - 1]);
       if (P > 3) kk[P - 2] = fma(s[P - 1] - s[P - 4], s[P - 3], -s[P - 2]);
       if (st < 3) {
-        const double n0 = fma(ca, kk[0], st == 2 ? xd[0] : xh[0]);
-        const double n2 = fma(ca, kk[P - 2], st == 2 ? xd[P - 2] : xh[P - 2]);
-        const double n1 = fma(ca, kk[P - 1], st == 2 ? xd[P - 1] : xh[P - 1]);
+        const double n0 = fma(L96_CA, kk[0], st == 2 ? xd[0] : xh[0]);
+        const double n2 = fma(L96_CA, kk[P - 2], st == 2 ? xd[P - 2] : xh[P - 2]);
+        const double n1 = fma(L96_CA, kk[P - 1], st == 2 ? xd[P - 1] : xh[P - 1]);
         e_first[buf * T + t] = n0;
         e_last2[buf * T + t] = make_double2(n2, n1);
       } else {
-        const double n0 = fma(cw, kk[0], acc[0]);
-        const double n2 = fma(cw, kk[P - 2], acc[P - 2]);
-        const double n1 = fma(cw, kk[P - 1], acc[P - 1]);
+        const double n0 = fma(L96_CW, kk[0], acc[0]);
+        const double n2 = fma(L96_CW, kk[P - 2], acc[P - 2]);
+        const double n1 = fma(L96_CW, kk[P - 1], acc[P - 1]);
         e_first[buf * T + t] = n0;
         e_last2[buf * T + t] = make_double2(n2, n1);
       }
@@ -152,11 +154,13 @@ l96_rk4_window_kernel(const L96Args a) {
       for (int i = 2; i < P - 2; ++i) kk[i] = fma(s[i + 1] - s[i - 2], s[i - 1], -s[i]);
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        if (st == 0) acc[i] = fma(cw, kk[i], xd[i]);
-        else if (st < 3) acc[i] = fma(cw, kk[i], acc[i]);
-        if (st < 3) s[i] = fma(ca, kk[i], st == 2 ? xd[i] : xh[i]);
-        else { s[i] = fma(cw, kk[i], acc[i]); xh[i] = s[i] + h2F; xd[i] = s[i] + dtF; }
+        if (st == 0) acc[i] = fma(L96_CW, kk[i], xd[i]);
+        else if (st < 3) acc[i] = fma(L96_CW, kk[i], acc[i]);
+        if (st < 3) s[i] = fma(L96_CA, kk[i], st == 2 ? xd[i] : xh[i]);
+        else { s[i] = fma(L96_CW, kk[i], acc[i]); xh[i] = s[i] + a.h2F; xd[i] = s[i] + a.dtF; }
       }
+#undef L96_CA
+#undef L96_CW
     }
     if (a.traj != nullptr) {
       double* trow = a.traj + (long long)step * a.traj_stride + (long long)member * a.out_ld;
@@ -289,6 +293,7 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
   a.n = n; a.traj_stride = traj_stride;
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
   a.dt = dt; a.F = F;
+  a.h2 = 0.5 * dt; a.h3 = dt / 3.0; a.h6 = dt / 6.0; a.h2F = a.h2 * F; a.dtF = dt * F;
   if (P == 12) return launch_p<12>(a, k, T, periodic, dense, st);
   if (P == 16) return launch_p<16>(a, k, T, periodic, dense, st);
   return launch_p<8>(a, k, T, periodic, dense, st);
