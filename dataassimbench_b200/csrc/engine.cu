@@ -41,6 +41,32 @@ struct DevBuf {
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
+// scratch of the warp-dataflow forecast kernel (l96_forecast_v2.cu): two ping-pong chunk buffers, one flag
+// per job, the job dispenser.  Flags and dispenser are monotonic (epoch / running base), never reset.
+struct V2Work {
+  DevBuf scr[2], flags, counter;
+  unsigned epoch = 0;
+  unsigned long long ctr_base = 0;
+  cudaError_t reserve(long long n, int k, int n_steps) {
+    const size_t bytes = sizeof(double) * (size_t)k * (size_t)l96_v2_scratch_ld(n, n_steps);
+    cudaError_t e = cudaSuccess;
+    for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = scr[w].reserve(bytes);
+    const size_t fb = sizeof(unsigned) * l96_v2_flag_count(n, k, n_steps);
+    if (e == cudaSuccess && fb > flags.bytes) {
+      e = flags.reserve(fb);
+      if (e == cudaSuccess) e = cudaMemset(flags.p, 0, flags.bytes);
+      epoch = 0;
+    }
+    if (e == cudaSuccess && counter.p == nullptr) {
+      e = counter.reserve(sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMemset(counter.p, 0, sizeof(unsigned long long));
+      ctr_base = 0;
+    }
+    return e;
+  }
+  void release() { scr[0].release(); scr[1].release(); flags.release(); counter.release(); epoch = 0; ctr_base = 0; }
+};
+
 struct Cycler {
   bool ready = false;
   dab_cycle_config cfg{};
@@ -94,7 +120,9 @@ struct dab_handle {
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
+  V2Work v2;                                             // warp-dataflow forecast kernel
   int eig_method = kEigAuto;
+  unsigned long long xchg_timeout_ns = 10000000000ull;   // statistics exchange: give up on a lost peer (DAB_XCHG_TIMEOUT_S, 0 = never)
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
   Cycler cyc;
   // optional per-kernel timing (CUDA events on the launching stream)
@@ -121,6 +149,11 @@ static void prof_mark(dab_handle* h, int tag) {
   h->prof_tags[h->prof_used] = tag;
   h->prof_used++;
 }
+
+// R^-1 for R = sd^2 I the way the reference gets it: pinv(R, rtol=1e-15) (dabench/dacycler/_etkf.py:142),
+// so sd == 0 gives Rinv = 0 (the observations carry no weight; the analysis is the inflated background)
+// and not infinity.  Observer's default error_sd is 0.0, so this case is reachable by default.
+static double r_inv_of(double sd) { return sd == 0.0 ? 0.0 : 1.0 / (sd * sd); }
 
 static std::string g_create_err;
 
@@ -172,6 +205,22 @@ static void cycler_free(dab_handle* h) {
   c.ready = false;
 }
 
+// one launch of the warp-dataflow forecast kernel (workspace reserved by the caller)
+static cudaError_t forecast_v2(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
+                               int chunk_steps, double dt, double F, long long in_ld, long long out_ld,
+                               bool periodic, long long in_base, long long in_lo, long long in_hi) {
+  V2Work& w = h->v2;
+  if (++w.epoch == 0) {                       // 2^32 launches: start the flags over
+    cudaError_t e = cudaMemsetAsync(w.flags.p, 0, w.flags.bytes, h->stream);
+    if (e != cudaSuccess) return e;
+    w.epoch = 1;
+  }
+  return l96_v2_launch(in, out, w.scr[0].as<double>(), w.scr[1].as<double>(),
+                       periodic ? n : l96_v2_scratch_ld(n, steps), w.flags.as<unsigned>(), w.epoch,
+                       w.counter.as<unsigned long long>(), &w.ctr_base, n, k, steps, chunk_steps, dt, F, in_ld,
+                       out_ld, periodic, in_base, in_lo, in_hi, h->sms, h->stream);
+}
+
 // K1 over one window of `steps` <= first_steps steps: extended-layout analysis `in_ext` -> `dst`
 // ([k][n_loc]).  chunks > 1 splits the window into shorter launches through extended scratch
 // buffers: the tile halo is 12 points per step OF THE LAUNCH, so shorter launches recompute less
@@ -181,6 +230,15 @@ static void cycler_free(dab_handle* h) {
 static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, double* dst, double* traj,
                                 long long traj_stride, int steps, int T, int chunks, int* n_launches) {
   const int k = c.cfg.ensemble_dim;
+  if (T >= kL96V2Code && l96_v2_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
+    cudaError_t e = h->v2.reserve(c.n_loc, k, c.first_steps);
+    if (e != cudaSuccess) return e;
+    e = forecast_v2(h, in_ext, dst, c.n_loc, k, steps, T - kL96V2Code, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc,
+                    false, c.halo_l, -8ll * steps, c.n_loc + 4ll * steps);
+    if (e == cudaSuccess && n_launches) ++*n_launches;
+    return e;
+  }
+  if (T >= kL96V2Code) T = 0;                 // not eligible (odd sizes, trajectory wanted): first design, heuristic shape
   if (traj != nullptr || chunks <= 1 || steps < 2 * chunks) chunks = 1;
   const double* src = in_ext;
   int done = 0;
@@ -239,6 +297,7 @@ int dab_create(dab_handle** out, int device) {
   if (e == cudaSuccess) e = h->ns_ws.reserve(ns_ws_bytes(kMaxEns));
   if (e == cudaSuccess) e = cudaMemset(h->ns_ws.p, 0, 16);
   if (e != cudaSuccess) { delete h; return fail(nullptr, (int)e, "dab_create: %s", cudaGetErrorString(e)); }
+  if (const char* ev = getenv("DAB_XCHG_TIMEOUT_S")) { const double v = atof(ev); h->xchg_timeout_ns = v > 0.0 ? (unsigned long long)(v * 1e9) : 0ull; }
   if (const char* ev = getenv("DAB_EIG_METHOD")) {
     if (!strcmp(ev, "jacobi")) h->eig_method = kEigJacobi;
     else if (!strcmp(ev, "ns")) h->eig_method = kEigNewtonSchulz;
@@ -254,6 +313,7 @@ int dab_destroy(dab_handle* h) {
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_seg.release();
   h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release();
+  h->v2.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
   h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -405,14 +465,25 @@ static int stats_from_arrays(dab_handle* h, const double* X, const double* y, co
   DAB_CUDA(h, h->s_seg.reserve(sizeof(long long) * 3));
   const int grid = contract_grid(n_y, h->sms);
   DAB_CUDA(h, h->s_partial.reserve(sizeof(double) * contract_partial_doubles(k, grid)));
-  DAB_CUDA(h, pack_obs_launch(reinterpret_cast<const long long*>(idx), mask, y, n_y,
-                              h->s_loc.as<int>(), h->s_val.as<double>(), st));
+  DAB_CUDA(h, h->s_flag.reserve(sizeof(int)));
+  DAB_CUDA(h, cudaMemsetAsync(h->s_flag.p, 0, sizeof(int), st));
+  DAB_CUDA(h, pack_obs_launch(reinterpret_cast<const long long*>(idx), mask, y, n_y, N,
+                              h->s_loc.as<int>(), h->s_val.as<double>(), h->s_flag.as<int>(), st));
   const long long seg[3] = {0, n_y, 0};
   DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
   DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
                               h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, false, st));
-  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, 1.0 / (sd * sd), stats, nullptr, st));
+  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, r_inv_of(sd), stats, nullptr, st));
   h->launches += (n_y > 0 ? 1 : 0) + 2;
+  return 0;
+}
+
+// the device-side index check of pack_obs_kernel: read back (synchronises the stream)
+static int check_index_flag(dab_handle* h, const char* who, cudaStream_t st) {
+  int bad = 0;
+  DAB_CUDA(h, cudaMemcpyAsync(&bad, h->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, -1, "%s: an observation index of a valid row is outside [0, N)", who);
   return 0;
 }
 
@@ -422,10 +493,14 @@ int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, const in
   DAB_ARG(h, h != nullptr);
   DAB_ARG(h, X != nullptr && stats != nullptr && N >= 1 && n_y >= 0);
   DAB_ARG(h, k >= 2 && k <= DAB_MAX_ENSEMBLE);
-  DAB_ARG(h, obs_error_sd > 0.0);
+  DAB_ARG(h, obs_error_sd == obs_error_sd);            // not NaN; 0 means Rinv = 0 (see r_inv_of)
+  DAB_ARG(h, N < (1ll << 31));
+  DAB_ARG(h, n_y == 0 || (y != nullptr && idx != nullptr));
   DAB_CUDA(h, cudaSetDevice(h->device));
-  return stats_from_arrays(h, X, y, idx, mask, obs_error_sd, N, k, n_y, stats,
-                           static_cast<cudaStream_t>(stream));
+  int rc = stats_from_arrays(h, X, y, idx, mask, obs_error_sd, N, k, n_y, stats,
+                             static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return n_y > 0 ? check_index_flag(h, "dab_etkf_stats_f64", static_cast<cudaStream_t>(stream)) : 0;
 }
 
 int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, double rho,
@@ -446,7 +521,7 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
   DAB_ARG(h, h != nullptr);
   DAB_ARG(h, Xb != nullptr && Xa != nullptr && Xb != Xa);
   DAB_ARG(h, N >= 1 && n_y >= 0 && k >= 2 && k <= DAB_MAX_ENSEMBLE);
-  DAB_ARG(h, rho > 0.0 && (n_y == 0 || obs_error_sd > 0.0));
+  DAB_ARG(h, rho > 0.0 && obs_error_sd == obs_error_sd);
   DAB_ARG(h, n_y == 0 || (y != nullptr && idx != nullptr));
   DAB_ARG(h, N < (1ll << 31));
   DAB_CUDA(h, cudaSetDevice(h->device));
@@ -468,7 +543,7 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
   a.halo_l = 0; a.halo_r = 0; a.k = k; a.rank = 0;
   DAB_CUDA(h, transform_launch(a, h->sms, st));
   h->launches += 2;
-  return 0;
+  return empty_R ? 0 : check_index_flag(h, "dab_etkf_analysis_f64", st);
 }
 
 // ------------------------------------------------------------------------------ the cycler
@@ -482,6 +557,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   DAB_ARG(h, cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= DAB_MAX_ENSEMBLE);
   DAB_ARG(h, cfg->n_steps >= 0 && cfg->n_cycles >= 0 && cfg->t_pad >= 0);
   DAB_ARG(h, cfg->rho > 0.0 && cfg->model_dt > 0.0);
+  DAB_ARG(h, cfg->obs_error_sd == cfg->obs_error_sd);   // not NaN; 0 means Rinv = 0 (see r_inv_of)
   DAB_ARG(h, cfg->world >= 1 && cfg->world <= DAB_MAX_RANKS && cfg->rank >= 0 && cfg->rank < cfg->world);
   DAB_ARG(h, cfg->system_dim % cfg->world == 0);
   DAB_ARG(h, cfg->n_obs_times >= 0 && cfg->n_obs >= 0);
@@ -506,6 +582,10 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   c.ld_e = (c.halo_l + c.n_loc + c.halo_r + 1) & ~1ll;
   // the reference's empty-R branch: no observation slot at all (T_pad * n_obs == 0)
   c.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
+  // grid-sharded runs are ordered by the statistics exchange alone (the halo reads of the transform
+  // rely on it); without any observation slot there is no exchange, so such a run is refused
+  if (cfg->world > 1 && c.empty_R)
+    return fail(h, -1, "a grid-sharded run (world = %d) needs observations: the statistics exchange is its only inter-rank ordering", cfg->world);
   c.cur = 0;
   const size_t slab = sizeof(double) * (size_t)k * c.n_loc;
   if (slab > c.xb_bytes) {
@@ -637,8 +717,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     cudaEvent_t e0, e1;
     DAB_CUDA(h, cudaEventCreate(&e0));
     DAB_CUDA(h, cudaEventCreate(&e1));
-    const int n_cand = 17;
-    const int cand[n_cand] = {128, 192, 256, 320, 384, 512,
+    const int n_cand = 20;
+    const int cand[n_cand] = {kL96V2Code + 5, kL96V2Code + 4, kL96V2Code + 3, 128, 192, 256, 320, 384, 512,
                               l96_shape_code(16, 128), l96_shape_code(16, 160), l96_shape_code(16, 192),
                               l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
                               l96_shape_code(17, 160), l96_shape_code(17, 192),
@@ -654,8 +734,12 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
       if (chunks > 1 && c.first_steps < 2 * chunks) continue;
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
-        if (l96_shape_width(cand[ci]) < 12 * longest + 16) continue;
-        if (chunks > 1 && cand[ci] >= 1000) continue;
+        if (cand[ci] >= kL96V2Code) {
+          if (chunks > 1 || !l96_v2_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
+        } else {
+          if (l96_shape_width(cand[ci]) < 12 * longest + 16) continue;
+          if (chunks > 1 && cand[ci] >= 1000) continue;
+        }
         float ms = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
           DAB_CUDA(h, cudaEventRecord(e0, h->stream));
@@ -676,6 +760,11 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     h->tune_key.push_back(tkey);
     h->tune_T.push_back(c.l96_T);
     h->tune_chunks.push_back(c.l96_chunks);
+  }
+  if (const char* ev = getenv("DAB_L96_V2")) {              // force (1..6 = steps per chunk) or forbid (0) the warp-dataflow kernel
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 6) c.l96_T = kL96V2Code + v;
+    else if (v == 0 && c.l96_T >= kL96V2Code) c.l96_T = 0;
   }
   if (const char* ev = getenv("DAB_L96_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) c.l96_chunks = v; }
   h->launches = 0;
@@ -723,7 +812,7 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
                               c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
                               c.partial.as<double>(), grid, true, h->stream));
   prof_mark(h, PROF_CONTRACT);
-  const double r_inv = 1.0 / (c.cfg.obs_error_sd * c.cfg.obs_error_sd);
+  const double r_inv = r_inv_of(c.cfg.obs_error_sd);
   if (stats_exchange_ready(c)) {
     // reduction fused with the all-gather of the ranks' statistics over peer memory, then the
     // rank-ordered sum (replaces reduce + NCCL all-reduce; see stats_reduce_kernel)
@@ -741,7 +830,7 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
     DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k, r_inv, nullptr, &push, h->stream));
     DAB_CUDA(h, stats_gather_launch(c.xchg.as<unsigned long long>() + par * kMaxRanks, seq,
                                     reinterpret_cast<const double*>(c.xchg.as<char>() + kXchgHeader) + (size_t)par * G * len,
-                                    k, G, c.stats.as<double>(), h->stream));
+                                    k, G, c.stats.as<double>(), h->xchg_timeout_ns, h->stream));
     h->launches += 1;
   } else {
     DAB_CUDA(h, stats_reduce_launch(c.partial.as<double>(), grid, k, r_inv, c.stats.as<double>(), nullptr, h->stream));
@@ -771,6 +860,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   DAB_CUDA(h, eig_transform_launch(c.stats.as<double>(), k, c.cfg.rho, c.empty_R, c.T.as<double>(),
                                    nullptr, c.info.as<int>(), h->ns_ws.as<double>(), h->eig_method, h->stream));
   prof_mark(h, PROF_EIG);
+  if (k > 64 && !c.empty_R && h->eig_method != kEigJacobi) h->launches += 1;   // Newton-Schulz + the (flag-gated) Jacobi fallback kernel
   if (c.copied_pending[eb]) {                 // the D2H of cycle-2's analysis still reads ext[eb]
     DAB_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_copied[eb], 0));
     c.copied_pending[eb] = false;
@@ -833,7 +923,8 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
     double* first_dst = (rest_chunks % 2 == 0) ? nxt : tmp;
     DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), first_dst, out_traj, c.n_loc, k, c.first_steps,
                                     c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l,
-                                    -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms, c.l96_T, h->stream));
+                                    -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms,
+                                    c.l96_T >= kL96V2Code ? 0 : c.l96_T, h->stream));
     h->launches++;
     const double* src = first_dst;
     int done = c.first_steps;
@@ -942,7 +1033,7 @@ int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int b
   DAB_ARG(h, cfg->system_dim * cfg->ensemble_dim <= 4096);
   DAB_ARG(h, cfg->n_steps >= 0 && cfg->n_cycles >= 0 && cfg->t_pad >= 0 && cfg->n_obs >= 0);
   DAB_ARG(h, (long long)cfg->t_pad * cfg->n_obs * cfg->ensemble_dim <= 8192);
-  DAB_ARG(h, cfg->model_dt > 0.0 && (cfg->obs_error_sd > 0.0 || cfg->t_pad * cfg->n_obs == 0));
+  DAB_ARG(h, cfg->model_dt > 0.0 && cfg->obs_error_sd == cfg->obs_error_sd);
   DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 || (obs_values != nullptr && system_index != nullptr));
   DAB_ARG(h, cfg->n_cycles * cfg->t_pad == 0 || padded_time_idx != nullptr);
   DAB_CUDA(h, cudaSetDevice(h->device));
@@ -983,7 +1074,7 @@ int dab_etkf_cycle_batched_f64(dab_handle* h, const dab_cycle_config* cfg, int b
   a.n_obs = (int)cfg->n_obs;
   a.empty_R = ((long long)cfg->t_pad * cfg->n_obs == 0) || cfg->n_obs_times == 0;
   a.force_jacobi = h->eig_method == kEigJacobi;
-  a.dt = cfg->model_dt; a.F = cfg->forcing; a.sd = cfg->obs_error_sd > 0.0 ? cfg->obs_error_sd : 1.0;
+  a.dt = cfg->model_dt; a.F = cfg->forcing; a.r_inv = r_inv_of(cfg->obs_error_sd); a.stationary = cfg->stationary;
   DAB_CUDA(h, batched_launch(a, batch, st));
   h->launches++;
   if (out_analysis) DAB_CUDA(h, cudaMemcpyAsync(out_analysis, a.out_analysis, sizeof(double) * kN * batch * cfg->n_cycles, cudaMemcpyDeviceToHost, st));

@@ -63,7 +63,7 @@ etkf_batched_kernel(const BatchedArgs a) {
   double* ew = Tm + k * k;                              // eigensolver workspace
 
   const double rho = a.rho[b];
-  const double r_inv = 1.0 / (a.sd * a.sd);
+  const double r_inv = a.r_inv;
   const double inv_k = 1.0 / (double)k;
   const double dt = a.dt, F = a.F, h2 = 0.5 * dt, h6 = dt / 6.0, h3 = dt / 3.0;
   const int lpp = eig_small_lpp(k);
@@ -118,7 +118,9 @@ etkf_batched_kernel(const BatchedArgs a) {
       if (ti > 0) {
         y = vals_b[(ti - 1) * a.n_obs + o];
         loc = (int)idx_b[(ti - 1) * a.n_obs + o];
-        if (y != y) { loc = -1; y = 0.0; }              // NaN = padded slot of a non-stationary network
+        // NaN = padded slot of a non-stationary network (_dacycler.py:266-268); for a stationary one the
+        // reference's location mask is all ones and a NaN value is data (it propagates), as in engine.cu
+        if (!a.stationary && y != y) { loc = -1; y = 0.0; }
       }
       double sum = 0.0;
       for (int j = 0; j < k; ++j) {

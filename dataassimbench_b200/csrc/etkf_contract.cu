@@ -212,10 +212,11 @@ stats_reduce_kernel(const double* __restrict__ partial, int n_part, int kp, int 
 
 // Waits until every rank's flag has reached `seq` (P2P stores, see above), then
 // stats = sum over ranks of their slots, in rank order.  A peer that never arrives is a lost
-// process: after 10 s the kernel traps instead of hanging the GPU.
+// process: after `timeout_ns` (10 s by default, DAB_XCHG_TIMEOUT_S; 0 = wait for ever, e.g. under a
+// profiler's kernel replay or a debugger) the kernel traps instead of hanging the GPU.
 __global__ void __launch_bounds__(256)
 stats_gather_kernel(const unsigned long long* flags, unsigned long long seq, const double* slots,
-                    int n_el, int world, double* __restrict__ stats) {
+                    int n_el, int world, double* __restrict__ stats, unsigned long long timeout_ns) {
   if (threadIdx.x == 0) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -224,7 +225,7 @@ stats_gather_kernel(const unsigned long long* flags, unsigned long long seq, con
       while (*f < seq) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 10000000000ull) __trap();
+        if (timeout_ns != 0ull && t1 - t0 > timeout_ns) __trap();
         __nanosleep(100);
       }
     }
@@ -280,10 +281,10 @@ cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double
 }
 
 cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,
-                                int k, int world, double* stats, cudaStream_t st) {
+                                int k, int world, double* stats, unsigned long long timeout_ns, cudaStream_t st) {
   const int n_el = k * k + k;
   return launch_chain(true, stats_gather_kernel, dim3((n_el + 255) / 256), dim3(256), 0, st, flags, seq, slots,
-                      n_el, world, stats);
+                      n_el, world, stats, timeout_ns);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,20 +406,24 @@ cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, lon
 
 // Build a compact (loc, val) list on device from reference-style arrays (used by the
 // single-analysis entry point): rows with mask == 0 are kept as loc = -1 (contribute nothing).
+// An index of a valid row outside [0, N) is reported through *bad (and contributes nothing) instead of
+// being dereferenced by the contraction.
 __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigned char* __restrict__ mask,
-                                const double* __restrict__ y, long long n_y,
-                                int* __restrict__ loc, double* __restrict__ val) {
+                                const double* __restrict__ y, long long n_y, long long N,
+                                int* __restrict__ loc, double* __restrict__ val, int* __restrict__ bad) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= n_y) return;
-  const bool ok = mask == nullptr || mask[r] != 0;
-  loc[r] = ok ? (int)idx[r] : -1;
+  bool ok = mask == nullptr || mask[r] != 0;
+  const long long l = idx[r];
+  if (ok && (l < 0 || l >= N)) { ok = false; *bad = 1; }
+  loc[r] = ok ? (int)l : -1;
   val[r] = ok ? y[r] : 0.0;
 }
 
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
-                            long long n_y, int* loc, double* val, cudaStream_t st) {
+                            long long n_y, long long N, int* loc, double* val, int* bad, cudaStream_t st) {
   if (n_y <= 0) return cudaSuccess;
-  pack_obs_kernel<<<(unsigned)((n_y + 255) / 256), 256, 0, st>>>(idx, mask, y, n_y, loc, val);
+  pack_obs_kernel<<<(unsigned)((n_y + 255) / 256), 256, 0, st>>>(idx, mask, y, n_y, N, loc, val, bad);
   return cudaGetLastError();
 }
 

@@ -20,6 +20,18 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 long long traj_stride, int sms, int forced_T /* 0 = heuristic */,
                                 cudaStream_t st);
 
+// K1, warp-dataflow design  l96_forecast_v2.cu (shape code 20000 + steps per chunk)
+constexpr int kL96V2Code = 20000;
+bool l96_v2_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
+                     long long in_base, int n_steps, bool traj);
+long long l96_v2_scratch_ld(long long n, int n_steps);
+size_t l96_v2_flag_count(long long n, int k, int n_steps);
+cudaError_t l96_v2_launch(const double* in, double* out, double* scratch0, double* scratch1, long long scr_ld,
+                          unsigned* flags, unsigned epoch, unsigned long long* counter, unsigned long long* ctr_base,
+                          long long n, int k, int n_steps, int chunk_steps,
+                          double dt, double F, long long in_ld, long long out_ld, bool periodic,
+                          long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st);
+
 // Lorenz-63 members [k][3]  l63_forecast.cu
 cudaError_t l63_forecast_launch(const double* x_in, double* x_out, double* traj, long long k, int n_steps,
                                 double dt, double sigma, double rho, double beta, cudaStream_t st);
@@ -45,7 +57,7 @@ struct StatsPush {
 cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
                                 const StatsPush* push /* nullable */, cudaStream_t st);
 cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,
-                                int k, int world, double* stats, cudaStream_t st);
+                                int k, int world, double* stats, unsigned long long timeout_ns, cudaStream_t st);
 cudaError_t gather_launch(const double* X, long long ld, int k, const long long* idx,
                           const unsigned char* mask, long long n_y, double* Yb, cudaStream_t st);
 cudaError_t observe_launch(const double* state, long long N, long long n_state_times, const long long* time_pos, long long n_t,
@@ -55,7 +67,7 @@ cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, lon
                                   const double* val, long long n_rows, double w, int* bad, int sms,
                                   cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
-                            long long n_y, int* loc, double* val, cudaStream_t st);
+                            long long n_y, long long N, int* loc, double* val, int* bad, cudaStream_t st);
 
 // K4  etkf_eig.cu (Jacobi eigensolver) and etkf_ns.cu (cluster Newton-Schulz, 32 < k <= 128)
 enum { kEigAuto = 0, kEigJacobi = 1, kEigNewtonSchulz = 2 };
@@ -100,7 +112,8 @@ struct BatchedArgs {
   long long n_obs_times;
   int k, N, n_steps, n_cycles, t_pad, n_obs, empty_R;
   int force_jacobi;            // K4 by the Jacobi eigensolver only (dab_set_eig_method)
-  double dt, F, sd;
+  double dt, F, r_inv;       // r_inv = 1 / sd^2, or 0 for sd == 0 (pinv of a zero R)
+  int stationary;            // != 0: NaN observation values are data (they propagate), not padding
 };
 size_t batched_smem_bytes(int k, int N, int t_pad, int n_obs);
 cudaError_t batched_launch(const BatchedArgs& a, int batch, cudaStream_t st);

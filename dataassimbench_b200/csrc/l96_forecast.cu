@@ -248,9 +248,8 @@ static cudaError_t launch_p(const L96Args& a, int k, int T, bool periodic, bool 
 // more SMs get a tile, wider when the halo would exceed half of the tile.  Problems large enough to
 // matter do not come through here: the cycler measures all shapes at setup (engine.cu) and passes
 // the winner as `forced_T`.
-static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per_thread, int forced_T,
+static bool l96_plan(long long n, int k, int steps, int sms, int P, int t_max, int forced_T,
                      int* T_out, int* useful_out, int* tiles_out) {
-  (void)regs_per_thread;
   const int halo = 12 * steps;
   int T = 256;
   if (forced_T >= 32 && forced_T <= 512 && forced_T % 32 == 0 && forced_T * P >= halo + 16) {
@@ -259,10 +258,14 @@ static void l96_plan(long long n, int k, int steps, int sms, int P, int regs_per
     while (T * P < 2 * halo + 16 && T < 512) T += 32;      // keep the halo below half of the tile
     while (T > 64 && ceil_div_ll(n, T * P - halo) * k < 3ll * sms && (T / 2) * P >= 2 * halo + 16) T /= 2;
   }
+  // the launch is bounded by the build's __launch_bounds__: plan for the width that will really run
+  if (T > t_max) T = t_max;
+  if (T * P < halo + 16) return false;                     // this build cannot hold the window's halo
   const long long tiles = ceil_div_ll(n, T * P - halo);
   *T_out = T;
   *tiles_out = (int)tiles;
   *useful_out = (int)ceil_div_ll(n, tiles);                // balance the tiles
+  return true;
 }
 
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
@@ -282,11 +285,15 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
     forced_T %= 1000;
     P = c == 12 ? 12 : 16;
     dense = c == 17;
-    const int tmax = P == 12 ? 192 : (dense ? 192 : 256);
-    if (forced_T > tmax) forced_T = tmax;
   }
   int T = 256, useful = 0, tiles = 0;
-  l96_plan(n, k, n_steps, sms, P, P == 8 ? 88 : 72, forced_T, &T, &useful, &tiles);
+  int tmax = P == 8 ? 512 : (P == 12 ? 192 : (dense ? 192 : 256));
+  if (forced_T > tmax) forced_T = tmax;
+  if (!l96_plan(n, k, n_steps, sms, P, tmax, forced_T, &T, &useful, &tiles)) {
+    // a forced 12/16-point shape too narrow for this window's halo: the 8-point build (up to 512 threads) holds it
+    P = 8; dense = false; tmax = 512;
+    if (!l96_plan(n, k, n_steps, sms, P, tmax, 0, &T, &useful, &tiles)) return cudaErrorInvalidValue;
+  }
   L96Args a;
   a.in = in; a.out = out; a.traj = traj;
   a.in_ld = in_ld; a.out_ld = out_ld; a.in_base = in_base; a.in_lo = in_lo; a.in_hi = in_hi;

@@ -15,9 +15,11 @@
  *     never frees caller memory; "host" pointers are host memory (pinned for async overlap);
  *   - work is enqueued on the stream passed in (or the handle's own stream for the cycler);
  *     nothing synchronises implicitly except dab_destroy, dab_sync and the *_host entry points;
- *   - one handle per host thread and per GPU; multi-GPU = one process (rank) per GPU, the
- *     k*k+k statistics are all-reduced by the caller between dab_cycler_stats and
- *     dab_cycler_update (NCCL through torch.distributed), halos travel by peer-mapped loads.
+ *   - one handle per host thread and per GPU; multi-GPU = one process (rank) per GPU.  With the peers'
+ *     buffers registered (dab_cycler_ipc_import / dab_cycler_set_peer) the k*k+k statistics are summed
+ *     on the device inside dab_cycler_stats (P2P stores over NVLink) and halos travel by peer-mapped
+ *     loads; without them the caller all-reduces dab_cycler_stats_ptr between dab_cycler_stats and
+ *     dab_cycler_update (e.g. NCCL through torch.distributed).
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef DAB_B200_H
@@ -49,9 +51,9 @@ DAB_API int dab_sync(dab_handle* h);
 DAB_API const char* dab_last_error(const dab_handle* h);   /* h may be NULL: last create() error */
 
 /* How the k x k part of the analysis (pinv + sqrtm, dabench/dacycler/_etkf.py:142-154) is solved
- * for 32 < k <= 128.  AUTO: Newton-Schulz inverse square root on an 8-CTA cluster, with the
- * Jacobi eigensolver as the automatic fallback (ill-conditioned or non-finite statistics, or when
- * eigenvalues are requested); JACOBI: always the eigensolver.  k <= 32 always uses Jacobi.
+ * AUTO: Newton-Schulz inverse square root -- on an 8-CTA cluster for 32 < k <= 128, inside one CTA for
+ * k <= 32 -- with the Jacobi eigensolver as the automatic fallback (ill-conditioned or non-finite
+ * statistics, the empty-R branch, or when eigenvalues are requested); JACOBI: always the eigensolver.
  * Also settable with the environment variable DAB_EIG_METHOD=jacobi|ns before dab_create. */
 #define DAB_EIG_AUTO 0
 #define DAB_EIG_JACOBI 1
@@ -123,7 +125,9 @@ DAB_API int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, 
 /* ---- K3+K4: statistics and transform matrix (exposed for tests and for rank-parallel use) -
  * stats = [C (k*k, row-major) | g (k)] with C = Yb'^T Rinv Yb', g = Yb'^T Rinv (y - ybar)
  * (dabench/dacycler/_etkf.py:137-146,154) for R = obs_error_sd^2 I
- * (DACycler._calc_default_R, dabench/dacycler/_dacycler.py:68-72). */
+ * (DACycler._calc_default_R, dabench/dacycler/_dacycler.py:68-72).  obs_error_sd == 0 gives Rinv = 0, as
+ * the reference's pinv(R) does (stats = 0).  Synchronises the stream; returns -1 if the index of a
+ * valid row is outside [0, N). */
 DAB_API int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, const int64_t* idx,
                        const uint8_t* mask, double obs_error_sd, int64_t N, int k, int64_t n_y,
                        double* stats, void* stream);
@@ -139,7 +143,9 @@ DAB_API int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, in
  * the default operators (H = index gather, R = sd^2 I).
  *   Xb [k][N] dev, Xa [k][N] dev (may not alias), y [n_y] dev, idx [n_y] dev int64,
  *   mask nullable [n_y] dev uint8 (time mask AND location mask), rho = multiplicative inflation.
- *   n_y == 0 reproduces the reference's empty-R branch. */
+ *   n_y == 0 reproduces the reference's empty-R branch; obs_error_sd == 0 gives Rinv = 0 (pinv of a zero R:
+ *   the analysis is the inflated background).  With n_y > 0 the call synchronises the stream and returns -1
+ *   if the index of a valid row is outside [0, N). */
 DAB_API int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
                           const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
                           int64_t N, int k, int64_t n_y, void* stream);

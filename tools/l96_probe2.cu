@@ -36,9 +36,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
       "@!p bra W; }" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
-template <int CM, int XM, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) probe(double* out, int n_steps, double dt_in, double F_in, const Coef c) {
-  constexpr int P = 16;
+template <int CM, int XM, int MAXT, int MINB, int NCH = 1, int P = 16>
+__global__ void __launch_bounds__(MAXT, MINB) probe(double* out, int n_steps, double dt_in, double F_in, const Coef c, int stagger) {
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5, NW = blockDim.x >> 5;
   // per warp and parity: 8 doubles for the right neighbour's left halo, 4 for the left neighbour's right halo
@@ -57,6 +56,15 @@ __global__ void __launch_bounds__(MAXT, MINB) probe(double* out, int n_steps, do
   if (XM == 5) {
     if (t < NW) reinterpret_cast<volatile int*>(bars)[t] = 0;
     __syncthreads();
+  }
+  // chains: NCH independent groups of consecutive warps inside the CTA (own named barrier, no exchange
+  // across the group boundary), started `stagger` cycles apart so that their per-step sync bubbles do
+  // not coincide; with NCH == 1 the stagger goes by blockIdx (co-resident CTAs)
+  const int wpc = NW / NCH, chain = w / wpc, wc = w - chain * wpc;
+  if (stagger > 0) {
+    const long long t0 = clock64();
+    const long long d = (long long)stagger * (NCH > 1 ? chain : (int)(blockIdx.x % MINB));
+    while (clock64() - t0 < d) { }
   }
   for (int step = 0; step < n_steps; ++step) {
 #pragma unroll
@@ -93,44 +101,46 @@ __global__ void __launch_bounds__(MAXT, MINB) probe(double* out, int n_steps, do
       double* mine = edge + (b * NW + w) * 12;
       if (lane == 31) {
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(mine + i) = make_double2(s[4 + i], s[5 + i]);
+        for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2*>(mine + i) = make_double2(s[P - 12 + i], s[P - 11 + i]);
       }
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 4; i += 2) *reinterpret_cast<double2*>(mine + 8 + i) = make_double2(s[8 + i], s[9 + i]);
       }
       if (XM == 2) __syncthreads();
-      else if (XM == 5) {                       // monotonic step counters in shared memory
-        volatile int* flags = reinterpret_cast<volatile int*>(bars);
+      else if (XM == 6) asm volatile("bar.sync %0, %1;" ::"r"(chain + 1), "r"(wpc * 32) : "memory");
+      else if (XM == 5) {                       // monotonic step counters in shared memory; the WHOLE warp polls
+        unsigned* flags = reinterpret_cast<unsigned*>(bars);   // (a spin loop under `if (lane == ..)` leaves the warp split)
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); flags[w] = step + 1; }
-        if (lane == 0 && w > 0) flag_wait(flags + w - 1, step + 1);
-        if (lane == 31 && w < NW - 1) flag_wait(flags + w + 1, step + 1);
-        __syncwarp();
+        if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(flags + w)), "r"(step + 1) : "memory");
+        const unsigned fl = smem_u32(flags + (w > 0 ? w - 1 : w + 1)), fr = smem_u32(flags + (w < NW - 1 ? w + 1 : w - 1));
+        unsigned a, bb;
+        do {
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(a) : "r"(fl) : "memory");
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(bb) : "r"(fr) : "memory");
+        } while ((int)a < step + 1 || (int)bb < step + 1);
       } else if (XM == 4) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[b * NW + w]);
         const unsigned par = (step >> 1) & 1;
-        if (lane == 0 && w > 0) mbar_test_wait(&bars[b * NW + w - 1], par);
-        if (lane == 31 && w < NW - 1) mbar_test_wait(&bars[b * NW + w + 1], par);
-        __syncwarp();
+        mbar_test_wait(&bars[b * NW + (w > 0 ? w - 1 : w + 1)], par);
+        mbar_test_wait(&bars[b * NW + (w < NW - 1 ? w + 1 : w - 1)], par);
       } else {
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[b * NW + w]);
         const unsigned par = (step >> 1) & 1;
-        if (lane == 0 && w > 0) mbar_wait(&bars[b * NW + w - 1], par);
-        if (lane == 31 && w < NW - 1) mbar_wait(&bars[b * NW + w + 1], par);
-        __syncwarp();
+        mbar_wait(&bars[b * NW + (w > 0 ? w - 1 : w + 1)], par);
+        mbar_wait(&bars[b * NW + (w < NW - 1 ? w + 1 : w - 1)], par);
       }
-      if (lane == 0 && w > 0) {
+      if (lane == 0 && (XM == 6 ? wc > 0 : w > 0)) {
         const double* src = edge + (b * NW + w - 1) * 12;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) { const double2 v = *reinterpret_cast<const double2*>(src + i); s[i] = v.x; s[i + 1] = v.y; }
       }
-      if (lane == 31 && w < NW - 1) {
+      if (lane == 31 && (XM == 6 ? wc < wpc - 1 : w < NW - 1)) {
         const double* src = edge + (b * NW + w + 1) * 12 + 8;
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) { const double2 v = *reinterpret_cast<const double2*>(src + i); s[12 + i] = v.x; s[13 + i] = v.y; }
+        for (int i = 0; i < 4; i += 2) { const double2 v = *reinterpret_cast<const double2*>(src + i); s[P - 4 + i] = v.x; s[P - 3 + i] = v.y; }
       }
     }
 #pragma unroll
@@ -173,8 +183,8 @@ __global__ void __launch_bounds__(384, 1) rate(double* out, int iters, double a,
 static int g_sms = 148;
 static double* g_out;
 
-template <int CM, int XM, int MAXT, int MINB>
-void run(const char* name, int T, int ctas_per_sm) {
+template <int CM, int XM, int MAXT, int MINB, int NCH = 1, int P = 16>
+void run(const char* name, int T, int ctas_per_sm, int stagger = 0) {
   const int steps = 400;
   const int NW = T / 32;
   const size_t smem = (2 * NW * 12 + 2 * NW) * sizeof(double) + 64;
@@ -185,15 +195,15 @@ void run(const char* name, int T, int ctas_per_sm) {
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    probe<CM, XM, MAXT, MINB><<<grid, T, smem>>>(g_out, steps, dt, F, c);
+    probe<CM, XM, MAXT, MINB, NCH, P><<<grid, T, smem>>>(g_out, steps, dt, F, c, stagger);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
   }
-  const double inst = (double)grid * T * 16 * steps * 17;
+  const double inst = (double)grid * T * P * steps * 17;
   const double rate = inst / (best * 1e-3) / (g_sms * 64.0) / 1.965e9;
-  printf("%-34s CM=%d XM=%d T=%3d x%d  %.3f ms  FP64 pipe %.1f %%  (%.2f TF by the 29-flop convention) %s\n", name, CM, XM, T,
-         ctas_per_sm, best, 100 * rate, (double)grid * T * 16 * steps * 29 / (best * 1e-3) / 1e12,
+  printf("%-34s P=%d CM=%d XM=%d NCH=%d stagger=%4d T=%3d x%d  %.3f ms  FP64 pipe %.1f %%  (%.2f TF by the 29-flop convention) %s\n", name, P, CM, XM, NCH, stagger, T,
+         ctas_per_sm, best, 100 * rate, (double)grid * T * P * steps * 29 / (best * 1e-3) / 1e12,
          cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -218,16 +228,22 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   g_sms = p.multiProcessorCount;
   cudaMalloc(&g_out, sizeof(double) * 148 * 16 * 512);
-  run<1, 1, 384, 1>("shuffles", 384, 1);
-  run<1, 2, 128, 3>("shfl+step halo, syncthreads", 128, 3);
-  run<1, 2, 384, 1>("shfl+step halo, syncthreads", 384, 1);
-  run<1, 4, 128, 3>("shfl+step halo, mbar test_wait", 128, 3);
-  run<1, 4, 384, 1>("shfl+step halo, mbar test_wait", 384, 1);
-  run<1, 5, 128, 3>("shfl+step halo, smem flags", 128, 3);
-  run<1, 5, 384, 1>("shfl+step halo, smem flags", 384, 1);
-  run<1, 5, 192, 2>("shfl+step halo, smem flags", 192, 2);
-  run<1, 5, 256, 1>("shfl+step halo, smem flags", 256, 1);
-  run<1, 5, 320, 1>("shfl+step halo, smem flags", 320, 1);
+  // warps per SMSP: how well do 1 / 2 / 3 warps fill the FP64 pipe?
+  run<1, 1, 128, 1>("shuffles, 1 warp/SMSP", 128, 1);
+  run<1, 1, 256, 1>("shuffles, 2 warps/SMSP", 256, 1);
+  run<1, 1, 384, 1>("shuffles, 3 warps/SMSP", 384, 1);
+  run<1, 0, 128, 1>("regs only, 1 warp/SMSP", 128, 1);
+  run<1, 0, 256, 1>("regs only, 2 warps/SMSP", 256, 1);
+  run<1, 2, 128, 1>("step halo sync, 1 warp/SMSP", 128, 1);
+  run<1, 2, 256, 1>("step halo sync, 2 warps/SMSP", 256, 1);
+  run<1, 6, 256, 1, 2>("step halo 2 chains x 4, 2 warps/SMSP", 256, 1);
+  // more, smaller warps: P = 12 with 16 warps per SM
+  run<1, 1, 512, 1, 1, 12>("shuffles P=12 4 warps/SMSP", 512, 1);
+  run<1, 2, 512, 1, 1, 12>("step halo sync P=12 1 chain x 16", 512, 1);
+  run<1, 6, 512, 1, 2, 12>("step halo P=12 2 chains x 8", 512, 1);
+  run<1, 6, 512, 1, 4, 12>("step halo P=12 4 chains x 4", 512, 1);
+  run<1, 6, 512, 1, 8, 12>("step halo P=12 8 chains x 2", 512, 1);
+  run<1, 2, 128, 4, 1, 12>("step halo sync P=12 128x4", 128, 4);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
