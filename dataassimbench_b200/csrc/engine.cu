@@ -41,25 +41,26 @@ struct DevBuf {
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
-// scratch of the warp-dataflow forecast kernel (l96_forecast_v2.cu): two ping-pong chunk buffers, one flag
-// per job, the job dispenser.  Flags and dispenser are monotonic (epoch / running base), never reset.
+// scratch of the persistent forecast kernel (l96_forecast_v3.cu): two ping-pong chunk buffers (only touched
+// when a window is cut into chunks), one flag per job (monotonic epoch, never reset), the job dispenser
+// (two counters; the kernel leaves them at zero).
 struct V2Work {
   DevBuf scr[2], flags, counter;
   unsigned epoch = 0;
   unsigned long long ctr_base = 0;
-  cudaError_t reserve(long long n, int k, int n_steps) {
-    const size_t bytes = sizeof(double) * (size_t)k * (size_t)l96_v2_scratch_ld(n, n_steps);
+  cudaError_t reserve(long long n, int k, int n_steps, bool chunked) {
+    const size_t bytes = chunked ? sizeof(double) * (size_t)k * (size_t)l96_v3_scratch_ld(n, n_steps) : 16;
     cudaError_t e = cudaSuccess;
     for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = scr[w].reserve(bytes);
-    const size_t fb = sizeof(unsigned) * l96_v2_flag_count(n, k, n_steps);
+    const size_t fb = sizeof(unsigned) * l96_v3_flag_count(n, k, n_steps);
     if (e == cudaSuccess && fb > flags.bytes) {
       e = flags.reserve(fb);
       if (e == cudaSuccess) e = cudaMemset(flags.p, 0, flags.bytes);
       epoch = 0;
     }
     if (e == cudaSuccess && counter.p == nullptr) {
-      e = counter.reserve(sizeof(unsigned long long));
-      if (e == cudaSuccess) e = cudaMemset(counter.p, 0, sizeof(unsigned long long));
+      e = counter.reserve(2 * sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMemset(counter.p, 0, 2 * sizeof(unsigned long long));
       ctr_base = 0;
     }
     return e;
@@ -120,7 +121,7 @@ struct dab_handle {
   DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
-  V2Work v2;                                             // warp-dataflow forecast kernel
+  V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
   int eig_method = kEigAuto;
   unsigned long long xchg_timeout_ns = 10000000000ull;   // statistics exchange: give up on a lost peer (DAB_XCHG_TIMEOUT_S, 0 = never)
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
@@ -205,8 +206,8 @@ static void cycler_free(dab_handle* h) {
   c.ready = false;
 }
 
-// one launch of the warp-dataflow forecast kernel (workspace reserved by the caller)
-static cudaError_t forecast_v2(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
+// one launch of the persistent forecast kernel (workspace reserved by the caller)
+static cudaError_t forecast_v3(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
                                int chunk_steps, double dt, double F, long long in_ld, long long out_ld,
                                bool periodic, long long in_base, long long in_lo, long long in_hi) {
   V2Work& w = h->v2;
@@ -215,8 +216,8 @@ static cudaError_t forecast_v2(dab_handle* h, const double* in, double* out, lon
     if (e != cudaSuccess) return e;
     w.epoch = 1;
   }
-  return l96_v2_launch(in, out, w.scr[0].as<double>(), w.scr[1].as<double>(),
-                       periodic ? n : l96_v2_scratch_ld(n, steps), w.flags.as<unsigned>(), w.epoch,
+  return l96_v3_launch(in, out, w.scr[0].as<double>(), w.scr[1].as<double>(),
+                       periodic ? n : l96_v3_scratch_ld(n, steps), w.flags.as<unsigned>(), w.epoch,
                        w.counter.as<unsigned long long>(), &w.ctr_base, n, k, steps, chunk_steps, dt, F, in_ld,
                        out_ld, periodic, in_base, in_lo, in_hi, h->sms, h->stream);
 }
@@ -230,15 +231,16 @@ static cudaError_t forecast_v2(dab_handle* h, const double* in, double* out, lon
 static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, double* dst, double* traj,
                                 long long traj_stride, int steps, int T, int chunks, int* n_launches) {
   const int k = c.cfg.ensemble_dim;
-  if (T >= kL96V2Code && l96_v2_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
-    cudaError_t e = h->v2.reserve(c.n_loc, k, c.first_steps);
+  if (T >= kL96V3Code && l96_v3_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
+    const int chunk_steps = T - kL96V3Code;
+    cudaError_t e = h->v2.reserve(c.n_loc, k, c.first_steps, chunk_steps < steps);
     if (e != cudaSuccess) return e;
-    e = forecast_v2(h, in_ext, dst, c.n_loc, k, steps, T - kL96V2Code, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc,
+    e = forecast_v3(h, in_ext, dst, c.n_loc, k, steps, chunk_steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc,
                     false, c.halo_l, -8ll * steps, c.n_loc + 4ll * steps);
     if (e == cudaSuccess && n_launches) ++*n_launches;
     return e;
   }
-  if (T >= kL96V2Code) T = 0;                 // not eligible (odd sizes, trajectory wanted): first design, heuristic shape
+  if (T >= kL96V3Code) T = 0;                 // not eligible (odd sizes, trajectory wanted): first design, heuristic shape
   if (traj != nullptr || chunks <= 1 || steps < 2 * chunks) chunks = 1;
   const double* src = in_ext;
   int done = 0;
@@ -717,8 +719,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     cudaEvent_t e0, e1;
     DAB_CUDA(h, cudaEventCreate(&e0));
     DAB_CUDA(h, cudaEventCreate(&e1));
-    const int n_cand = 20;
-    const int cand[n_cand] = {kL96V2Code + 5, kL96V2Code + 4, kL96V2Code + 3, 128, 192, 256, 320, 384, 512,
+    const int n_cand = 19;
+    const int cand[n_cand] = {kL96V3Code + 32, kL96V3Code + 10, 128, 192, 256, 320, 384, 512,
                               l96_shape_code(16, 128), l96_shape_code(16, 160), l96_shape_code(16, 192),
                               l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
                               l96_shape_code(17, 160), l96_shape_code(17, 192),
@@ -734,8 +736,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
       if (chunks > 1 && c.first_steps < 2 * chunks) continue;
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
-        if (cand[ci] >= kL96V2Code) {
-          if (chunks > 1 || !l96_v2_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
+        if (cand[ci] >= kL96V3Code) {
+          if (chunks > 1 || !l96_v3_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
         } else {
           if (l96_shape_width(cand[ci]) < 12 * longest + 16) continue;
           if (chunks > 1 && cand[ci] >= 1000) continue;
@@ -761,10 +763,10 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     h->tune_T.push_back(c.l96_T);
     h->tune_chunks.push_back(c.l96_chunks);
   }
-  if (const char* ev = getenv("DAB_L96_V2")) {              // force (1..6 = steps per chunk) or forbid (0) the warp-dataflow kernel
+  if (const char* ev = getenv("DAB_L96_V3")) {              // force (1..32 = steps per chunk) or forbid (0) the persistent kernel
     const int v = atoi(ev);
-    if (v >= 1 && v <= 6) c.l96_T = kL96V2Code + v;
-    else if (v == 0 && c.l96_T >= kL96V2Code) c.l96_T = 0;
+    if (v >= 1 && v <= 32) c.l96_T = kL96V3Code + v;
+    else if (v == 0 && c.l96_T >= kL96V3Code) c.l96_T = 0;
   }
   if (const char* ev = getenv("DAB_L96_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) c.l96_chunks = v; }
   h->launches = 0;
@@ -924,7 +926,7 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
     DAB_CUDA(h, l96_forecast_launch(c.ext[eb].as<double>(), first_dst, out_traj, c.n_loc, k, c.first_steps,
                                     c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false, c.halo_l,
                                     -(long long)c.halo_l, c.n_loc + c.halo_r, traj_stride, h->sms,
-                                    c.l96_T >= kL96V2Code ? 0 : c.l96_T, h->stream));
+                                    c.l96_T >= kL96V3Code ? 0 : c.l96_T, h->stream));
     h->launches++;
     const double* src = first_dst;
     int done = c.first_steps;

@@ -20,13 +20,13 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 long long traj_stride, int sms, int forced_T /* 0 = heuristic */,
                                 cudaStream_t st);
 
-// K1, warp-dataflow design  l96_forecast_v2.cu (shape code 20000 + steps per chunk)
-constexpr int kL96V2Code = 20000;
-bool l96_v2_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
+// K1, persistent CTA-tile design  l96_forecast_v3.cu (shape code 30000 + steps per chunk)
+constexpr int kL96V3Code = 30000;
+bool l96_v3_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
                      long long in_base, int n_steps, bool traj);
-long long l96_v2_scratch_ld(long long n, int n_steps);
-size_t l96_v2_flag_count(long long n, int k, int n_steps);
-cudaError_t l96_v2_launch(const double* in, double* out, double* scratch0, double* scratch1, long long scr_ld,
+long long l96_v3_scratch_ld(long long n, int n_steps);
+size_t l96_v3_flag_count(long long n, int k, int n_steps);
+cudaError_t l96_v3_launch(const double* in, double* out, double* scratch0, double* scratch1, long long scr_ld,
                           unsigned* flags, unsigned epoch, unsigned long long* counter, unsigned long long* ctr_base,
                           long long n, int k, int n_steps, int chunk_steps,
                           double dt, double F, long long in_ld, long long out_ld, bool periodic,

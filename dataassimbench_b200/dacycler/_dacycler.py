@@ -11,6 +11,87 @@ from .. import _xr
 from . import _windows
 
 
+class IndexOperator:
+    """The default observation operator without its dense form.
+
+    `DACycler._calc_default_H` (dabench/dacycler/_dacycler.py:58-66) builds a dense one-hot matrix
+    `H[r, loc[r]] = 1` (10 GB at N=65536 with 30 % observed); the kernels take the index list itself
+    (`dab_obs_gather_f64`: `(H @ Xb)[r] = Xb[loc[r]]`), so that is what this object carries, together
+    with the row mask the reference applies by zeroing rows of H (dabench/dacycler/_etkf.py:202-203).
+    `dense()` materialises the reference's matrix for small cases and tests."""
+
+    def __init__(self, indices, system_dim, mask=None):
+        self.indices = np.ascontiguousarray(np.ravel(indices), dtype=np.int64)
+        self.system_dim = int(system_dim)
+        self.mask = None if mask is None else np.ascontiguousarray(np.ravel(mask)).astype(bool)
+        if self.mask is not None and self.mask.shape != self.indices.shape:
+            raise ValueError('mask and indices differ in length')
+
+    @property
+    def shape(self):
+        return (self.indices.shape[0], self.system_dim)
+
+    def masked(self, mask):
+        m = np.ravel(np.asarray(mask)).astype(bool)
+        return IndexOperator(self.indices, self.system_dim, m if self.mask is None else (self.mask & m))
+
+    def dense(self):
+        H = np.zeros(self.shape)
+        rows = np.arange(self.indices.shape[0])
+        keep = np.ones_like(rows, dtype=bool) if self.mask is None else self.mask
+        H[rows[keep], self.indices[keep]] = 1.0
+        return H
+
+    @staticmethod
+    def from_dense(H):
+        """A dense matrix whose rows are one-hot (or zero: masked) as an IndexOperator; anything else is
+        outside the accelerated contract."""
+        H = np.asarray(H)
+        if H.ndim != 2:
+            raise NotImplementedError('H must be an IndexOperator, an index array or a dense one-hot matrix')
+        nz = H != 0
+        cnt = nz.sum(axis=1)
+        if (cnt > 1).any() or not np.all(H[nz] == 1.0):
+            raise NotImplementedError('only one-hot (index-gather) observation operators are accelerated; '
+                                      'this dense H mixes grid points')
+        return IndexOperator(np.where(cnt == 1, nz.argmax(axis=1), 0), H.shape[1], cnt == 1)
+
+
+class ScaledIdentity:
+    """`sd**2 * I` without the dense matrix (`DACycler._calc_default_R`, dabench/dacycler/_dacycler.py:68-72;
+    3 GB at 19 661 observations).  `len()` is what the reference's empty-R test looks at
+    (dabench/dacycler/_etkf.py:141)."""
+
+    def __init__(self, n, sd):
+        self.n = int(n)
+        self.sd = float(sd)
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def dense(self):
+        return np.identity(self.n) * self.sd ** 2
+
+    @staticmethod
+    def sd_of(R):
+        """The scalar sd of an R that is sd**2 * I (ScaledIdentity, scalar variance-free dense matrix); raises
+        NotImplementedError for anything else."""
+        if isinstance(R, ScaledIdentity):
+            return R.sd
+        R = np.asarray(R, dtype=np.float64)
+        if R.ndim == 2 and R.shape[0] == R.shape[1]:
+            d = np.diag(R)
+            if R.shape[0] == 0:
+                return 1.0
+            if np.count_nonzero(R - np.diag(d)) == 0 and np.all(d == d[0]) and d[0] >= 0:
+                return float(np.sqrt(d[0]))
+        raise NotImplementedError('only R = sd**2 * I is accelerated')
+
+
 class DACycler:
     _in_4d = False
     _uses_ensemble = False
@@ -43,6 +124,16 @@ class DACycler:
                                             start_inclusive=True, end_inclusive=self._in_4d)
         return dict(centres=centres, padded=padded, obs_times=obs_times,
                     stationary=bool(_xr.get_attr(obs_vector, 'stationary_observers', True)))
+
+    # ---- default operators (dabench/dacycler/_dacycler.py:58-76), in their compact forms
+    def _calc_default_H(self, obs_values, obs_loc_indices):
+        return IndexOperator(obs_loc_indices, self.system_dim)
+
+    def _calc_default_R(self, obs_values, obs_error_sd):
+        return ScaledIdentity(np.size(obs_values), obs_error_sd)
+
+    def _calc_default_B(self):
+        return ScaledIdentity(self.system_dim, 1.0)
 
     def _lorenz96_generator(self):
         """The Lorenz-96 generator behind `model_obj`, or None.  The forecast plugin is recognised by

@@ -9,7 +9,7 @@ raises `NotImplementedError` -- there is deliberately no CPU fallback.
 import numpy as np
 
 from .. import _xr, _native
-from ._dacycler import DACycler
+from ._dacycler import DACycler, IndexOperator, ScaledIdentity
 
 
 class ETKF(DACycler):
@@ -23,6 +23,109 @@ class ETKF(DACycler):
         self.multiplicative_inflation = multiplicative_inflation
         super().__init__(system_dim=system_dim, delta_t=delta_t, model_obj=model_obj,
                          B=B, R=R, H=H, h=h)
+
+    # ------------------------------------------------------------------ the reference's overridable hooks
+    # Same names, argument meaning and array orientation as dabench/dacycler/_etkf.py:64-213 (Xb is
+    # (system_dim, ensemble_dim) there).  Each is one call into the C ABI; `cycle()` itself does not go
+    # through them (it runs the device-resident loop), exactly as the reference's `cycle()` runs a traced
+    # scan: they exist for user code that calls or composes the pieces.
+    def _step_forecast(self, Xa, n_steps=1):
+        """`model_obj.forecast` for every member (dabench/dacycler/_etkf.py:64-80): (last states
+        `x[ensemble, index]`, trajectories `x[ensemble, time, index]` of `n_steps` points, the first being
+        Xa itself) -- one `dab_l96_forecast_f64` launch for the whole ensemble."""
+        import torch
+        from .._runtime import handle
+        gen = self._lorenz96_generator()
+        if gen is None:
+            raise NotImplementedError('_step_forecast needs model_obj to wrap a data.Lorenz96 generator')
+        X = np.ascontiguousarray(_xr.var_array(Xa, 'x'), dtype=np.float64)
+        k, N = X.shape
+        dim = [d for d in _xr.var_dims(Xa, 'x') if d != 'ensemble'][0]
+        steps = int(n_steps) - 1
+        xin = torch.from_numpy(X).cuda()
+        xout = torch.empty_like(xin)
+        traj = torch.empty((max(steps, 1), k, N), dtype=torch.float64, device='cuda')
+        if steps > 0:
+            handle().l96_forecast(xin, xout, traj, N, k, steps, float(gen.delta_t), float(gen.forcing_term),
+                                  torch.cuda.current_stream().cuda_stream)
+            full = np.concatenate([X[None], traj.cpu().numpy()], axis=0)
+        else:
+            full = X[None]
+        times = np.arange(full.shape[0]) * float(gen.delta_t)
+        last = _xr.new_dataset({'x': (('ensemble', dim), full[-1].copy())})
+        trajs = _xr.new_dataset({'x': (('ensemble', 'time', dim), np.ascontiguousarray(full.transpose(1, 0, 2)))},
+                                coords={'time': times})
+        return last, trajs
+
+    @staticmethod
+    def _index_operator(H, h, system_dim):
+        if h is not None and H is None:
+            raise ValueError('Only linear obs operators (H) are supported right now.')
+        if isinstance(H, IndexOperator):
+            return H
+        H = np.asarray(H)
+        if H.ndim == 1 and np.issubdtype(H.dtype, np.integer):
+            return IndexOperator(H, system_dim)
+        return IndexOperator.from_dense(H)
+
+    def _apply_obsop(self, Xb, H, h):
+        """`Yb = H @ Xb` (dabench/dacycler/_etkf.py:82-92) for an index-gather H: the gather kernel,
+        bit-exact.  Xb is (system_dim, ensemble_dim); returns (n_obs, ensemble_dim)."""
+        from ..obsop import ObsOp
+        Xb = np.asarray(Xb, dtype=np.float64)
+        op = self._index_operator(H, h, Xb.shape[0])
+        return ObsOp.gather(np.ascontiguousarray(Xb.T), op.indices, op.mask).T
+
+    def _compute_analysis(self, Xb, Y, H, h, R, rho=1.0):
+        """The ETKF analysis (dabench/dacycler/_etkf.py:94-163) for an index-gather H and R = sd**2 I:
+        `dab_etkf_analysis_f64` (gather + DMMA contraction, k x k transform matrix, DMMA transform).
+        Xb and the result are (system_dim, ensemble_dim)."""
+        import torch
+        from .._runtime import handle
+        Xb = np.asarray(Xb, dtype=np.float64)
+        N, k = Xb.shape
+        y = np.ascontiguousarray(np.ravel(Y), dtype=np.float64)
+        empty_R = len(R) == 0                                   # the reference's zero branch (:149-152)
+        n_y = 0 if empty_R else y.shape[0]
+        Xd = torch.from_numpy(np.ascontiguousarray(Xb.T)).cuda()
+        Xa = torch.empty_like(Xd)
+        yd = idxd = md = None
+        sd = 1.0
+        if n_y > 0:
+            op = self._index_operator(H, h, N)
+            if op.indices.shape[0] != n_y:
+                raise ValueError('H has %d rows for %d observations' % (op.indices.shape[0], n_y))
+            sd = ScaledIdentity.sd_of(R)
+            yd = torch.from_numpy(y).cuda()
+            idxd = torch.from_numpy(op.indices).cuda()
+            md = None if op.mask is None else torch.from_numpy(op.mask.astype(np.uint8)).cuda()
+        handle().etkf_analysis(Xd, Xa, yd, idxd, md, sd, float(rho), N, k, n_y,
+                               torch.cuda.current_stream().cuda_stream)
+        return np.ascontiguousarray(Xa.cpu().numpy().T)
+
+    def _cycle_obsop(self, Xb_ds, obs_values, obs_loc_indices, obs_time_mask, obs_loc_mask,
+                     H=None, h=None, R=None, B=None):
+        """One analysis on a Dataset (dabench/dacycler/_etkf.py:165-213): default operators resolved as
+        the reference does, masks applied to H, `_compute_analysis`, result written back as
+        `x[ensemble, i]`."""
+        if H is None and h is None:
+            if self.H is None:
+                if self.h is None:
+                    H = self._calc_default_H(obs_values, obs_loc_indices)
+                else:
+                    h = self.h
+            else:
+                H = self.H
+        if R is None:
+            R = self._calc_default_R(obs_values, self.obs_error_sd) if self.R is None else self.R
+        Xb = np.asarray(_xr.var_array(Xb_ds, 'x'), dtype=np.float64).T
+        n_sys, n_ens = Xb.shape
+        assert n_ens == self.ensemble_dim, (
+            'cycle:: model_forecast must have dimension {}x{}').format(self.ensemble_dim, self.system_dim)
+        op = self._index_operator(H, h, n_sys)
+        op = op.masked(np.ravel(obs_time_mask)).masked(np.ravel(obs_loc_mask))
+        Xa = self._compute_analysis(Xb=Xb, Y=obs_values, H=op, h=None, R=R, rho=self.multiplicative_inflation)
+        return _xr.new_dataset({'x': (('ensemble', 'i'), np.ascontiguousarray(Xa.T))})
 
     # ------------------------------------------------------------------ marshalling (CPU-testable)
     def _plan(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
@@ -85,7 +188,7 @@ class ETKF(DACycler):
         dim = p['state_dim']
         if not return_forecast:
             H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out)
-            return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy().copy())})
+            return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy())})
         # The trajectories are S*k*N*8 bytes per cycle (671 MB at N=65536, k=64): they are produced in
         # blocks of cycles that fit `traj_block_bytes` of device memory and streamed to the host block
         # by block, instead of materialising n_cycles of them in HBM (the reference builds the whole

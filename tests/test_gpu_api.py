@@ -281,3 +281,118 @@ def test_cycle_batched_inflation_sweep_matches_single_cycles():
         assert rel_err(out['x'].values[b], single['x'].values) < 1e-10
     m = dab.dacycler.cycle_batched(cyclers, init, 0.0, obs, n_cycles, analysis_window=0.2, return_mean_only=True)
     assert rel_err(m['x_mean'].values, out['x'].values.mean(axis=2)) < 1e-12
+
+
+# ------------------------------------------------------------------ the reference's overridable hooks
+def _hook_case(N=120, k=12, n_obs=40, seed=3):
+    rng = np.random.default_rng(seed)
+    Xb = 8.0 + rng.standard_normal((N, k))                      # reference orientation: (system_dim, ensemble_dim)
+    idx = rng.choice(N, n_obs, replace=False, shuffle=False)
+    y = Xb.mean(axis=1)[idx] + 0.7 * rng.standard_normal(n_obs)
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.01))
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k, model_obj=model,
+                           multiplicative_inflation=1.1)
+    return dc, Xb, idx, y
+
+
+def test_hook_apply_obsop_is_the_reference_H_at_Xb_bit_for_bit():
+    """ETKF._apply_obsop (dabench/dacycler/_etkf.py:82-92) with the default H, against the dense
+    one-hot product the reference forms (oracle: default_H @ Xb is a pure selection, so bit-exact)."""
+    dc, Xb, idx, y = _hook_case()
+    H = dc._calc_default_H(y, idx)
+    Yb = dc._apply_obsop(Xb, H, None)
+    assert Yb.shape == (len(idx), Xb.shape[1])
+    assert np.array_equal(Yb, o_etkf.calc_default_H(len(idx), Xb.shape[0], idx) @ Xb)
+    assert np.array_equal(Yb, Xb[idx])
+    # the dense matrix the reference would pass works too (it is recognised as an index gather) ...
+    assert np.array_equal(dc._apply_obsop(Xb, H.dense(), None), Yb)
+    # ... masked rows are zero rows of H
+    m = np.arange(len(idx)) % 3 != 0
+    assert np.array_equal(dc._apply_obsop(Xb, H.masked(m), None), np.where(m[:, None], Xb[idx], 0.0))
+    with pytest.raises(NotImplementedError):
+        dc._apply_obsop(Xb, np.ones((3, Xb.shape[0])), None)
+    with pytest.raises(ValueError):
+        dc._apply_obsop(Xb, None, lambda x: x)
+
+
+def test_hook_compute_analysis_matches_the_literal_formula():
+    """ETKF._compute_analysis(Xb, Y, H, h, R, rho) (dabench/dacycler/_etkf.py:94-163), same signature and
+    orientation, against the oracle's literal restatement (dense H, dense R, pinv, sqrtm): <= 1e-10."""
+    dc, Xb, idx, y = _hook_case()
+    N, k = Xb.shape
+    H = dc._calc_default_H(y, idx)
+    R = dc._calc_default_R(y, 0.7)
+    Xa = dc._compute_analysis(Xb, y, H, None, R, rho=1.1)
+    ref = o_etkf.analysis_literal(Xb, y, o_etkf.calc_default_H(len(idx), N, idx), o_etkf.calc_default_R(len(idx), 0.7), 1.1)
+    assert Xa.shape == (N, k) and rel_err(Xa, ref) < 1e-10
+    # dense operands as the reference builds them
+    Xa2 = dc._compute_analysis(Xb, y.reshape(1, -1), H.dense(), None, R.dense(), rho=1.1)
+    assert np.array_equal(Xa2, Xa)
+    # empty R: the reference's zero branch (:149-152) collapses the ensemble onto its mean
+    Xe = dc._compute_analysis(Xb, np.zeros(0), None, None, np.zeros((0, 0)), rho=1.1)
+    ref_e = o_etkf.analysis_literal(Xb, np.zeros(0), np.zeros((0, N)), np.zeros((0, 0)), 1.1)
+    assert rel_err(Xe, ref_e) < 1e-12
+    with pytest.raises(NotImplementedError):
+        dc._compute_analysis(Xb, y, H, None, np.diag(np.linspace(1, 2, len(idx))), 1.0)
+
+
+def test_hook_cycle_obsop_applies_masks_and_defaults():
+    """ETKF._cycle_obsop (dabench/dacycler/_etkf.py:165-213): defaults resolved, time and location masks
+    zero rows of H, Dataset in, Dataset `x[ensemble, i]` out."""
+    dc, Xb, idx, y = _hook_case()
+    N, k = Xb.shape
+    dc.obs_error_sd = 0.7
+    tmask = np.arange(len(idx)) % 4 != 1
+    lmask = np.arange(len(idx)) % 5 != 2
+    ds = _xr.new_dataset({'x': (('ensemble', 'index'), np.ascontiguousarray(Xb.T))})
+    out = dc._cycle_obsop(ds, y.reshape(1, 1, -1), idx, tmask, lmask)
+    assert tuple(out['x'].dims) == ('ensemble', 'i')
+    Hd = o_etkf.calc_default_H(len(idx), N, idx)
+    Hd = np.where(tmask, Hd.T, 0).T
+    Hd = np.where(lmask, Hd.T, 0).T
+    ref = o_etkf.analysis_literal(Xb, y, Hd, o_etkf.calc_default_R(len(idx), 0.7), 1.1)
+    assert rel_err(out['x'].values.T, ref) < 1e-10
+    bad = _xr.new_dataset({'x': (('ensemble', 'index'), np.ascontiguousarray(Xb.T[:-1]))})
+    with pytest.raises(AssertionError):
+        dc._cycle_obsop(bad, y, idx, tmask, lmask)
+
+
+def test_hook_step_forecast_is_the_member_loop_of_the_reference():
+    """ETKF._step_forecast(Xa, n_steps) (dabench/dacycler/_etkf.py:64-80): (last, trajectories) with the
+    reference's dims; trajectory point 0 is Xa itself, `n_steps` points, against oracle RK4."""
+    dc, Xb, idx, y = _hook_case()
+    Xa = np.ascontiguousarray(Xb.T)
+    ds = _xr.new_dataset({'x': (('ensemble', 'index'), Xa)})
+    last, traj = dc._step_forecast(ds, n_steps=6)
+    assert last['x'].shape == Xa.shape and traj['x'].shape == (Xa.shape[0], 6, Xa.shape[1])
+    assert tuple(traj['x'].dims) == ('ensemble', 'time', 'index')
+    assert np.array_equal(traj['x'].values[:, 0], Xa)
+    assert np.array_equal(traj['x'].values[:, -1], last['x'].values)
+    ref = np.stack([o_l96.generate_rk4(Xa[j], 6, 0.01) for j in range(Xa.shape[0])])
+    assert rel_err(traj['x'].values, ref) < 1e-12
+    # n_steps = 1: nothing to integrate
+    last1, traj1 = dc._step_forecast(ds, n_steps=1)
+    assert np.array_equal(last1['x'].values, Xa) and traj1['x'].shape == (Xa.shape[0], 1, Xa.shape[1])
+
+
+def test_cycle_with_zero_error_sd_ignores_the_observations_like_pinv_of_zero_R():
+    """Observer's default error_sd is 0.0 and cycle() falls back to it: R = 0, pinv(R) = 0
+    (dabench/dacycler/_etkf.py:142), so the analysis is the inflated background -- finite, not NaN."""
+    N, k, S = 64, 6, 4
+    gen = dab.data.Lorenz96(system_dim=N, delta_t=0.01)
+    nature = gen.generate(n_steps=40)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(0, 40, 4)], random_location_count=20,
+                                random_seed=5, stationary_observers=True).observe()      # error_sd = 0.0
+    assert obs.attrs['error_sd'] == 0.0
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k,
+                           model_obj=dab.model.Lorenz96Model(model_obj=gen), multiplicative_inflation=1.21)
+    rng = np.random.default_rng(2)
+    X0 = nature['x'].values[0] + rng.standard_normal((k, N))
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), X0)})
+    out = dc.cycle(init, 0.0, obs, n_cycles=3, analysis_window=S * 0.01)
+    assert np.isfinite(out['x'].values).all()
+    # literal oracle with R = 0
+    Xb = X0.T
+    ref = o_etkf.analysis_literal(Xb, obs['x'].values[0], o_etkf.calc_default_H(20, N, obs["system_index"].values[0, 0]),
+                                  np.zeros((20, 20)), 1.21)
+    assert rel_err(out['x'].values[0].T, ref) < 1e-10

@@ -309,3 +309,31 @@ def test_var3d_rejects_what_it_does_not_accelerate():
         dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, h=lambda x: x).cycle(init, 0.0, obs, 2)
     with pytest.raises(NotImplementedError):
         dab.dacycler.Var3D(system_dim=3, delta_t=0.01, model_obj=dab.model.Lorenz63Model()).cycle(init, 0.0, obs, 2)
+
+
+def test_compact_default_operators_match_the_reference_dense_ones():
+    """DACycler._calc_default_H / _calc_default_R (dabench/dacycler/_dacycler.py:58-72) in their compact
+    forms (index list, scaled identity): `dense()` is exactly the matrix the reference builds, masking is
+    zeroing rows (dabench/dacycler/_etkf.py:202-203), and a dense one-hot matrix is recognised back."""
+    from dataassimbench_b200.dacycler._dacycler import IndexOperator, ScaledIdentity, DACycler
+    from oracle import etkf as o_etkf
+    dc = DACycler(system_dim=9, delta_t=0.01, model_obj=None)
+    idx = np.array([4, 0, 7, 7])
+    H = dc._calc_default_H(np.zeros(4), idx)
+    assert isinstance(H, IndexOperator) and H.shape == (4, 9)
+    assert np.array_equal(H.dense(), o_etkf.calc_default_H(4, 9, idx))
+    m = np.array([True, False, True, True])
+    Hm = H.masked(m)
+    assert np.array_equal(Hm.dense(), np.where(m, H.dense().T, 0).T)
+    back = IndexOperator.from_dense(Hm.dense())
+    assert np.array_equal(back.dense(), Hm.dense())
+    with pytest.raises(NotImplementedError):
+        IndexOperator.from_dense(np.full((2, 9), 0.5))
+    R = dc._calc_default_R(np.zeros((1, 2, 2)), 1.5)
+    assert isinstance(R, ScaledIdentity) and len(R) == 4
+    assert np.array_equal(R.dense(), o_etkf.calc_default_R(4, 1.5))
+    assert ScaledIdentity.sd_of(R) == 1.5 and ScaledIdentity.sd_of(R.dense()) == 1.5
+    assert ScaledIdentity.sd_of(np.zeros((3, 3))) == 0.0
+    with pytest.raises(NotImplementedError):
+        ScaledIdentity.sd_of(np.diag([1.0, 2.0]))
+    assert len(dc._calc_default_R(np.zeros(0), 1.0)) == 0          # the empty-R branch tests len(R)

@@ -1,4 +1,7 @@
-// K1, second design -- Lorenz-96 RK4 ensemble forecast as a persistent dataflow of WARP-private windows.
+// EXPERIMENT (not part of the product build; tools/l96_v2_test.cu runs it): K1 as a persistent dataflow of
+// WARP-private windows.  Correct (2e-15 against CPU RK4) but slower than the CTA-tile kernels: 21.3 TFLOP/s at
+// C4 against 22.6 for csrc/l96_forecast_v3.cu -- a warp spends ~40 % of its time on per-job bookkeeping (claim,
+// flags, gpu-scope fence, staging) that three warps per scheduler do not hide.  profiles/forecast_probes_r02.md.
 //
 // Replaces the same reference functions as l96_forecast.cu (ETKF._step_forecast
 // dabench/dacycler/_etkf.py:64-80 -> Model.forecast -> Data.generate dabench/data/_data.py:86-211 ->
@@ -33,72 +36,15 @@
 // 16-byte aligned rows, no trajectory output.
 #include <cstdlib>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "../../dataassimbench_b200/csrc/common.cuh"
+#include "../../dataassimbench_b200/csrc/kernels.h"
+#include "../../dataassimbench_b200/csrc/l96_dataflow.cuh"
 
 namespace dab {
 
 constexpr int V2_P = 16;              // points per thread
 constexpr int V2_W = 32 * V2_P;       // points per window
 constexpr int V2_STAGE = V2_W + 2 * (V2_W / 16);   // padded staging doubles per buffer (conflict-free LDS.128)
-constexpr int V2_MAX_CHUNKS = 8;
-
-struct V2Chunk {
-  int steps;        // RK4 steps of this chunk
-  int org, end;     // output region [org, end) in slab coordinates
-  int U, J;         // useful points per job, jobs per member
-  int job_base;     // number of the chunk's first job
-  int pad0, pad1;
-  double inv_J, inv_U;
-};
-
-struct L96V2Args {
-  const double* in;
-  double* out;
-  double* scratch[2];
-  long long in_ld, out_ld, scr_ld;    // member strides (doubles)
-  long long in_base, scr_base;        // column of slab coordinate 0 in an input / scratch row
-  int in_lo, in_hi;                   // EXT: valid slab-coordinate range of an input row
-  int n;                              // PERIODIC: ring size; EXT: slab length
-  int periodic, k, n_chunks, total;
-  V2Chunk ch[V2_MAX_CHUNKS];
-  unsigned* flags;                    // one per job; == epoch when the job's output is visible
-  unsigned epoch;
-  unsigned long long* counter;        // job dispenser: monotonic over launches, this launch starts at ctr_base
-  unsigned long long ctr_base;
-  double h2, h3, h6, dt, h2F, dtF;    // RK4 coefficients as uniform operands (see l96_forecast.cu)
-};
-
-__device__ __forceinline__ unsigned v2_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-struct V2Job { int n, c, m, p, q, g0; };   // number, chunk, member, useful range [p, q), window start
-
-// floor(x / d) for 0 <= x < 2^31 with inv = 1 / d: one FP64 multiply instead of an integer division chain
-__device__ __forceinline__ int v2_div(int x, double inv) { return (int)(((double)x + 0.5) * inv); }
-
-__device__ __forceinline__ V2Job v2_decode(const L96V2Args& a, int n, int c_hint) {
-  V2Job jb;
-  int c = c_hint;                               // jobs arrive in increasing order: the chunk only moves forward
-  while (c + 1 < a.n_chunks && n >= a.ch[c + 1].job_base) ++c;
-  const V2Chunk& ch = a.ch[c];
-  const int r = n - ch.job_base;
-  jb.n = n; jb.c = c;
-  jb.m = v2_div(r, ch.inv_J);
-  const int j = r - jb.m * ch.J;
-  jb.p = ch.org + j * ch.U;
-  jb.q = jb.p + ch.U < ch.end ? jb.p + ch.U : ch.end;
-  jb.g0 = jb.p - 8 * ch.steps;
-  return jb;
-}
-
-__device__ __forceinline__ int v2_wrap(int g, int n) {      // ring coordinate of g (any distance from [0, n))
-  if ((unsigned)g < (unsigned)n) return g;
-  if (g < 0) { g += n; if (g >= 0) return g; }
-  else { g -= n; if (g < n) return g; }
-  g %= n;
-  return g < 0 ? g + n : g;
-}
-
 // The jobs of chunk c-1 a job depends on.  RAW: their output intersects my input window; WAR: their
 // input window intersects the range I overwrite (same buffer, two chunks apart).  Both are covered by
 // the jobs whose output range meets [p - 8 s, q + 8 s), s the larger of the two chunks' steps: <= 3 jobs
@@ -106,35 +52,6 @@ __device__ __forceinline__ int v2_wrap(int g, int n) {      // ring coordinate o
 // loads, served by L2), so the outcome is warp-uniform by construction.  `v2_deps_load` only ISSUES the
 // loads; the values are tested a step of arithmetic later.  The data the flags guard is read through
 // cp.async.cg (L2 as well), issued after the branch on the flag values.
-struct V2Deps { unsigned v0, v1, v2; bool many; };
-
-__device__ __forceinline__ void v2_deps_range(const L96V2Args& a, const V2Job& jb, int& j0, int& cnt) {
-  const V2Chunk& cp = a.ch[jb.c - 1];
-  const int s0 = a.ch[jb.c].steps;
-  const int sm = s0 > cp.steps ? s0 : cp.steps;
-  const int lo = jb.p - 8 * sm - cp.org, hi = jb.q + 8 * sm - 1 - cp.org;
-  if (a.periodic) {                      // ring: job of the wrapped coordinate, then upwards around the ring
-    if (hi - lo + 1 >= a.n) { j0 = 0; cnt = cp.J; }
-    else {
-      j0 = v2_div(v2_wrap(lo, a.n), cp.inv_U);
-      cnt = v2_div(v2_wrap(hi, a.n), cp.inv_U) - j0;
-      if (cnt < 0) cnt += cp.J;
-      cnt += 1;
-    }
-  } else {
-    j0 = lo >= 0 ? v2_div(lo, cp.inv_U) : 0;
-    int j1 = hi >= 0 ? v2_div(hi, cp.inv_U) : -1;
-    if (j1 > cp.J - 1) j1 = cp.J - 1;
-    cnt = j1 - j0 + 1;
-  }
-}
-
-__device__ __forceinline__ unsigned v2_flag(const unsigned* f0, int j0, int i, int cnt, int Jp) {
-  int jj = j0 + (i < cnt ? i : 0);
-  if (jj >= Jp) jj -= Jp;
-  return *reinterpret_cast<const volatile unsigned*>(f0 + jj);
-}
-
 __device__ __forceinline__ V2Deps v2_deps_load(const L96V2Args& a, const V2Job& jb) {
   V2Deps d; d.v0 = d.v1 = d.v2 = a.epoch; d.many = false;
   if (jb.c == 0) return d;
@@ -349,7 +266,7 @@ l96_v2_kernel(const L96V2Args a) {
 }
 
 // ------------------------------------------------------------------------------------------ host side
-bool l96_v2_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
+static bool l96_v2x_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
                      long long in_base, int n_steps, bool traj) {
   if (traj || n_steps < 1 || n_steps > 6 * V2_MAX_CHUNKS) return false;
   if ((n & 1) || (in_ld & 1) || (out_ld & 1) || (in_base & 1)) return false;
@@ -359,9 +276,9 @@ bool l96_v2_eligible(const double* in, const double* out, long long n, long long
 }
 
 // scratch row stride for windows of `n_steps` steps over slabs of n points (extended layout, even)
-long long l96_v2_scratch_ld(long long n, int n_steps) { return (n + 12ll * n_steps + 2) & ~1ll; }
+static long long l96_v2x_scratch_ld(long long n, int n_steps) { return (n + 12ll * n_steps + 2) & ~1ll; }
 
-size_t l96_v2_flag_count(long long n, int k, int n_steps) {
+static size_t l96_v2x_flag_count(long long n, int k, int n_steps) {
   // upper bound: <= n_steps chunks, each over at most n + 12 n_steps points in jobs of >= 440 useful points
   // (fewer only when the whole row is shorter)
   const long long per = (n + 12ll * n_steps) / 256 + 2;
@@ -375,38 +292,12 @@ cudaError_t l96_v2_launch(const double* in, double* out, double* scratch0, doubl
                           long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st) {
   if (chunk_steps < 1) chunk_steps = 5;
   if (chunk_steps > 6) chunk_steps = 6;
-  const int nc = (n_steps + chunk_steps - 1) / chunk_steps;
-  if (nc < 1 || nc > V2_MAX_CHUNKS) return cudaErrorInvalidValue;
   L96V2Args a{};
   a.in = in; a.out = out; a.scratch[0] = scratch0; a.scratch[1] = scratch1;
   a.in_ld = in_ld; a.out_ld = out_ld; a.scr_ld = scr_ld;
   a.in_base = in_base; a.in_lo = (int)in_lo; a.in_hi = (int)in_hi;
-  a.n = (int)n; a.periodic = periodic ? 1 : 0; a.k = k; a.n_chunks = nc;
-  a.scr_base = periodic ? 0 : 8ll * n_steps;
-  int done = 0;
-  long long base = 0;
-  for (int c = 0; c < nc; ++c) {
-    const int sc = (n_steps - done + (nc - c) - 1) / (nc - c);      // near-equal chunks
-    done += sc;
-    const int rem = n_steps - done;
-    V2Chunk& ch = a.ch[c];
-    ch.steps = sc;
-    ch.org = periodic ? 0 : -8 * rem;
-    const long long len = periodic ? n : n + 12ll * rem;
-    ch.end = ch.org + (int)len;
-    const int cap = V2_W - 12 * sc;
-    long long J = (len + cap - 1) / cap;
-    long long U = (len + J - 1) / J;
-    U = (U + 1) & ~1ll;                                             // even: 16-byte pairs never straddle jobs
-    if (U > cap) U = cap & ~1;
-    J = (len + U - 1) / U;
-    ch.U = (int)U; ch.J = (int)J;
-    ch.inv_U = 1.0 / (double)U; ch.inv_J = 1.0 / (double)J;
-    ch.job_base = (int)base;
-    base += J * k;
-    if (base >= (1ll << 30)) return cudaErrorInvalidValue;
-  }
-  a.total = (int)base;
+  if (!l96_dataflow_plan(a, n, k, n_steps, chunk_steps, V2_W, periodic)) return cudaErrorInvalidValue;
+  const long long base = a.total;
   a.flags = flags; a.epoch = epoch;
   a.counter = counter; a.ctr_base = *ctr_base;
   a.dt = dt; a.h2 = 0.5 * dt; a.h3 = dt / 3.0; a.h6 = dt / 6.0; a.h2F = a.h2 * F; a.dtF = dt * F;

@@ -5,7 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../dataassimbench_b200/csrc/l96_forecast_v2.cu"
+#include "experiments/l96_forecast_v2.cu"
+#include "../dataassimbench_b200/csrc/l96_forecast_v3.cu"
 namespace dab { bool pdl_enabled() { return false; } }
 using namespace dab;
 
@@ -33,6 +34,7 @@ struct Bufs { double *in, *out, *s0, *s1; unsigned* flags; unsigned epoch = 0; }
 
 // world ranks emulated one after the other: rank r owns columns [r n_loc, (r+1) n_loc) and gets the
 // extended layout [8S | slab | 4S] cut from the ring
+static int g_ver = 2;
 static double check(long long N, int k, int S, int chunk, bool periodic, int world, int threads, bool verbose) {
   const double dt = 0.01, F = 8.0;
   std::vector<double> X((size_t)k * N);
@@ -46,14 +48,15 @@ static double check(long long N, int k, int S, int chunk, bool periodic, int wor
   }
   const long long n_loc = N / world;
   const long long ld_e = (8 * S + n_loc + 4 * S + 1) & ~1ll;
-  const long long scr_ld = l96_v2_scratch_ld(n_loc, S);
+  const long long scr_ld = l96_v3_scratch_ld(n_loc, S);
   double *d_in, *d_out, *d_s0, *d_s1; unsigned* d_flags;
   const size_t in_elems = periodic ? (size_t)k * N : (size_t)k * ld_e;
   cudaMalloc(&d_in, in_elems * 8); cudaMalloc(&d_out, (size_t)k * n_loc * 8);
   cudaMalloc(&d_s0, (size_t)k * scr_ld * 8); cudaMalloc(&d_s1, (size_t)k * scr_ld * 8);
-  const size_t nf = l96_v2_flag_count(n_loc, k, S);
+  const size_t nf = l96_v3_flag_count(n_loc, k, S);
   cudaMalloc(&d_flags, nf * 4); cudaMemset(d_flags, 0, nf * 4);
   unsigned long long* d_ctr; unsigned long long ctr_base = 0; cudaMalloc(&d_ctr, 8); cudaMemset(d_ctr, 0, 8);
+  unsigned long long* d_ctr3; cudaMalloc(&d_ctr3, 16); cudaMemset(d_ctr3, 0, 16);
   double worst = 0.0, scale = 0.0;
   for (double v : ref) scale = fmax(scale, fabs(v));
   unsigned epoch = 0;
@@ -68,9 +71,13 @@ static double check(long long N, int k, int S, int chunk, bool periodic, int wor
         }
     cudaMemcpy(d_in, hin.data(), in_elems * 8, cudaMemcpyHostToDevice);
     cudaMemset(d_out, 0xff, (size_t)k * n_loc * 8);
-    cudaError_t e = l96_v2_launch(d_in, d_out, d_s0, d_s1, periodic ? n_loc : scr_ld, d_flags, ++epoch, d_ctr, &ctr_base, n_loc, k, S, chunk, dt, F,
-                                  periodic ? N : ld_e, n_loc, periodic, periodic ? 0 : 8 * S, periodic ? 0 : -8ll * S,
-                                  periodic ? 0 : n_loc + 4ll * S, 148, 0);
+    cudaError_t e = g_ver == 2
+        ? l96_v2_launch(d_in, d_out, d_s0, d_s1, periodic ? n_loc : scr_ld, d_flags, ++epoch, d_ctr, &ctr_base, n_loc, k, S, chunk, dt, F,
+                        periodic ? N : ld_e, n_loc, periodic, periodic ? 0 : 8 * S, periodic ? 0 : -8ll * S,
+                        periodic ? 0 : n_loc + 4ll * S, 148, 0)
+        : l96_v3_launch(d_in, d_out, d_s0, d_s1, periodic ? n_loc : scr_ld, d_flags, ++epoch, d_ctr3, &ctr_base, n_loc, k, S, chunk, dt, F,
+                        periodic ? N : ld_e, n_loc, periodic, periodic ? 0 : 8 * S, periodic ? 0 : -8ll * S,
+                        periodic ? 0 : n_loc + 4ll * S, 148, 0);
     if (e != cudaSuccess) { printf("launch: %s\n", cudaGetErrorString(e)); return 1e9; }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("sync: %s\n", cudaGetErrorString(e)); exit(1); }
@@ -83,58 +90,66 @@ static double check(long long N, int k, int S, int chunk, bool periodic, int wor
       }
   }
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_s0); cudaFree(d_s1); cudaFree(d_flags);
-  if (verbose) printf("check N=%lld k=%d S=%d chunk=%d %s world=%d T=%d: max rel err %.3e\n", N, k, S, chunk,
+  if (verbose) printf("v%d check N=%lld k=%d S=%d chunk=%d %s world=%d T=%d: max rel err %.3e\n", g_ver, N, k, S, chunk,
                       periodic ? "periodic" : "extended", world, threads, worst / scale);
   return worst / scale;
 }
 
 static void timeit(long long N, int k, int S, int chunk, int threads) {
   const double dt = 0.01, F = 8.0;
-  const long long ld_e = (8 * S + N + 4 * S + 1) & ~1ll, scr_ld = l96_v2_scratch_ld(N, S);
+  const long long ld_e = (8 * S + N + 4 * S + 1) & ~1ll, scr_ld = l96_v3_scratch_ld(N, S);
   double *d_in, *d_out, *d_s0, *d_s1; unsigned* d_flags;
   cudaMalloc(&d_in, (size_t)k * ld_e * 8); cudaMalloc(&d_out, (size_t)k * N * 8);
   cudaMalloc(&d_s0, (size_t)k * scr_ld * 8); cudaMalloc(&d_s1, (size_t)k * scr_ld * 8);
   std::vector<double> h((size_t)k * ld_e);
   for (size_t i = 0; i < h.size(); ++i) h[i] = 8.0 + 2.0 * sin(0.01 * i);
   cudaMemcpy(d_in, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
-  const size_t nf = l96_v2_flag_count(N, k, S);
+  const size_t nf = l96_v3_flag_count(N, k, S);
   cudaMalloc(&d_flags, nf * 4); cudaMemset(d_flags, 0, nf * 4);
   unsigned long long* d_ctr; unsigned long long ctr_base = 0; cudaMalloc(&d_ctr, 8); cudaMemset(d_ctr, 0, 8);
+  unsigned long long* d_ctr3; cudaMalloc(&d_ctr3, 16); cudaMemset(d_ctr3, 0, 16);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   unsigned epoch = 0;
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
     cudaEventRecord(e0);
-    l96_v2_launch(d_in, d_out, d_s0, d_s1, scr_ld, d_flags, ++epoch, d_ctr, &ctr_base, N, k, S, chunk, dt, F, ld_e, N, false, 8 * S, -8ll * S,
+    if (g_ver == 2) l96_v2_launch(d_in, d_out, d_s0, d_s1, scr_ld, d_flags, ++epoch, d_ctr, &ctr_base, N, k, S, chunk, dt, F, ld_e, N, false, 8 * S, -8ll * S,
+                  N + 4ll * S, 148, 0);
+    else l96_v3_launch(d_in, d_out, d_s0, d_s1, scr_ld, d_flags, ++epoch, d_ctr3, &ctr_base, N, k, S, chunk, dt, F, ld_e, N, false, 8 * S, -8ll * S,
                   N + 4ll * S, 148, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (rep > 0 && ms < best) best = ms;
   }
-  printf("time N=%lld k=%d S=%d chunk=%d T=%d: %.1f us  %.2f TFLOP/s (29-flop convention)  %s\n", N, k, S, chunk, threads,
+  printf("v%d time N=%lld k=%d S=%d chunk=%d T=%d: %.1f us  %.2f TFLOP/s (29-flop convention)  %s\n", g_ver, N, k, S, chunk, threads,
          best * 1e3, 29.0 * N * k * S / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_s0); cudaFree(d_s1); cudaFree(d_flags);
 }
 
 int main(int argc, char** argv) {
-  double w = 0;
-  w = fmax(w, check(1024, 4, 20, 5, true, 1, 384, true));
-  w = fmax(w, check(1024, 16, 20, 5, false, 1, 384, true));
-  w = fmax(w, check(600, 3, 7, 5, true, 1, 128, true));
-  w = fmax(w, check(40, 20, 20, 5, true, 1, 384, true));
-  w = fmax(w, check(36, 10, 20, 4, false, 1, 384, true));
-  w = fmax(w, check(4096, 8, 20, 5, false, 4, 384, true));
-  w = fmax(w, check(4096, 8, 32, 6, false, 2, 256, true));
-  w = fmax(w, check(65536, 8, 20, 5, false, 1, 384, true));
-  w = fmax(w, check(65536, 4, 20, 4, true, 1, 384, true));
-  w = fmax(w, check(2000, 64, 3, 5, false, 1, 384, true));
-  w = fmax(w, check(1 << 20, 2, 20, 5, false, 8, 384, true));
-  printf("worst %.3e %s\n", w, w < 1e-11 ? "OK" : "FAIL");
+  for (g_ver = 3; g_ver >= 2; --g_ver) {
+    const int c1 = g_ver == 3 ? 10 : 5, c2 = g_ver == 3 ? 7 : 4;
+    double w = 0;
+    w = fmax(w, check(1024, 4, 20, c1, true, 1, 384, true));
+    w = fmax(w, check(1024, 16, 20, c1, false, 1, 384, true));
+    w = fmax(w, check(600, 3, 7, c2, true, 1, 128, true));
+    w = fmax(w, check(40, 20, 20, c1, true, 1, 384, true));
+    w = fmax(w, check(36, 10, 20, c2, false, 1, 384, true));
+    w = fmax(w, check(4096, 8, 20, c1, false, 4, 384, true));
+    w = fmax(w, check(4096, 8, 32, c2, false, 2, 256, true));
+    w = fmax(w, check(65536, 8, 20, c1, false, 1, 384, true));
+    w = fmax(w, check(65536, 4, 20, c2, true, 1, 384, true));
+    w = fmax(w, check(2000, 64, 3, c1, false, 1, 384, true));
+    w = fmax(w, check(1 << 20, 2, 20, c1, false, 8, 384, true));
+    if (g_ver == 3) { w = fmax(w, check(65536, 8, 20, 20, false, 1, 384, true)); w = fmax(w, check(8192, 64, 20, 5, false, 1, 384, true)); }
+    printf("v%d worst %.3e %s\n", g_ver, w, w < 1e-11 ? "OK" : "FAIL");
+  }
   if (argc > 1) return 0;
-  for (int chunk : {3, 4, 5}) timeit(65536, 64, 20, chunk, 384);
-  timeit(8192, 64, 20, 5, 384);      // C3 on 8 ranks
-  timeit(1 << 19, 64, 20, 5, 384);   // C4 on 8 ranks
-  timeit(1 << 22, 64, 20, 5, 384);   // C4
-  timeit(1 << 20, 128, 20, 5, 384);  // C5
+  g_ver = 3;
+  for (int chunk : {20, 10, 7, 5, 4}) timeit(65536, 64, 20, chunk, 384);
+  for (int chunk : {20, 10, 5}) timeit(8192, 64, 20, chunk, 384);      // C3 on 8 ranks
+  for (int chunk : {20, 10, 5}) timeit(1 << 19, 64, 20, chunk, 384);   // C4 on 8 ranks
+  for (int chunk : {20, 10, 5}) timeit(1 << 22, 64, 20, chunk, 384);   // C4
+  for (int chunk : {10}) timeit(1 << 20, 128, 20, chunk, 384);  // C5
   return 0;
 }

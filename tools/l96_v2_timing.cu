@@ -3,19 +3,19 @@
 #include <cstdio>
 #include <vector>
 #include <cmath>
-#include "../dataassimbench_b200/csrc/l96_forecast_v2.cu"
+#include "experiments/l96_forecast_v2.cu"
 namespace dab { bool pdl_enabled() { return false; } }
 using namespace dab;
 int main() {
   const long long N = 65536; const int k = 64, S = 20, chunk = 5; const double dt = 0.01, F = 8.0;
-  const long long ld_e = (8 * S + N + 4 * S + 1) & ~1ll, scr_ld = l96_v2_scratch_ld(N, S);
+  const long long ld_e = (8 * S + N + 4 * S + 1) & ~1ll, scr_ld = l96_v2x_scratch_ld(N, S);
   double *d_in, *d_out, *d_s0, *d_s1; unsigned* d_flags;
   cudaMalloc(&d_in, (size_t)k * ld_e * 8); cudaMalloc(&d_out, (size_t)k * N * 8);
   cudaMalloc(&d_s0, (size_t)k * scr_ld * 8); cudaMalloc(&d_s1, (size_t)k * scr_ld * 8);
   std::vector<double> h((size_t)k * ld_e);
   for (size_t i = 0; i < h.size(); ++i) h[i] = 8.0 + 2.0 * sin(0.01 * i);
   cudaMemcpy(d_in, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
-  const size_t nf = l96_v2_flag_count(N, k, S);
+  const size_t nf = l96_v2x_flag_count(N, k, S);
   cudaMalloc(&d_flags, nf * 4); cudaMemset(d_flags, 0, nf * 4);
   unsigned long long* d_ctr; unsigned long long ctr_base = 0; cudaMalloc(&d_ctr, 8); cudaMemset(d_ctr, 0, 8);
   unsigned epoch = 0;
