@@ -86,13 +86,14 @@ def device_generators(H):
     return forecast, padded_table
 
 
-def make_workload(name, seed=42, generators=None):
+def make_workload(name, seed=42, generators=None, n_cycles=None):
     """Synthetic experiment: truth spun up with RK4, ensemble = truth + N(0,1),
     one observation time per window placed at the analysis time, stationary random locations
     drawn like Observer does (default_rng.choice(N, n_obs, replace=False, shuffle=False))."""
     rk4, padded_table = generators if generators is not None else oracle_generators()
     w = dict(WORKLOADS[name])
     N, k, S, dt = w["N"], w["k"], w["S"], w["dt"]
+    n_cycles = BLOCK if n_cycles is None else int(n_cycles)
     rng = np.random.default_rng(seed)
     truth = 8.0 + rng.standard_normal(N)
     # spin-up onto the attractor (local decorrelation takes a few time units); bounded so that the
@@ -102,17 +103,17 @@ def make_workload(name, seed=42, generators=None):
     locs = np.sort(rng.choice(N, n_obs, replace=False, shuffle=False)) if n_obs == N else \
         rng.choice(N, n_obs, replace=False, shuffle=False)
     X0 = truth + rng.standard_normal((k, N))
-    vals = np.empty((BLOCK, n_obs))
+    vals = np.empty((n_cycles, n_obs))
     x = truth
-    for c in range(BLOCK):
+    for c in range(n_cycles):
         vals[c] = x[locs] + w["sd"] * rng.standard_normal(n_obs)
-        if c + 1 < BLOCK:
+        if c + 1 < n_cycles:
             x = rk4(x, S, dt)
-    obs_times = np.arange(BLOCK) * (S * dt)
-    padded = padded_table(obs_times, S * dt, BLOCK)
+    obs_times = np.arange(n_cycles) * (S * dt)
+    padded = padded_table(obs_times, S * dt, n_cycles)
     w.update(n_obs=n_obs, X0=np.ascontiguousarray(X0), vals=np.ascontiguousarray(vals),
-             sysidx=np.ascontiguousarray(np.tile(locs, (BLOCK, 1)).astype(np.int64)), padded=padded,
-             name=name)
+             sysidx=np.ascontiguousarray(np.tile(locs, (n_cycles, 1)).astype(np.int64)), padded=padded,
+             name=name, obs_times=obs_times, n_cycles=n_cycles)
     return w
 
 
@@ -242,20 +243,25 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------ reference arm
+def shared_config(w):
+    """The keys both arms print under `config` (the driver compares them)."""
+    return {"workload": w["label"], "N": w["N"], "k": w["k"], "n_obs": w["n_obs"], "S": w["S"],
+            "window": w["S"] * w["dt"], "integrator": "rk4"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = make_workload(args.workload)
-    cps, done = time_oracle(w, args.steps, min(args.warmup, 1), budget_s=args.cpu_budget)
+    cps, done = time_oracle(w, args.steps, args.warmup, budget_s=args.cpu_budget)
     k, S = w["k"], w["S"]
     line = {
         "impl": "reference", "metric": "etkf_cycles_per_s", "value": cps, "unit": "cycles/s",
-        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
         "ms_per_step": 1e3 / cps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "N": w["N"], "k": k, "n_obs": w["n_obs"], "S": S,
-                   "window": S * w["dt"], "integrator": "rk4"},
+        "config": shared_config(w),
         "member_steps_per_s": cps * k * S,
         "cpu_baseline": {"value": cps, "unit": "cycles/s", "cores": cpu_threads(), "kind": "port",
                          "sample": "%d full cycles of the NumPy/SciPy oracle (gather + diagonal R + eigh + "
@@ -268,7 +274,7 @@ def run_reference(args):
     emit(line)
 
 
-def run_c2_batched(H, B=4096, n_cycles=50):
+def run_c2_batched(H, B=4096, n_cycles=200):
     """4096 independent Lorenz-96 N=40, k=20 ETKF experiments (inflation sweep 1.0..1.5), S=20,
     through dab_etkf_cycle_batched_f64 with host buffers; wall clock of the second call."""
     from dataassimbench_b200 import _native
@@ -293,168 +299,33 @@ def run_c2_batched(H, B=4096, n_cycles=50):
     t0 = time.perf_counter()
     H.etkf_cycle_batched(cfg, B, rho, x0, vals1, idx, 3, padded, None, mean, None)
     t1 = time.perf_counter()
-    return {"workload": "%d x (Lorenz96 N=40, k=20) ETKF, inflation sweep, %d cycles, S=20, one launch" % (B, n_cycles),
+    finite = np.isfinite(mean).all(axis=(1, 2))
+    return {"workload": "%d x (Lorenz96 N=40, k=20) ETKF, inflation sweep %.2f..%.2f, %d cycles, S=20, one launch"
+                        % (B, rho[0], rho[-1], n_cycles),
             "experiment_cycles_per_s": B * n_cycles / (t1 - t0), "member_steps_per_s": B * n_cycles * k * S / (t1 - t0),
-            "seconds": t1 - t0, "all_finite": bool(np.isfinite(mean).all()),
+            "seconds": t1 - t0, "finite_experiments": int(finite.sum()),
+            "largest_inflation_still_finite": float(rho[finite].max()) if finite.any() else None,
+            "smallest_inflation_not_finite": float(rho[~finite].min()) if (~finite).any() else None,
             "timer": "host wall clock, host buffers in, ensemble-mean analyses out"}
 
 
 # ------------------------------------------------------------------------------ product arm
-def run_product(args):
-    import torch
-    import torch.distributed as dist
-    from dataassimbench_b200 import _native
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product arm has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world != args.gpus:
-        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
-                         % (args.gpus, world))
-
-    H = _native.Handle(local_rank)
-    w = make_workload(args.workload, generators=device_generators(H))
-    N, k, S = w["N"], w["k"], w["S"]
-    from dataassimbench_b200.sharded import ShardedCycler
-    cyc = ShardedCycler(H, w, BLOCK, rank, world)
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    stream = torch.cuda.ExternalStream(H.cycler_stream())
-    K, W = args.steps, args.warmup
-
-    def run_cycles(n):
-        done = 0
-        while done < n:
-            m = min(BLOCK, n - done)
-            cyc.reset()
-            cyc.run(0, m)
-            done += m
-
-    run_cycles(W)
-    H.sync()
-    barrier()
-    launches0 = H.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    run_cycles(K)
-    ev1.record(stream)
-    H.sync()
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
-    launches = H.kernel_launches() - launches0
-    final = cyc.state_is_finite()
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        f = torch.tensor([1.0 if final else 0.0], device="cuda")
-        dist.all_reduce(f, op=dist.ReduceOp.MIN)
-        final = bool(f.item() > 0.5)
-    cps = K / (ms * 1e-3)
-
-    # ---- per-kernel timing (separate pass: event records between kernels perturb the main timing)
-    H.set_profiling(True)
-    run_cycles(BLOCK)            # warm
-    H.read_profile()
-    run_cycles(max(BLOCK, min(K, 100)))
-    prof = H.read_profile()
-    H.set_profiling(False)
-    peaks = H.measure_fp64_peak()
-    sampler.stop_flag = True
-
-    # ---- e2e through the host-buffer C-ABI call (rank-local; N=1 only)
-    e2e = None
-    if world == 1:
-        x0 = torch.from_numpy(w["X0"]).pin_memory()
-        out = torch.empty((BLOCK, k, N), dtype=torch.float64).pin_memory()
-        cfg = cyc.config(n_cycles=BLOCK)
-        reps = max(1, min(K, 200) // BLOCK)
-        H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)      # warm-up
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)
-        t1 = time.perf_counter()
-        assert bool(torch.isfinite(out).all())
-        h2d = (w["X0"].nbytes + w["vals"].nbytes + w["sysidx"].nbytes + w["padded"].nbytes) / BLOCK
-        e2e = {"value": reps * BLOCK / (t1 - t0), "unit": "cycles/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * N * 8),
-               "timer": "host wall clock around dab_etkf_cycle_host_f64 (setup, H2D, %d cycles, "
-                        "per-cycle D2H of the analysis, sync)" % BLOCK, "steps": reps * BLOCK}
-
-    else:
-        # grid-sharded e2e: every rank uploads its slab of the ensemble from pinned host memory,
-        # cycles, and copies its slab of EVERY analysis back to pinned host memory over its own PCIe
-        # link (copy stream, overlapped with the next cycle); observations were uploaded at setup.
-        lo, hi = cyc.plan.slab(rank)
-        n_loc = hi - lo
-        x0 = torch.from_numpy(np.ascontiguousarray(w["X0"][:, lo:hi])).pin_memory()
-        out_host = torch.empty((BLOCK, k, n_loc), dtype=torch.float64).pin_memory()
-        reps = max(1, min(K, 200) // BLOCK)
-
-        def one_block():
-            H.cycler_set_state(x0, True)
-            with torch.cuda.stream(stream):
-                for c in range(BLOCK):
-                    H.cycler_stats(c)
-                    if not cyc.device_exchange:
-                        dist.all_reduce(cyc.stats)
-                    H.cycler_update_host(c, out_host[c])      # D2H on the handle's copy stream
-            H.sync()
-
-        one_block()                                                     # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            one_block()
-        barrier()
-        t1 = time.perf_counter()
-        tt = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ok = torch.tensor([1.0 if bool(torch.isfinite(out_host).all()) else 0.0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        assert bool(ok.item() > 0.5)
-        e2e = {"value": reps * BLOCK / float(tt.item()), "unit": "cycles/s",
-               "h2d_bytes_per_step": int(w["X0"].nbytes / BLOCK), "d2h_bytes_per_step": int(k * N * 8),
-               "timer": "host wall clock, max over ranks: per rank H2D of its ensemble slab, %d cycles, per-cycle "
-                        "D2H of its slab of the analysis (copy stream), sync; bytes are the whole job's" % BLOCK,
-               "steps": reps * BLOCK}
-
-    # ---- BASELINE configs[1] in passing (N=1 only): 4096 x (N=40, k=20) inflation sweep, one launch
-    c2 = None
-    if world == 1 and w["name"] == "c3":
-        c2 = run_c2_batched(H)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline bookkeeping
+def load_peaks():
     measured = {}
     try:
         measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = measured.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in measured else "fallback"
-    fp64_peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
+    return measured.get("hbm_gbs", 6650.0), ("measured (MEASURED_PEAKS.json)" if "hbm_gbs" in measured else "fallback")
+
+
+def kernel_table(prof, w, world, fp64_peak, hbm_peak):
+    """Per-kernel time share and roofline fractions from the CUDA-event profiling pass; algorithmic
+    flops / bytes per launch on one rank as in SURVEY.md 8d / DESIGN.md 4."""
+    N, k, S = w["N"], w["k"], w["S"]
     n_loc = N // world
     n_y = w["n_obs"] / world
-    alg = {   # algorithmic flops / bytes per launch on one rank
+    alg = {
         "forecast": dict(flops=FLOPS_PER_POINT_STEP * n_loc * k * S, bytes=16.0 * n_loc * k),
         "transform": dict(flops=2.0 * n_loc * k * k, bytes=16.0 * n_loc * k),
         "contraction": dict(flops=2.0 * n_y * k * k + 4.0 * n_y * k, bytes=8.0 * k * n_y + 16.0 * n_y),
@@ -476,20 +347,300 @@ def run_product(args):
             ent["gbs"] = round(a["bytes"] / (us * 1e-6) / 1e9, 1)
             ent["frac_hbm"] = round(ent["gbs"] / hbm_peak, 4)
         kernels[name] = ent
-    fc = kernels.get("forecast", {})
+    return kernels, alg
+
+
+class Ctx:
+    """Rank plumbing shared by the workload runs of one bench invocation."""
+
+    def __init__(self, torch, dist, rank, world, local_rank):
+        self.torch, self.dist, self.rank, self.world, self.local_rank = torch, dist, rank, world, local_rank
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok):
+        if self.world == 1:
+            return bool(ok)
+        f = self.torch.tensor([1.0 if ok else 0.0], device="cuda")
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.MIN)
+        return bool(f.item() > 0.5)
+
+
+def timed_cycles(ctx, H, cyc, K, W):
+    """W untimed + K timed cycles (experiments of BLOCK cycles from a fresh ensemble, reset inside the
+    timed region); CUDA events on the cycler's stream, max over ranks.  Returns (ms, launches, t0, t1)."""
+    torch = ctx.torch
+    stream = torch.cuda.ExternalStream(H.cycler_stream())
+
+    def run_cycles(n):
+        done = 0
+        while done < n:
+            m = min(BLOCK, n - done)
+            cyc.reset()
+            cyc.run(0, m)
+            done += m
+
+    run_cycles(W)
+    H.sync()
+    ctx.barrier()
+    launches0 = H.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    run_cycles(K)
+    ev1.record(stream)
+    H.sync()
+    ctx.barrier()
+    t_wall1 = time.perf_counter()
+    ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
+    return ms, H.kernel_launches() - launches0, t_wall0, t_wall1, run_cycles
+
+
+def profile_kernels(H, run_cycles, K):
+    """Per-kernel timing in a separate pass (event records between kernels perturb the main timing)."""
+    H.set_profiling(True)
+    run_cycles(BLOCK)            # warm
+    H.read_profile()
+    run_cycles(max(BLOCK, min(K, 100)))
+    prof = H.read_profile()
+    H.set_profiling(False)
+    return prof
+
+
+def single_gpu_reference(ctx, w, K):
+    """Rank 0 alone runs the same experiment on ONE GPU through a second handle: its rate (for the strong-
+    scaling efficiency of this workload) and the state after BLOCK cycles (for the N-rank parity check)."""
+    from dataassimbench_b200 import _native
+    from dataassimbench_b200.sharded import ShardedCycler
+    H1 = _native.Handle(ctx.local_rank)
+    one = Ctx(ctx.torch, ctx.dist, 0, 1, ctx.local_rank)
+    cyc1 = ShardedCycler(H1, w, BLOCK, 0, 1)
+    ms, _, _, _, _ = timed_cycles(one, H1, cyc1, K, BLOCK)
+    cyc1.reset()
+    cyc1.run(0, 1)
+    first = cyc1.state()
+    cyc1.run(1, BLOCK)
+    final = cyc1.state()
+    H1.sync()
+    del cyc1
+    H1.close()
+    return K / (ms * 1e-3), (first, final)
+
+
+def parity_vs_single_gpu(ctx, cyc, final1):
+    """max |x_N - x_1| / max |x_1| of the ensemble after BLOCK cycles from the same fresh ensemble: the
+    N-rank run (slabs gathered on rank 0 over NCCL) against rank 0's single-GPU run."""
+    torch, dist = ctx.torch, ctx.dist
+    out = []
+    cyc.reset()
+    for i, (c0, c1) in enumerate(((0, 1), (1, BLOCK))):
+        cyc.run(c0, c1)
+        slab = cyc.state().contiguous()
+        parts = [torch.empty_like(slab) for _ in range(ctx.world)] if ctx.rank == 0 else None
+        dist.gather(slab, parts, dst=0)
+        if ctx.rank == 0:
+            full = torch.cat(parts, dim=1)
+            out.append(float(((full - final1[i]).abs().max() / final1[i].abs().max()).item()))
+            del full, parts
+    return out if ctx.rank == 0 else None
+
+
+def run_workload(ctx, H, name, K, W, peaks, hbm):
+    """One workload on all ranks: rate, per-kernel table, forecast roofline; with more than one rank also the
+    single-GPU rate measured in the same run and the parity of the N-rank result against it."""
+    from dataassimbench_b200.sharded import ShardedCycler
+    w = make_workload(name, generators=device_generators(H))
+    cps1 = final1 = None
+    if ctx.world > 1:
+        if ctx.rank == 0:
+            cps1, final1 = single_gpu_reference(ctx, w, max(BLOCK, min(K, 5 * BLOCK)))
+        ctx.barrier()
+    cyc = ShardedCycler(H, w, BLOCK, ctx.rank, ctx.world)
+    ms, launches, t0, t1, run_cycles = timed_cycles(ctx, H, cyc, K, W)
+    final_ok = ctx.all_true(cyc.state_is_finite())
+    prof = profile_kernels(H, run_cycles, K)
+    parity = parity_vs_single_gpu(ctx, cyc, final1) if ctx.world > 1 else None
+    fp64_peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
+    kernels, alg = kernel_table(prof, w, ctx.world, fp64_peak, hbm[0])
+    cps = K / (ms * 1e-3)
+    rec = {"workload": w["label"], "cycles_per_s": cps, "ms_per_cycle": ms / K, "steps": K, "warmup": W,
+           "member_steps_per_s": cps * w["k"] * w["S"], "all_finite": final_ok,
+           "forecast_frac_fp64": kernels.get("forecast", {}).get("frac_fp64"),
+           "forecast_shape": dict(zip(("code", "launches_per_window"), H.cycler_forecast_shape())),
+           "kernels": kernels}
+    if ctx.world > 1:
+        rec["single_gpu_cycles_per_s"] = cps1
+        rec["efficiency_vs_1gpu"] = None if cps1 is None else cps / (ctx.world * cps1)
+        rec["parity_vs_1gpu"] = None if parity is None else parity[0]
+        rec["parity_vs_1gpu_after_%d_cycles" % BLOCK] = None if parity is None else parity[1]
+        rec["parity_note"] = ("max |x_N - x_1| / max |x_1| over the whole ensemble after 1 cycle (analysis + forecast; the north "
+                              "star's single-cycle tolerance is 1e-10) and after %d cycles from the same fresh ensemble (the "
+                              "statistics are summed in a different order on N ranks; the chaotic dynamics double that "
+                              "rounding difference every ~2 cycles); the 1-GPU run is rank 0's, in this process, through a "
+                              "second handle" % BLOCK)
+    return rec, dict(w=w, cyc=cyc, ms=ms, launches=launches, t0=t0, t1=t1, kernels=kernels, alg=alg)
+
+
+def run_e2e(ctx, H, w, cyc, K):
+    """Cycles/s with HOST buffers in and out (see the module docstring)."""
+    torch, dist = ctx.torch, ctx.dist
+    N, k = w["N"], w["k"]
+    reps = max(1, min(K, 200) // BLOCK)
+    if ctx.world == 1:
+        x0 = torch.from_numpy(w["X0"]).pin_memory()
+        out = torch.empty((BLOCK, k, N), dtype=torch.float64).pin_memory()
+        cfg = cyc.config(n_cycles=BLOCK)
+        H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)      # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            H.etkf_cycle_host(cfg, x0, w["vals"], w["sysidx"], w["padded"], out)
+        t1 = time.perf_counter()
+        assert bool(torch.isfinite(out).all())
+        h2d = (w["X0"].nbytes + w["vals"].nbytes + w["sysidx"].nbytes + w["padded"].nbytes) / BLOCK
+        return {"value": reps * BLOCK / (t1 - t0), "unit": "cycles/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * N * 8),
+                "timer": "host wall clock around dab_etkf_cycle_host_f64 (setup, H2D, %d cycles, "
+                         "per-cycle D2H of the analysis, sync); ensemble and result buffers pinned" % BLOCK,
+                "steps": reps * BLOCK}
+    # grid-sharded: every rank uploads its slab of the ensemble from pinned host memory, cycles, and copies
+    # its slab of EVERY analysis back to pinned host memory over its own PCIe link (copy stream, overlapped
+    # with the next cycle); observations were uploaded at setup.
+    stream = torch.cuda.ExternalStream(H.cycler_stream())
+    lo, hi = cyc.plan.slab(ctx.rank)
+    x0 = torch.from_numpy(np.ascontiguousarray(w["X0"][:, lo:hi])).pin_memory()
+    out_host = torch.empty((BLOCK, k, hi - lo), dtype=torch.float64).pin_memory()
+
+    def one_block():
+        H.cycler_set_state(x0, True)
+        with torch.cuda.stream(stream):
+            for c in range(BLOCK):
+                H.cycler_stats(c)
+                if not cyc.device_exchange:
+                    dist.all_reduce(cyc.stats)
+                H.cycler_update_host(c, out_host[c])      # D2H on the handle's copy stream
+        H.sync()
+
+    one_block()                                                     # warm-up
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_block()
+    ctx.barrier()
+    t1 = time.perf_counter()
+    tt = ctx.max_over_ranks(t1 - t0)
+    assert ctx.all_true(bool(torch.isfinite(out_host).all()))
+    return {"value": reps * BLOCK / tt, "unit": "cycles/s",
+            "h2d_bytes_per_step": int(w["X0"].nbytes / BLOCK), "d2h_bytes_per_step": int(k * N * 8),
+            "timer": "host wall clock, max over ranks: per rank H2D of its ensemble slab, %d cycles, per-cycle "
+                     "D2H of its slab of the analysis (copy stream), sync; bytes are the whole job's" % BLOCK,
+            "steps": reps * BLOCK}
+
+
+def run_e2e_api(w, K):
+    """The same metric through the public Python API, `dacycler.ETKF(...).cycle()`, with pageable NumPy inputs
+    in a Dataset and a Dataset of analyses out: what a dabench user's script does (N = 1)."""
+    import dataassimbench_b200 as dab
+    from dataassimbench_b200 import _xr
+    N, k, S, dt = w["N"], w["k"], w["S"], w["dt"]
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=dt, store_as_jax=True))
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=dt, ensemble_dim=k, model_obj=model,
+                           multiplicative_inflation=w["rho"])
+    init = _xr.new_dataset({"x": (("ensemble", "index"), w["X0"])}, coords={"time": 0.0})
+    obs = _xr.new_dataset({"x": (("time", "observations"), w["vals"]),
+                           "system_index": (("variable", "time", "observations"), w["sysidx"][None])},
+                          coords={"time": w["obs_times"], "variable": np.array(["x"])},
+                          attrs={"error_sd": w["sd"], "stationary_observers": True})
+    kw = dict(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=BLOCK, obs_error_sd=w["sd"],
+              analysis_window=S * dt, analysis_time_in_window=0.0)
+    out = dc.cycle(**kw)                                            # warm-up
+    reps = max(1, min(K, 100) // BLOCK)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = dc.cycle(**kw)
+    t1 = time.perf_counter()
+    assert bool(np.isfinite(out["x"].values[-1]).all())
+    return {"value": reps * BLOCK / (t1 - t0), "unit": "cycles/s", "steps": reps * BLOCK,
+            "timer": "host wall clock around ETKF.cycle(): window bookkeeping, setup, H2D from pageable NumPy, "
+                     "%d cycles, per-cycle D2H, Dataset out" % BLOCK}
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from dataassimbench_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
+                         % (args.gpus, world))
+    ctx = Ctx(torch, dist, rank, world, local_rank)
+    H = _native.Handle(local_rank)
+    peaks = H.measure_fp64_peak()
+    hbm = load_peaks()
+    K, W = args.steps, args.warmup
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rec, aux = run_workload(ctx, H, args.workload, K, W, peaks, hbm)
+    w, cyc = aux["w"], aux["cyc"]
+    e2e = run_e2e(ctx, H, w, cyc, K)
+    sampler.stop_flag = True
+    clocks = sampler.summary(aux["t0"], aux["t1"])
+
+    # ---- the other BASELINE configs (sub-records of the same line; the headline stays `args.workload`)
+    extra = {}
+    if w["name"] == "c3" and not args.no_extra:
+        del cyc
+        for name in ("c4", "c5"):
+            r2, aux2 = run_workload(ctx, H, name, max(BLOCK, min(K, 3 * BLOCK)), BLOCK, peaks, hbm)
+            del aux2
+            extra[name] = r2
+        if world == 1:
+            extra["c2_batched"] = run_c2_batched(H, n_cycles=200)
+            c1, _ = run_workload(ctx, H, "c1", 200, 20, peaks, hbm)
+            extra["c1"] = {kk: c1[kk] for kk in ("workload", "cycles_per_s", "ms_per_cycle", "steps", "all_finite")}
+            extra["e2e_api"] = run_e2e_api(w, K)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fp64_peak = max(peaks["dmma_tflops"], peaks["dfma_tflops"])
+    fc = rec["kernels"].get("forecast", {})
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("forecast")
     except Exception:
         pass
-    roofline = {"kernel": "l96_rk4_window_kernel (forecast)", "bound": "fp64",
-                "achieved": fc.get("tflops"), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
+    roofline = {"kernel": "forecast (K1; kernel chosen by the setup-time tuner: config_detail.forecast_shape)",
+                "bound": "fp64", "achieved": fc.get("tflops"), "peak": round(fp64_peak, 2), "unit": "TFLOP/s",
                 "frac": fc.get("frac_fp64"), "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                  "ncu --set full capture of this kernel at this workload (cold cache, single launch); "
+                                  "static file, not measured in this run",
                 "peak_source": "DMMA.8x8x4 / DFMA chains measured in this run through "
                                "dab_measure_fp64_peak (dfma %.2f, dmma %.2f TFLOP/s)"
                                % (peaks["dfma_tflops"], peaks["dmma_tflops"]),
-                "flops_per_launch": alg["forecast"]["flops"],
-                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src}
+                "flops_per_launch": aux["alg"]["forecast"]["flops"],
+                "hbm_peak_gbs": hbm[0], "hbm_peak_source": hbm[1]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -499,25 +650,32 @@ def run_product(args):
                          "(restatement of the reference; JAX is not installable here)" % done,
                "host_cpus": os.cpu_count()}
 
+    N, k, S = w["N"], w["k"], w["S"]
+    cps = rec["cycles_per_s"]
     line = {
         "metric": "etkf_cycles_per_s", "value": cps, "unit": "cycles/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": aux["ms"] / K, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "N": N, "k": k, "n_obs": w["n_obs"], "S": S,
-                   "window": S * w["dt"], "integrator": "rk4",
-                   "l2": "state (%.1f MB) is L2-resident; no flush: the cycle streams through all of it "
-                         "between reuses" % (N * k * 8 / 1e6),
-                   "experiment": "%d-cycle run from a fresh ensemble, repeated; reset copy inside the "
-                                 "timed region" % BLOCK,
-                   "parallelism": "grid-sharded x%d" % world if world > 1 else "single GPU",
-                   "forecast_shape": dict(zip(("code", "launches_per_window"), H.cycler_forecast_shape()))},
+        "config": shared_config(w),
+        "config_detail": {
+            "l2": "state (%.1f MB) is L2-resident; no flush: the cycle streams through all of it "
+                  "between reuses" % (N * k * 8 / 1e6),
+            "experiment": "%d-cycle run from a fresh ensemble, repeated; reset copy inside the "
+                          "timed region" % BLOCK,
+            "parallelism": "grid-sharded x%d" % world if world > 1 else "single GPU",
+            "forecast_shape": rec["forecast_shape"]},
         "member_steps_per_s": cps * k * S,
         "point_steps_per_s": cps * k * S * N,
-        "all_finite": final,
-        "roofline": roofline, "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "c2_batched": c2,
-        "clocks": sampler.summary(t_wall0, t_wall1),
+        "all_finite": rec["all_finite"],
+        "roofline": roofline, "kernels": rec["kernels"],
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": aux["launches"],
+        "clocks": clocks,
     }
+    for key in ("single_gpu_cycles_per_s", "efficiency_vs_1gpu", "parity_vs_1gpu",
+                "parity_vs_1gpu_after_%d_cycles" % BLOCK, "parity_note"):
+        if key in rec:
+            line[key] = rec[key]
+    line.update(extra)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -532,6 +690,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU oracle time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 / C2 / C1 / API sub-records")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
     # line when the box sets NCCL_DEBUG): point fd 1 at stderr for the run and give the real stdout

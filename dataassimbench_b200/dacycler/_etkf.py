@@ -184,7 +184,9 @@ class ETKF(DACycler):
         cfg = p['cfg']
         k, N, S = cfg.ensemble_dim, cfg.system_dim, cfg.n_steps
         H = handle()
-        out = torch.empty((n_cycles, k, N), dtype=torch.float64).pin_memory()
+        # pinned directly (no pageable detour); torch's caching host allocator recycles the block of a result the
+        # caller has dropped, so repeated calls do not pay the page-locking again
+        out = torch.empty((n_cycles, k, N), dtype=torch.float64, pin_memory=True)
         dim = p['state_dim']
         if not return_forecast:
             H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out)
