@@ -138,6 +138,27 @@ def test_observer_samples_a_device_trajectory_bit_for_bit(stationary, N, n_times
     assert np.array_equal(v[ok], (traj[pos][np.arange(len(pos))[:, None], si[0]] + e[0])[ok])
 
 
+@pytest.mark.parametrize("stationary", [True, False])
+def test_observer_device_route_matches_the_oracle_observer(stationary):
+    """The device route of Observer.observe (draws on the host, sampling by dab_observe_f64) directly against
+    oracle/observer.py (the restatement pinned by the reference's own known answers,
+    tests/observer_base_test.py:133-180): indices, times, errors and values to the bit."""
+    from oracle import observer as o_obs
+    rng = np.random.default_rng(3)
+    N, n_times = 3000, 20
+    traj = rng.standard_normal((n_times, N))
+    times = np.arange(n_times) * 0.05
+    kw = dict(random_time_density=0.6, random_location_density=0.25, error_sd=0.9, error_bias=-0.1,
+              stationary_observers=stationary, random_seed=17)
+    ref = o_obs.observe(traj, times, **kw)
+    ds = dab.observer.Observer(_xr.new_dataset({'x': (('time', 'index'), torch.from_numpy(traj).cuda())},
+                                               coords={'time': times, 'index': np.arange(N)}), **kw).observe()
+    assert np.array_equal(np.asarray(ds['time'].values), ref['time'])
+    assert np.array_equal(np.asarray(ds['system_index'].values)[0], ref['system_index'])
+    assert np.array_equal(np.asarray(ds['errors'].values)[0], ref['errors'], equal_nan=True)
+    assert np.array_equal(np.asarray(ds['x'].values), ref['values'], equal_nan=True)
+
+
 def test_observe_entry_point_rejects_bad_indices():
     from dataassimbench_b200._runtime import handle
     H = handle()

@@ -143,6 +143,44 @@ def test_forecast_cta_shapes_agree(H, shape, N, k, steps, monkeypatch):
     assert torch.equal(out, base)
 
 
+def run_window_through_cycler(H, X, S, forced=None, monkeypatch=None, dt=0.01):
+    """One analysis-free cycle (no observation in the window: T = inflation only, rho = 1 -> identity) through the
+    cycler, i.e. through the extended-layout path the tuner serves: returns the forecast of X."""
+    k, N = X.shape
+    padded = np.zeros((1, 1), dtype=np.int64)                  # the reference's "no observation time" slot
+    cfg = _native.CycleConfig(system_dim=N, ensemble_dim=k, n_steps=S, model_dt=dt, forcing=8.0, rho=1.0,
+                              obs_error_sd=1.0, n_obs_times=1, n_obs=1, stationary=1, n_cycles=1, t_pad=1,
+                              rank=0, world=1)
+    if forced is not None:
+        monkeypatch.setenv(*forced)
+    H.cycler_setup(cfg, np.zeros((1, 1)), np.zeros((1, 1), dtype=np.int64), padded)
+    if forced is not None:
+        monkeypatch.delenv(forced[0])
+    H.cycler_set_state(np.ascontiguousarray(X), True)
+    H.cycler_run(0, 1)
+    H.sync()
+    out = np.empty((k, N))
+    H.cycler_get_state(out, True)
+    return out, H.cycler_forecast_shape()[0]
+
+
+@pytest.mark.parametrize("N,k,S", [(40000, 8, 20), (65536, 16, 20), (30000, 12, 7), (9000, 64, 32), (262144, 6, 20)])
+def test_forecast_pipelined_chain_kernel_is_bit_identical(H, N, k, S, monkeypatch):
+    """The pipelined-chain kernel (l96_forecast_v5.cu: tiles take their left boundary from the previous tile's
+    history instead of recomputing a halo) against the first design, through the cycler: identical bits, and
+    the oracle tolerance on a few members."""
+    X, _ = make_ensemble(N, k, seed=N + S, spinup=50)
+    X = X + 0.0
+    # all-masked window: the analysis is Xb T with T = U + sqrt(rho)(I - U) = I at rho = 1 up to rounding, so
+    # compare the two forecast kernels on the analysis the cycler itself produced (same T, same bits)
+    base, code0 = run_window_through_cycler(H, X, S, ("DAB_L96_V5", "0"), monkeypatch)
+    out, code5 = run_window_through_cycler(H, X, S, ("DAB_L96_V5", "1"), monkeypatch)
+    assert code5 == 50000 and code0 != 50000
+    assert np.array_equal(out, base)
+    ref = o_l96.rk4_forecast(X[:2], S, 0.01)
+    assert rel_err(out[:2], ref) < 1e-9          # the identity transform adds its own rounding
+
+
 # ------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("N,k,n_y", [(36, 10, 18), (40, 20, 20), (65536, 64, 19661), (1000, 7, 1), (50, 3, 0)])
 def test_gather_bit_exact(H, N, k, n_y):
@@ -326,6 +364,50 @@ def test_analysis_matches_sparse_oracle_large(H, N, k, n_y):
                     torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rel_err(Xa.cpu().numpy(), ref) < 1e-10
+
+
+@pytest.mark.parametrize("N,k,frac", [(1048576, 128, 1.0), (4194304, 64, 0.3)])
+def test_analysis_full_size_c5_c4(H, N, k, frac):
+    """BASELINE configs[4] and [3] at FULL size (contract_kernel<16>, > 2^31-byte ensembles): one analysis against
+    the sparse oracle, every element compared."""
+    rng = np.random.default_rng(N % 1000 + k)
+    truth = 3.0 * rng.standard_normal(N) + 2.0
+    X = truth + rng.standard_normal((k, N))
+    n_y = int(round(frac * N))
+    idx = np.sort(rng.choice(N, n_y, replace=False, shuffle=False)) if n_y == N else rng.choice(N, n_y, replace=False, shuffle=False)
+    idx = idx.astype(np.int64)
+    y = truth[idx] + rng.standard_normal(n_y)
+    ref = o_etkf.analysis_sparse(X, y, idx, np.ones(n_y), 1.0)
+    Xd = dev(X)
+    Xa = torch.empty((k, N), dtype=torch.float64, device='cuda')
+    H.etkf_analysis(Xd, Xa, dev(y), dev(idx), None, 1.0, 1.0, N, k, n_y, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = Xa.cpu().numpy()
+    del Xd, Xa
+    err = 0.0
+    for j in range(k):                                   # row by row: no second 2 GB temporary
+        err = max(err, float(np.max(np.abs(got[j] - ref[j]))))
+    assert err / float(np.max(np.abs(ref))) < 1e-10
+
+
+def test_cycler_ten_cycles_full_c3_matches_oracle_rk4(H):
+    """BASELINE configs[2] at full size (N = 65 536, k = 64, 19 661 stationary observations, S = 20): ten cycles
+    against the oracle cycling with the same RK4 -- analyses of the first cycles to 1e-9, the last one within the
+    growth the chaotic dynamics allow (errors double every ~2 cycles)."""
+    N, k, n_obs, n_cycles, S, sd, rho = 65536, 64, 19661, 10, 20, 1.0, 1.0
+    case = cycler_case(N, k, n_obs, n_cycles, S, sd, rho, True, seed=11)
+    out, final, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, True)
+    X = case['X0'].copy()
+    w = np.full(n_obs, 1.0 / sd ** 2)
+    errs = []
+    for c in range(n_cycles):
+        Xa = o_etkf.analysis_sparse(X, case['vals'][c], case['sysidx'][c], w, rho)
+        errs.append(rel_err(out[c], Xa))
+        X = o_l96.rk4_forecast(Xa, S, case['dt'])
+    assert np.all(np.isfinite(out))
+    assert max(errs[:4]) < 1e-10, errs
+    assert max(errs) < 1e-8, errs
+    assert rel_err(final, X) < 1e-8
 
 
 def test_analysis_empty_obs_collapses_to_mean(H):
