@@ -18,9 +18,13 @@ class ETKF(DACycler):
     traj_block_bytes = 4 << 30      # device memory for return_forecast trajectories, per block of cycles
 
     def __init__(self, system_dim, delta_t, model_obj, B=None, R=None, H=None, h=None,
-                 ensemble_dim=4, multiplicative_inflation=1.0):
+                 ensemble_dim=4, multiplicative_inflation=1.0, distributed=None):
         self.ensemble_dim = ensemble_dim
         self.multiplicative_inflation = multiplicative_inflation
+        # grid sharding over the ranks of torch.distributed's default group (one process per GPU): None =
+        # whenever such a group with more than one rank exists and the grid divides over it, False = never,
+        # True = required (ValueError otherwise).  Not an argument of the reference (it has no multi-GPU path).
+        self.distributed = distributed
         super().__init__(system_dim=system_dim, delta_t=delta_t, model_obj=model_obj,
                          B=B, R=R, H=H, h=h)
 
@@ -169,6 +173,56 @@ class ETKF(DACycler):
         return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx,
                     padded=np.ascontiguousarray(w['padded']), state_dim=state_dim[0] if state_dim else 'index')
 
+    # ------------------------------------------------------------------ grid sharding (one rank per GPU)
+    def _shard_group(self, N, S):
+        """(rank, world) of the run's process group when this call is to be grid-sharded, else None."""
+        if self.distributed is False:
+            return None
+        try:
+            import torch.distributed as dist
+            ready = dist.is_available() and dist.is_initialized()
+        except Exception:
+            ready = False
+        world = dist.get_world_size() if ready else 1
+        # every rank's slab must hold the halo its neighbours read from it (8 S points to the left)
+        ok = world > 1 and world <= 8 and N % world == 0 and N // world >= max(12 * S, 32)
+        if not ok:
+            if self.distributed is True:
+                raise ValueError('distributed=True needs an initialised torch.distributed group of 2..8 ranks and a '
+                                 'grid that divides over them into slabs of at least 12 steps_per_window points')
+            return None
+        return dist.get_rank(), world
+
+    def _cycle_sharded(self, p, group):
+        """The same experiment with the grid cut into one slab per rank (`sharded.ShardedCycler`):
+        every rank passes the SAME inputs, runs the cycles on its slab -- the ranks exchange k*k+k statistics per
+        cycle and read each other's halo columns over NVLink -- and gets the full analyses back (one all-gather
+        of the slabs per block of cycles)."""
+        import torch
+        import torch.distributed as dist
+        from .._runtime import handle
+        from ..sharded import ShardedCycler
+        rank, world = group
+        cfg = p['cfg']
+        k, N, n_cycles = cfg.ensemble_dim, cfg.system_dim, cfg.n_cycles
+        w = dict(N=N, k=k, S=cfg.n_steps, dt=cfg.model_dt, rho=cfg.rho, sd=cfg.obs_error_sd, X0=p['X0'],
+                 vals=p['vals'], sysidx=p['sysidx'], padded=p['padded'], forcing=cfg.forcing,
+                 stationary=cfg.stationary)
+        cyc = ShardedCycler(handle(), w, n_cycles, rank, world)
+        n_loc = N // world
+        out = np.empty((n_cycles, k, N))
+        blk = int(max(1, min(n_cycles, self.traj_block_bytes // (k * N * 8))))
+        slab = torch.empty((blk, k, n_loc), dtype=torch.float64, device='cuda')
+        full = torch.empty((world, blk, k, n_loc), dtype=torch.float64, device='cuda')
+        for c0 in range(0, n_cycles, blk):
+            c1 = min(n_cycles, c0 + blk)
+            cyc.run(c0, c1, slab[:c1 - c0])
+            handle().sync()
+            dist.all_gather_into_tensor(full, slab)
+            got = full[:, :c1 - c0].permute(1, 2, 0, 3).reshape(c1 - c0, k, N)
+            out[c0:c1] = got.cpu().numpy()
+        return out
+
     # ------------------------------------------------------------------ the call
     def cycle(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
               analysis_window=0.2, analysis_time_in_window=None, return_forecast=False):
@@ -183,6 +237,11 @@ class ETKF(DACycler):
                        analysis_window, analysis_time_in_window)
         cfg = p['cfg']
         k, N, S = cfg.ensemble_dim, cfg.system_dim, cfg.n_steps
+        group = self._shard_group(N, S)
+        if group is not None:
+            if return_forecast:
+                raise NotImplementedError('return_forecast=True is single-GPU only')
+            return _xr.new_dataset({'x': (('cycle', 'ensemble', p['state_dim']), self._cycle_sharded(p, group))})
         H = handle()
         # pinned directly (no pageable detour); torch's caching host allocator recycles the block of a result the
         # caller has dropped, so repeated calls do not pay the page-locking again

@@ -101,9 +101,9 @@ class ShardedCycler:
     def config(self, n_cycles):
         w = self.w
         return _native.CycleConfig(
-            system_dim=w["N"], ensemble_dim=w["k"], n_steps=w["S"], model_dt=w["dt"], forcing=8.0,
+            system_dim=w["N"], ensemble_dim=w["k"], n_steps=w["S"], model_dt=w["dt"], forcing=w.get("forcing", 8.0),
             rho=w["rho"], obs_error_sd=w["sd"], n_obs_times=w["vals"].shape[0], n_obs=w["vals"].shape[1],
-            stationary=1, n_cycles=n_cycles, t_pad=w["padded"].shape[1], rank=self.rank, world=self.world)
+            stationary=int(w.get("stationary", 1)), n_cycles=n_cycles, t_pad=w["padded"].shape[1], rank=self.rank, world=self.world)
 
     def reset(self):
         """Fresh ensemble (device-to-device copy on the cycler's stream)."""

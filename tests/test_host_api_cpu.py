@@ -337,3 +337,12 @@ def test_compact_default_operators_match_the_reference_dense_ones():
     with pytest.raises(NotImplementedError):
         ScaledIdentity.sd_of(np.diag([1.0, 2.0]))
     assert len(dc._calc_default_R(np.zeros(0), 1.0)) == 0          # the empty-R branch tests len(R)
+
+
+def test_etkf_grid_sharding_switch_without_a_process_group():
+    """`ETKF(distributed=...)`: no torch.distributed group -> single GPU unless sharding was demanded."""
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=4096, delta_t=0.01))
+    assert dab.dacycler.ETKF(system_dim=4096, delta_t=0.01, model_obj=model)._shard_group(4096, 20) is None
+    assert dab.dacycler.ETKF(system_dim=4096, delta_t=0.01, model_obj=model, distributed=False)._shard_group(4096, 20) is None
+    with pytest.raises(ValueError, match='distributed=True needs'):
+        dab.dacycler.ETKF(system_dim=4096, delta_t=0.01, model_obj=model, distributed=True)._shard_group(4096, 20)
