@@ -63,7 +63,10 @@ _SIGNATURES = {
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
     "dab_etkf_transform_matrix_f64": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
+    "dab_etkf_analysis_diag_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P]),
     "dab_cycler_setup": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P]),
+    "dab_cycler_setup_diag": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P]),
+    "dab_etkf_cycle_host_diag_f64": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P, _P, _P]),
     "dab_cycler_set_state": (C.c_int, [_P, _P, C.c_int]),
     "dab_cycler_get_state": (C.c_int, [_P, _P, C.c_int]),
     "dab_cycler_run": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
@@ -200,12 +203,22 @@ class Handle:
                                                             _ptr(T), _ptr(lam), _ptr(sweeps), _ptr(stream)))
 
     def etkf_analysis(self, Xb, Xa, y, idx, mask, sd, rho, N, k, n_y, stream=None):
-        self._check(self._lib.dab_etkf_analysis_f64(self._h, _ptr(Xb), _ptr(Xa), _ptr(y), _ptr(idx),
-                                                    _ptr(mask), sd, rho, N, k, n_y, _ptr(stream)))
+        """`sd`: a float (R = sd^2 I) or a device array [n_y] (diagonal R, one sigma per observation)."""
+        if isinstance(sd, (int, float)):
+            self._check(self._lib.dab_etkf_analysis_f64(self._h, _ptr(Xb), _ptr(Xa), _ptr(y), _ptr(idx),
+                                                        _ptr(mask), sd, rho, N, k, n_y, _ptr(stream)))
+        else:
+            self._check(self._lib.dab_etkf_analysis_diag_f64(self._h, _ptr(Xb), _ptr(Xa), _ptr(y), _ptr(idx),
+                                                             _ptr(mask), _ptr(sd), rho, N, k, n_y, _ptr(stream)))
 
-    def cycler_setup(self, cfg, obs_values, system_index, padded_time_idx):
-        self._check(self._lib.dab_cycler_setup(self._h, C.byref(cfg), _ptr(obs_values),
-                                               _ptr(system_index), _ptr(padded_time_idx)))
+    def cycler_setup(self, cfg, obs_values, system_index, padded_time_idx, obs_error_sd=None):
+        """`obs_error_sd`: None (cfg.obs_error_sd) or a host array [n_obs_times][n_obs] (diagonal R per slot)."""
+        if obs_error_sd is None:
+            self._check(self._lib.dab_cycler_setup(self._h, C.byref(cfg), _ptr(obs_values),
+                                                   _ptr(system_index), _ptr(padded_time_idx)))
+        else:
+            self._check(self._lib.dab_cycler_setup_diag(self._h, C.byref(cfg), _ptr(obs_values), _ptr(system_index),
+                                                        _ptr(padded_time_idx), _ptr(obs_error_sd)))
 
     def cycler_set_state(self, x, is_host):
         self._check(self._lib.dab_cycler_set_state(self._h, _ptr(x), int(is_host)))
@@ -289,7 +302,12 @@ class Handle:
             self._h, C.byref(cfg), int(batch), _ptr(rho), _ptr(x0), _ptr(obs_values), _ptr(system_index),
             int(shared_index), _ptr(padded_time_idx), _ptr(out_analysis), _ptr(out_mean), _ptr(out_final)))
 
-    def etkf_cycle_host(self, cfg, x0, obs_values, system_index, padded_time_idx, out_analysis):
-        self._check(self._lib.dab_etkf_cycle_host_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),
-                                                      _ptr(system_index), _ptr(padded_time_idx),
-                                                      _ptr(out_analysis)))
+    def etkf_cycle_host(self, cfg, x0, obs_values, system_index, padded_time_idx, out_analysis, obs_error_sd=None):
+        if obs_error_sd is None:
+            self._check(self._lib.dab_etkf_cycle_host_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),
+                                                          _ptr(system_index), _ptr(padded_time_idx),
+                                                          _ptr(out_analysis)))
+        else:
+            self._check(self._lib.dab_etkf_cycle_host_diag_f64(self._h, C.byref(cfg), _ptr(x0), _ptr(obs_values),
+                                                               _ptr(system_index), _ptr(padded_time_idx),
+                                                               _ptr(obs_error_sd), _ptr(out_analysis)))

@@ -89,7 +89,8 @@ struct Cycler {
   double* xb[2] = {nullptr, nullptr};      // plain [k][n_loc], separately cudaMalloc'ed (IPC-exportable)
   size_t xb_bytes = 0;
   DevBuf ext[2];                           // extended-layout analysis buffers
-  DevBuf obs_loc, obs_val, seg, partial, stats, T, lam, info;
+  DevBuf obs_loc, obs_val, obs_sw, seg, partial, stats, T, lam, info;
+  bool has_sw = false;                     // obs_sw holds 1 / sigma per row (diagonal R with unequal entries)
   std::vector<long long> csr_off;          // [n_obs_times + 1]
   std::vector<int> n_seg;                  // per cycle
   std::vector<long long> n_rows;           // per cycle
@@ -129,7 +130,7 @@ struct dab_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   std::string err;
   long launches = 0;
-  DevBuf s_loc, s_val, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
+  DevBuf s_loc, s_val, s_sw, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
@@ -212,7 +213,7 @@ static void cycler_free(dab_handle* h) {
     c.copied_pending[w] = false;
   }
   c.xb_bytes = 0;
-  c.obs_loc.release(); c.obs_val.release(); c.seg.release(); c.partial.release();
+  c.obs_loc.release(); c.obs_val.release(); c.obs_sw.release(); c.seg.release(); c.partial.release();
   c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
   c.xchg.release(); c.xchg_ctr.release(); c.sse_partial.release();
   c.ready = false;
@@ -355,7 +356,7 @@ int dab_destroy(dab_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cycler_free(h);
-  h->s_loc.release(); h->s_val.release(); h->s_seg.release();
+  h->s_loc.release(); h->s_val.release(); h->s_sw.release(); h->s_seg.release();
   h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release();
   h->v2.release();
   h->v5.release();
@@ -502,23 +503,25 @@ int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, int64_t 
 }
 
 // ------------------------------------------------------------------------------- K3 / K4
+// `sd_vec` (nullable, device, [n_y]): per-observation sigma of a diagonal R; `sd` is then ignored
 static int stats_from_arrays(dab_handle* h, const double* X, const double* y, const int64_t* idx,
-                             const uint8_t* mask, double sd, long long N, int k, long long n_y,
+                             const uint8_t* mask, double sd, const double* sd_vec, long long N, int k, long long n_y,
                              double* stats, cudaStream_t st) {
   DAB_CUDA(h, h->s_loc.reserve(sizeof(int) * (size_t)(n_y > 0 ? n_y : 1)));
   DAB_CUDA(h, h->s_val.reserve(sizeof(double) * (size_t)(n_y > 0 ? n_y : 1)));
+  if (sd_vec) DAB_CUDA(h, h->s_sw.reserve(sizeof(double) * (size_t)(n_y > 0 ? n_y : 1)));
   DAB_CUDA(h, h->s_seg.reserve(sizeof(long long) * 3));
   const int grid = contract_grid(n_y, h->sms);
   DAB_CUDA(h, h->s_partial.reserve(sizeof(double) * contract_partial_doubles(k, grid)));
   DAB_CUDA(h, h->s_flag.reserve(sizeof(int)));
   DAB_CUDA(h, cudaMemsetAsync(h->s_flag.p, 0, sizeof(int), st));
-  DAB_CUDA(h, pack_obs_launch(reinterpret_cast<const long long*>(idx), mask, y, n_y, N,
-                              h->s_loc.as<int>(), h->s_val.as<double>(), h->s_flag.as<int>(), st));
+  DAB_CUDA(h, pack_obs_launch(reinterpret_cast<const long long*>(idx), mask, y, sd_vec, n_y, N,
+                              h->s_loc.as<int>(), h->s_val.as<double>(), h->s_sw.as<double>(), h->s_flag.as<int>(), st));
   const long long seg[3] = {0, n_y, 0};
   DAB_CUDA(h, cudaMemcpyAsync(h->s_seg.p, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
-  DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(),
+  DAB_CUDA(h, contract_launch(X, N, k, h->s_loc.as<int>(), h->s_val.as<double>(), sd_vec ? h->s_sw.as<double>() : nullptr,
                               h->s_seg.as<long long>(), 1, n_y, h->s_partial.as<double>(), grid, false, st));
-  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, r_inv_of(sd), stats, nullptr, st));
+  DAB_CUDA(h, stats_reduce_launch(h->s_partial.as<double>(), grid, k, sd_vec ? 1.0 : r_inv_of(sd), stats, nullptr, st));
   h->launches += (n_y > 0 ? 1 : 0) + 2;
   return 0;
 }
@@ -542,7 +545,7 @@ int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, const in
   DAB_ARG(h, N < (1ll << 31));
   DAB_ARG(h, n_y == 0 || (y != nullptr && idx != nullptr));
   DAB_CUDA(h, cudaSetDevice(h->device));
-  int rc = stats_from_arrays(h, X, y, idx, mask, obs_error_sd, N, k, n_y, stats,
+  int rc = stats_from_arrays(h, X, y, idx, mask, obs_error_sd, nullptr, N, k, n_y, stats,
                              static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   return n_y > 0 ? check_index_flag(h, "dab_etkf_stats_f64", static_cast<cudaStream_t>(stream)) : 0;
@@ -560,9 +563,9 @@ int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, dou
   return 0;
 }
 
-int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
-                          const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
-                          int64_t N, int k, int64_t n_y, void* stream) {
+static int analysis_impl(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                         const int64_t* idx, const uint8_t* mask, double obs_error_sd, const double* sd_vec, double rho,
+                         int64_t N, int k, int64_t n_y, void* stream) {
   DAB_ARG(h, h != nullptr);
   DAB_ARG(h, Xb != nullptr && Xa != nullptr && Xb != Xa);
   DAB_ARG(h, N >= 1 && n_y >= 0 && k >= 2 && k <= DAB_MAX_ENSEMBLE);
@@ -575,7 +578,7 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
   DAB_CUDA(h, h->s_T.reserve(sizeof(double) * (size_t)k * k));
   const int empty_R = n_y == 0;
   if (!empty_R) {
-    int rc = stats_from_arrays(h, Xb, y, idx, mask, obs_error_sd, N, k, n_y, h->s_stats.as<double>(), st);
+    int rc = stats_from_arrays(h, Xb, y, idx, mask, obs_error_sd, sd_vec, N, k, n_y, h->s_stats.as<double>(), st);
     if (rc) return rc;
   }
   DAB_CUDA(h, eig_transform_launch(h->s_stats.as<double>(), k, rho, empty_R, h->s_T.as<double>(),
@@ -591,12 +594,27 @@ int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const dou
   return empty_R ? 0 : check_index_flag(h, "dab_etkf_analysis_f64", st);
 }
 
+int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                          const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
+                          int64_t N, int k, int64_t n_y, void* stream) {
+  return analysis_impl(h, Xb, Xa, y, idx, mask, obs_error_sd, nullptr, rho, N, k, n_y, stream);
+}
+
+int dab_etkf_analysis_diag_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                               const int64_t* idx, const uint8_t* mask, const double* obs_error_sd, double rho,
+                               int64_t N, int k, int64_t n_y, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, n_y == 0 || obs_error_sd != nullptr);
+  return analysis_impl(h, Xb, Xa, y, idx, mask, 1.0, obs_error_sd, rho, N, k, n_y, stream);
+}
+
 // ------------------------------------------------------------------------------ the cycler
 // `x0_host` (nullable): initial ensemble in host memory; its upload is enqueued as soon as the
 // buffers exist, so that it overlaps the host-side preparation of the observation tables.
+// `obs_sd` (nullable, host, [n_obs_times][n_obs]): per-slot sigma of a diagonal R; cfg->obs_error_sd is then ignored.
 static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
                              const int64_t* system_index, const int64_t* padded_time_idx,
-                             const double* x0_host) {
+                             const double* x0_host, const double* obs_sd = nullptr) {
   DAB_ARG(h, h != nullptr && cfg != nullptr);
   DAB_ARG(h, cfg->system_dim >= 4 && cfg->system_dim < (1ll << 31));
   DAB_ARG(h, cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= DAB_MAX_ENSEMBLE);
@@ -653,9 +671,10 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   const long long nt = cfg->n_obs_times, no = cfg->n_obs;
   c.csr_off.assign((size_t)nt + 1, 0);
   std::vector<int> loc;
-  std::vector<double> val;
+  std::vector<double> val, swv;
   loc.reserve((size_t)(nt * no / cfg->world + 16));
   val.reserve((size_t)(nt * no / cfg->world + 16));
+  c.has_sw = obs_sd != nullptr;
   // The statistics are sums over observation rows, so the rows of one observation time may be
   // visited in any order: order them by grid location (stable counting sort, O(n)) so that the 32
   // rows of a contraction block touch neighbouring columns of every member instead of 32 random
@@ -702,6 +721,11 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     loc.resize(base + nr); val.resize(base + nr);
     memcpy(loc.data() + base, lrow.data(), sizeof(int) * nr);
     for (size_t i = 0; i < nr; ++i) val[base + i] = vrow[src[i]];
+    if (obs_sd != nullptr) {
+      swv.resize(base + nr);
+      const double* srow = obs_sd + t * no;
+      for (size_t i = 0; i < nr; ++i) { const double sg = srow[src[i]]; swv[base + i] = sg == 0.0 ? 0.0 : 1.0 / sg; }
+    }
     c.csr_off[(size_t)t + 1] = (long long)loc.size();
   }
   DAB_CUDA(h, c.obs_loc.reserve(sizeof(int) * (loc.size() + 1)));
@@ -709,6 +733,10 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   if (!loc.empty()) {
     DAB_CUDA(h, cudaMemcpyAsync(c.obs_loc.p, loc.data(), sizeof(int) * loc.size(), cudaMemcpyHostToDevice, h->stream));
     DAB_CUDA(h, cudaMemcpyAsync(c.obs_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
+    if (c.has_sw) {
+      DAB_CUDA(h, c.obs_sw.reserve(sizeof(double) * (swv.size() + 1)));
+      DAB_CUDA(h, cudaMemcpyAsync(c.obs_sw.p, swv.data(), sizeof(double) * swv.size(), cudaMemcpyHostToDevice, h->stream));
+    }
   }
   // ---- per-cycle segment tables from the padded time indices (0 = masked, t+1 otherwise)
   const int tp = cfg->t_pad > 0 ? cfg->t_pad : 1;
@@ -829,6 +857,11 @@ int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* o
   return cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, nullptr);
 }
 
+int dab_cycler_setup_diag(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                          const int64_t* system_index, const int64_t* padded_time_idx, const double* obs_error_sd) {
+  return cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, nullptr, obs_error_sd);
+}
+
 int dab_cycler_set_state(dab_handle* h, const double* x, int is_host) {
   DAB_ARG(h, h != nullptr && h->cyc.ready && x != nullptr);
   DAB_CUDA(h, cudaSetDevice(h->device));
@@ -861,10 +894,11 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
   const int ns = c.n_seg[(size_t)cycle] > 0 ? c.n_seg[(size_t)cycle] : 1;
   prof_mark(h, PROF_START);
   DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
+                              c.has_sw ? c.obs_sw.as<double>() : nullptr,
                               c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
                               c.partial.as<double>(), grid, true, h->stream));
   prof_mark(h, PROF_CONTRACT);
-  const double r_inv = r_inv_of(c.cfg.obs_error_sd);
+  const double r_inv = c.has_sw ? 1.0 : r_inv_of(c.cfg.obs_error_sd);
   if (stats_exchange_ready(c)) {
     // reduction fused with the all-gather of the ranks' statistics over peer memory, then the
     // rank-ordered sum (replaces reduce + NCCL all-reduce; see stats_reduce_kernel)
@@ -1167,12 +1201,12 @@ int dab_measure_fp64_peak(dab_handle* h, double* dfma_tflops, double* dmma_tflop
   return 0;
 }
 
-int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
-                            const double* obs_values, const int64_t* system_index,
-                            const int64_t* padded_time_idx, double* out_analysis) {
+static int cycle_host_impl(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                           const double* obs_values, const int64_t* system_index,
+                           const int64_t* padded_time_idx, const double* obs_sd, double* out_analysis) {
   DAB_ARG(h, h != nullptr && cfg != nullptr && x0 != nullptr);
   DAB_ARG(h, cfg->world == 1);
-  int rc = cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, x0);   // uploads x0 too
+  int rc = cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, x0, obs_sd);   // uploads x0 too
   if (rc) return rc;
   // pin the output range if the caller did not, so the per-cycle D2H overlaps the next cycle
   bool registered = false;
@@ -1190,6 +1224,18 @@ int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const do
   if (!rc) rc = dab_sync(h);
   if (registered) cudaHostUnregister(out_analysis);
   return rc;
+}
+
+int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                            const double* obs_values, const int64_t* system_index,
+                            const int64_t* padded_time_idx, double* out_analysis) {
+  return cycle_host_impl(h, cfg, x0, obs_values, system_index, padded_time_idx, nullptr, out_analysis);
+}
+
+int dab_etkf_cycle_host_diag_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                                 const double* obs_values, const int64_t* system_index,
+                                 const int64_t* padded_time_idx, const double* obs_error_sd, double* out_analysis) {
+  return cycle_host_impl(h, cfg, x0, obs_values, system_index, padded_time_idx, obs_error_sd, out_analysis);
 }
 
 }  // extern "C"

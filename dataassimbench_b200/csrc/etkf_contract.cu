@@ -30,15 +30,19 @@ constexpr int YLD = RB + 4;      // smem row stride (doubles): (4*j + r) mod 16 
 // pipelined: the gather of block b+1 (L2/HBM latency) is in flight while the tensor core
 // contracts block b, and the (location, value) pairs of block b+2 are fetched one block earlier
 // still.  A short last block runs only the k-steps it has rows for.
+// `obs_sw` (nullable): 1 / sigma of every row for a diagonal R with unequal entries (0 where sigma = 0: pinv);
+// the centred row and its innovation are scaled by it, so C and g come out weighted by 1 / sigma^2.
 __device__ __forceinline__ void fetch_row(const int* __restrict__ obs_loc, const double* __restrict__ obs_val,
+                                          const double* __restrict__ obs_sw,
                                           const long long* __restrict__ seg, int n_seg, long long r,
-                                          long long r_end, int& loc, double& val) {
-  loc = -1; val = 0.0;
+                                          long long r_end, int& loc, double& val, double& sw) {
+  loc = -1; val = 0.0; sw = 1.0;
   if (r < r_end) {
     int s = 0;
     while (s + 1 < n_seg && seg[3 * (s + 1) + 2] <= r) ++s;
     const long long p = seg[3 * s] + (r - seg[3 * s + 2]);
     loc = obs_loc[p]; val = obs_val[p];
+    if (obs_sw != nullptr) sw = obs_sw[p];
   }
 }
 
@@ -46,6 +50,7 @@ template <int K8>
 __global__ void __launch_bounds__(32 * K8)
 contract_kernel(const double* __restrict__ X, long long ld, int k,
                 const int* __restrict__ obs_loc, const double* __restrict__ obs_val,
+                const double* __restrict__ obs_sw,
                 const long long* __restrict__ seg, int n_seg, long long n_rows,
                 double* __restrict__ partial) {
   constexpr int KP = 8 * K8;
@@ -53,7 +58,7 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
   __shared__ double psum[K8][RB];     // per-warp partial row sums
   __shared__ double dvec[RB];         // innovation y - ybar (0 for padding rows)
   __shared__ int s_loc[2][RB];
-  __shared__ double s_val[2][RB];
+  __shared__ double s_val[2][RB], s_sw[2][RB];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inv_k = 1.0 / (double)k;
@@ -70,11 +75,11 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
   const int n_blocks = (int)((r_end - r_begin + RB - 1) / RB);
 
   // pipeline prologue: rows of block 0 -> shared, rows of block 1 -> registers, gather of block 0
-  int nloc = -1; double nval = 0.0;          // (tid < RB) the row `tid` of the block after next
+  int nloc = -1; double nval = 0.0, nsw = 1.0;   // (tid < RB) the row `tid` of the block after next
   if (tid < RB) {
-    fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + tid, r_end, nloc, nval);
-    s_loc[0][tid] = nloc; s_val[0][tid] = nval;
-    fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + RB + tid, r_end, nloc, nval);
+    fetch_row(obs_loc, obs_val, obs_sw, seg, n_seg, r_begin + tid, r_end, nloc, nval, nsw);
+    s_loc[0][tid] = nloc; s_val[0][tid] = nval; s_sw[0][tid] = nsw;
+    fetch_row(obs_loc, obs_val, obs_sw, seg, n_seg, r_begin + RB + tid, r_end, nloc, nval, nsw);
   }
   __syncthreads();
   // everything above read the observation tables only; the state is the previous kernel's output
@@ -95,18 +100,19 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
 #pragma unroll
     for (int i = 0; i < 8; ++i) ps += v[i];
     psum[warp][lane] = ps;
-    if (tid < RB) { s_loc[cur ^ 1][tid] = nloc; s_val[cur ^ 1][tid] = nval; }   // rows of block b+1
+    if (tid < RB) { s_loc[cur ^ 1][tid] = nloc; s_val[cur ^ 1][tid] = nval; s_sw[cur ^ 1][tid] = nsw; }   // rows of block b+1
     __syncthreads();                                   // also: every warp is done with tile b-1
     double tot = 0.0;
 #pragma unroll
     for (int w = 0; w < K8; ++w) tot += psum[w][lane];
     const double ybar = tot * inv_k;
+    const double sw = s_sw[cur][lane];                 // 1 unless R has unequal diagonal entries (x * 1.0 is exact)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = warp + i * K8;
-      Ys[j * YLD + lane] = (loc >= 0 && j < k) ? v[i] - ybar : 0.0;
+      Ys[j * YLD + lane] = (loc >= 0 && j < k) ? (v[i] - ybar) * sw : 0.0;
     }
-    if (warp == 0) dvec[lane] = (loc >= 0) ? s_val[cur][lane] - ybar : 0.0;
+    if (warp == 0) dvec[lane] = (loc >= 0) ? (s_val[cur][lane] - ybar) * sw : 0.0;
     __syncthreads();
     // ---- put the next gather (block b+1) and the rows of block b+2 in flight
     loc = s_loc[cur ^ 1][lane];
@@ -115,7 +121,7 @@ contract_kernel(const double* __restrict__ X, long long ld, int k,
       const int j = warp + i * K8;
       v[i] = (loc >= 0 && j < k) ? X[(long long)j * ld + loc] : 0.0;
     }
-    if (tid < RB) fetch_row(obs_loc, obs_val, seg, n_seg, r_begin + (long long)(b + 2) * RB + tid, r_end, nloc, nval);
+    if (tid < RB) fetch_row(obs_loc, obs_val, obs_sw, seg, n_seg, r_begin + (long long)(b + 2) * RB + tid, r_end, nloc, nval, nsw);
     // ---- C strip `warp` += Y'^T Y' over the rows of block b, 4 rows per DMMA
     const long long left = r_end - (r_begin + (long long)b * RB);
     const int rows_here = left < RB ? (int)left : RB;
@@ -259,14 +265,14 @@ int contract_grid(long long n_rows, int sms) {
 }
 
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
-                            const double* obs_val, const long long* seg, int n_seg,
+                            const double* obs_val, const double* obs_sw, const long long* seg, int n_seg,
                             long long n_rows, double* partial, int grid, bool chain, cudaStream_t st) {
   const int k8 = contract_k8(k);
   switch (k8) {
-    case 2: return launch_chain(chain, contract_kernel<2>, dim3(grid), dim3(64), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
-    case 4: return launch_chain(chain, contract_kernel<4>, dim3(grid), dim3(128), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
-    case 8: return launch_chain(chain, contract_kernel<8>, dim3(grid), dim3(256), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
-    default: return launch_chain(chain, contract_kernel<16>, dim3(grid), dim3(512), 0, st, X, ld, k, obs_loc, obs_val, seg, n_seg, n_rows, partial);
+    case 2: return launch_chain(chain, contract_kernel<2>, dim3(grid), dim3(64), 0, st, X, ld, k, obs_loc, obs_val, obs_sw, seg, n_seg, n_rows, partial);
+    case 4: return launch_chain(chain, contract_kernel<4>, dim3(grid), dim3(128), 0, st, X, ld, k, obs_loc, obs_val, obs_sw, seg, n_seg, n_rows, partial);
+    case 8: return launch_chain(chain, contract_kernel<8>, dim3(grid), dim3(256), 0, st, X, ld, k, obs_loc, obs_val, obs_sw, seg, n_seg, n_rows, partial);
+    default: return launch_chain(chain, contract_kernel<16>, dim3(grid), dim3(512), 0, st, X, ld, k, obs_loc, obs_val, obs_sw, seg, n_seg, n_rows, partial);
   }
   return cudaGetLastError();
 }
@@ -409,8 +415,9 @@ cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, lon
 // An index of a valid row outside [0, N) is reported through *bad (and contributes nothing) instead of
 // being dereferenced by the contraction.
 __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigned char* __restrict__ mask,
-                                const double* __restrict__ y, long long n_y, long long N,
-                                int* __restrict__ loc, double* __restrict__ val, int* __restrict__ bad) {
+                                const double* __restrict__ y, const double* __restrict__ sd, long long n_y, long long N,
+                                int* __restrict__ loc, double* __restrict__ val, double* __restrict__ sw,
+                                int* __restrict__ bad) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= n_y) return;
   bool ok = mask == nullptr || mask[r] != 0;
@@ -418,12 +425,13 @@ __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigne
   if (ok && (l < 0 || l >= N)) { ok = false; *bad = 1; }
   loc[r] = ok ? (int)l : -1;
   val[r] = ok ? y[r] : 0.0;
+  if (sw != nullptr) { const double s = sd[r]; sw[r] = s == 0.0 ? 0.0 : 1.0 / s; }   // pinv of a zero variance
 }
 
-cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
-                            long long n_y, long long N, int* loc, double* val, int* bad, cudaStream_t st) {
+cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y, const double* sd,
+                            long long n_y, long long N, int* loc, double* val, double* sw, int* bad, cudaStream_t st) {
   if (n_y <= 0) return cudaSuccess;
-  pack_obs_kernel<<<(unsigned)((n_y + 255) / 256), 256, 0, st>>>(idx, mask, y, n_y, N, loc, val, bad);
+  pack_obs_kernel<<<(unsigned)((n_y + 255) / 256), 256, 0, st>>>(idx, mask, y, sd, n_y, N, loc, val, sd ? sw : nullptr, bad);
   return cudaGetLastError();
 }
 

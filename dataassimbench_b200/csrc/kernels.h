@@ -56,7 +56,8 @@ int contract_k8(int k);
 int contract_grid(long long n_rows, int sms);
 size_t contract_partial_doubles(int k, int n_cta);
 cudaError_t contract_launch(const double* X, long long ld, int k, const int* obs_loc,
-                            const double* obs_val, const long long* seg, int n_seg,
+                            const double* obs_val, const double* obs_sw /* nullable: 1 / sigma per row */,
+                            const long long* seg, int n_seg,
                             long long n_rows, double* partial, int grid,
                             bool chain /* obs tables are not the previous kernel's output: PDL allowed */,
                             cudaStream_t st);
@@ -82,7 +83,8 @@ cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, lon
                                   const double* val, long long n_rows, double w, int* bad, int sms,
                                   cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
-                            long long n_y, long long N, int* loc, double* val, int* bad, cudaStream_t st);
+                            const double* sd /* nullable: per-row sigma */, long long n_y, long long N, int* loc,
+                            double* val, double* sw /* 1 / sigma when sd != NULL */, int* bad, cudaStream_t st);
 
 // K4  etkf_eig.cu (Jacobi eigensolver) and etkf_ns.cu (cluster Newton-Schulz, 32 < k <= 128)
 enum { kEigAuto = 0, kEigJacobi = 1, kEigNewtonSchulz = 2 };

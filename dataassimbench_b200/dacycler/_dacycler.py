@@ -78,18 +78,27 @@ class ScaledIdentity:
 
     @staticmethod
     def sd_of(R):
-        """The scalar sd of an R that is sd**2 * I (ScaledIdentity, scalar variance-free dense matrix); raises
-        NotImplementedError for anything else."""
+        """sigma of a DIAGONAL R: a float when R = sd**2 * I (ScaledIdentity, or a dense matrix of that form),
+        a vector of per-observation sigmas when the diagonal entries differ (a 1-D array is taken as the
+        diagonal of variances).  Anything with off-diagonal entries raises NotImplementedError."""
         if isinstance(R, ScaledIdentity):
             return R.sd
         R = np.asarray(R, dtype=np.float64)
-        if R.ndim == 2 and R.shape[0] == R.shape[1]:
+        if R.ndim == 1:
+            d = R
+        elif R.ndim == 2 and R.shape[0] == R.shape[1]:
             d = np.diag(R)
-            if R.shape[0] == 0:
-                return 1.0
-            if np.count_nonzero(R - np.diag(d)) == 0 and np.all(d == d[0]) and d[0] >= 0:
-                return float(np.sqrt(d[0]))
-        raise NotImplementedError('only R = sd**2 * I is accelerated')
+            if np.count_nonzero(R - np.diag(d)) != 0:
+                raise NotImplementedError('only a diagonal R is accelerated')
+        else:
+            raise NotImplementedError('only a diagonal R is accelerated')
+        if d.shape[0] == 0:
+            return 1.0
+        if np.any(d < 0):
+            raise NotImplementedError('only a diagonal R with non-negative variances is accelerated')
+        if np.all(d == d[0]):
+            return float(np.sqrt(d[0]))
+        return np.sqrt(d)
 
 
 class DACycler:

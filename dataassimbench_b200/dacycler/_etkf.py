@@ -100,10 +100,14 @@ class ETKF(DACycler):
             if op.indices.shape[0] != n_y:
                 raise ValueError('H has %d rows for %d observations' % (op.indices.shape[0], n_y))
             sd = ScaledIdentity.sd_of(R)
+            if np.ndim(sd) != 0:                               # diagonal R with unequal entries
+                if sd.shape[0] != n_y:
+                    raise ValueError('R has %d rows for %d observations' % (sd.shape[0], n_y))
+                sd = torch.from_numpy(np.ascontiguousarray(sd)).cuda()
             yd = torch.from_numpy(y).cuda()
             idxd = torch.from_numpy(op.indices).cuda()
             md = None if op.mask is None else torch.from_numpy(op.mask.astype(np.uint8)).cuda()
-        handle().etkf_analysis(Xd, Xa, yd, idxd, md, sd, float(rho), N, k, n_y,
+        handle().etkf_analysis(Xd, Xa, yd, idxd, md, sd if torch.is_tensor(sd) else float(sd), float(rho), N, k, n_y,
                                torch.cuda.current_stream().cuda_stream)
         return np.ascontiguousarray(Xa.cpu().numpy().T)
 
@@ -138,9 +142,9 @@ class ETKF(DACycler):
         if self.h is not None and self.H is None:
             # dabench/dacycler/_dacycler.py:103-104
             raise ValueError('Only linear obs operators (H) are supported right now.')
-        if self.H is not None or self.R is not None or self.B is not None:
-            raise NotImplementedError('user-supplied H / R / B matrices are outside the accelerated path '
-                                      '(default index-gather H and obs_error_sd**2 * I only)')
+        if self.H is not None or self.B is not None:
+            raise NotImplementedError('user-supplied H / B matrices are outside the accelerated path '
+                                      '(default index-gather H only)')
         gen = self._lorenz96_generator()
         if gen is None:
             raise NotImplementedError('the accelerated ETKF.cycle() needs model_obj to be a Model wrapping a '
@@ -150,8 +154,20 @@ class ETKF(DACycler):
         if self._data_vars != ['x'] or self._observed_vars != ['x']:
             raise NotImplementedError("single-variable states named 'x' only (as the reference's ETKF, "
                                       "dabench/dacycler/_etkf.py:213)")
-        if np.ndim(self.obs_error_sd) != 0:
-            raise NotImplementedError('scalar obs_error_sd only')
+        # R: the default obs_error_sd**2 * I, a vector obs_error_sd (one sigma per observation slot: a diagonal R),
+        # or a user R that is diagonal (dabench/dacycler/_etkf.py:142 takes pinv(R): for a diagonal R that is
+        # 1 / sd**2 entry by entry, 0 where sd == 0)
+        sd = ScaledIdentity.sd_of(self.R) if self.R is not None else self.obs_error_sd
+        sd_slots = None
+        if np.ndim(sd) != 0:
+            sd = np.asarray(sd, dtype=np.float64)
+            n_t = len(w['obs_times'])
+            n_o = int(np.size(_xr.var_array(obs_vector, 'x')) // max(n_t, 1))
+            if sd.shape not in ((n_o,), (n_t, n_o)):
+                raise ValueError('a vector obs_error_sd / diagonal R needs one entry per observation slot: '
+                                 'shape (%d,) or (%d, %d), got %s' % (n_o, n_t, n_o, sd.shape))
+            sd_slots = np.ascontiguousarray(np.broadcast_to(sd, (n_t, n_o)))
+            sd = 1.0
         X0 = np.ascontiguousarray(_xr.var_array(input_state, 'x'), dtype=np.float64)
         if X0.ndim != 2:
             raise ValueError("input_state['x'] must have dims ('ensemble', <state>)")
@@ -166,11 +182,11 @@ class ETKF(DACycler):
         cfg = _native.CycleConfig(
             system_dim=n_sys, ensemble_dim=n_ens, n_steps=self.steps_per_window - 1,
             model_dt=float(gen.delta_t), forcing=float(gen.forcing_term),
-            rho=float(self.multiplicative_inflation), obs_error_sd=float(self.obs_error_sd),
+            rho=float(self.multiplicative_inflation), obs_error_sd=float(sd),
             n_obs_times=vals.shape[0], n_obs=vals.shape[1], stationary=int(w['stationary']),
             n_cycles=int(n_cycles), t_pad=w['padded'].shape[1], rank=0, world=1)
         state_dim = [d for d in _xr.var_dims(input_state, 'x') if d != 'ensemble']
-        return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx,
+        return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx, sd_slots=sd_slots,
                     padded=np.ascontiguousarray(w['padded']), state_dim=state_dim[0] if state_dim else 'index')
 
     # ------------------------------------------------------------------ grid sharding (one rank per GPU)
@@ -207,7 +223,7 @@ class ETKF(DACycler):
         k, N, n_cycles = cfg.ensemble_dim, cfg.system_dim, cfg.n_cycles
         w = dict(N=N, k=k, S=cfg.n_steps, dt=cfg.model_dt, rho=cfg.rho, sd=cfg.obs_error_sd, X0=p['X0'],
                  vals=p['vals'], sysidx=p['sysidx'], padded=p['padded'], forcing=cfg.forcing,
-                 stationary=cfg.stationary)
+                 stationary=cfg.stationary, sd_slots=p['sd_slots'])
         cyc = ShardedCycler(handle(), w, n_cycles, rank, world)
         n_loc = N // world
         out = np.empty((n_cycles, k, N))
@@ -248,13 +264,13 @@ class ETKF(DACycler):
         out = torch.empty((n_cycles, k, N), dtype=torch.float64, pin_memory=True)
         dim = p['state_dim']
         if not return_forecast:
-            H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out)
+            H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out, p['sd_slots'])
             return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy())})
         # The trajectories are S*k*N*8 bytes per cycle (671 MB at N=65536, k=64): they are produced in
         # blocks of cycles that fit `traj_block_bytes` of device memory and streamed to the host block
         # by block, instead of materialising n_cycles of them in HBM (the reference builds the whole
         # array inside its scan, dabench/dacycler/_dacycler.py:276-290).
-        H.cycler_setup(cfg, p['vals'], p['sysidx'], p['padded'])
+        H.cycler_setup(cfg, p['vals'], p['sysidx'], p['padded'], p['sd_slots'])
         H.cycler_set_state(p['X0'], True)
         full = np.empty((n_cycles, k, max(S, 1), N))
         per_cycle = max(S, 1) * k * N * 8

@@ -73,7 +73,7 @@ class ShardedCycler:
         self.k = w["k"]
         self.n_cycles = n_cycles
         cfg = self.config(n_cycles)
-        self.H.cycler_setup(cfg, w["vals"], w["sysidx"], w["padded"])
+        self.H.cycler_setup(cfg, w["vals"], w["sysidx"], w["padded"], w.get("sd_slots"))
         lo, hi = self.plan.slab(rank)
         self.x0_dev = torch.from_numpy(np.ascontiguousarray(w["X0"][:, lo:hi])).cuda()
         self.stream = torch.cuda.ExternalStream(self.H.cycler_stream())

@@ -149,6 +149,12 @@ DAB_API int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, in
 DAB_API int dab_etkf_analysis_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
                           const int64_t* idx, const uint8_t* mask, double obs_error_sd, double rho,
                           int64_t N, int k, int64_t n_y, void* stream);
+/* The same for a diagonal R with unequal entries (a user R = diag(sd_r^2), dabench/dacycler/_etkf.py:142:
+ * pinv of a diagonal matrix): obs_error_sd [n_y] dev, one sigma per observation; sigma == 0 gives that row
+ * weight 0 (pinv).  The rows are scaled by 1 / sigma inside the contraction (K3). */
+DAB_API int dab_etkf_analysis_diag_f64(dab_handle* h, const double* Xb, double* Xa, const double* y,
+                               const int64_t* idx, const uint8_t* mask, const double* obs_error_sd, double rho,
+                               int64_t N, int k, int64_t n_y, void* stream);
 
 /* ---- the cycler: DACycler.cycle() for the ETKF -------------------------------------------
  * Replaces DACycler.cycle / _cycle_and_forecast (dabench/dacycler/_dacycler.py:110-141,186-290):
@@ -175,6 +181,10 @@ typedef struct dab_cycle_config {
  * (`all_filtered_padded`, dabench/dacycler/_dacycler.py:259). */
 DAB_API int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
                      const int64_t* system_index, const int64_t* padded_time_idx);
+/* The same with a diagonal R given slot by slot: obs_error_sd [n_obs_times][n_obs] host (cfg->obs_error_sd is
+ * ignored; sigma == 0 gives the slot weight 0). */
+DAB_API int dab_cycler_setup_diag(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
+                          const int64_t* system_index, const int64_t* padded_time_idx, const double* obs_error_sd);
 /* local slab [k][N/world]; is_host selects the copy direction kind */
 DAB_API int dab_cycler_set_state(dab_handle* h, const double* x, int is_host);
 DAB_API int dab_cycler_get_state(dab_handle* h, double* x, int is_host);
@@ -234,6 +244,10 @@ DAB_API int dab_measure_fp64_peak(dab_handle* h, double* dfma_tflops, double* dm
 DAB_API int dab_etkf_cycle_host_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
                             const double* obs_values, const int64_t* system_index,
                             const int64_t* padded_time_idx, double* out_analysis);
+/* ... with a diagonal R given slot by slot (see dab_cycler_setup_diag). */
+DAB_API int dab_etkf_cycle_host_diag_f64(dab_handle* h, const dab_cycle_config* cfg, const double* x0,
+                                 const double* obs_values, const int64_t* system_index,
+                                 const int64_t* padded_time_idx, const double* obs_error_sd, double* out_analysis);
 
 /* Batched small problems (BASELINE.json configs[1]: 4096 x (N=40, k=20), inflation sweep): `batch`
  * independent DACycler.cycle() experiments, one CTA each, the whole experiment in ONE launch.

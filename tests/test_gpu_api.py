@@ -353,8 +353,11 @@ def test_hook_compute_analysis_matches_the_literal_formula():
     Xe = dc._compute_analysis(Xb, np.zeros(0), None, None, np.zeros((0, 0)), rho=1.1)
     ref_e = o_etkf.analysis_literal(Xb, np.zeros(0), np.zeros((0, N)), np.zeros((0, 0)), 1.1)
     assert rel_err(Xe, ref_e) < 1e-12
+    # a diagonal R with unequal entries is accelerated; one with off-diagonal entries is refused, not approximated
+    Rd = np.diag(np.linspace(1, 2, len(idx)))
+    assert rel_err(dc._compute_analysis(Xb, y, H, None, Rd, 1.0), o_etkf.analysis_literal(Xb, y, H.dense(), Rd, 1.0)) < 1e-10
     with pytest.raises(NotImplementedError):
-        dc._compute_analysis(Xb, y, H, None, np.diag(np.linspace(1, 2, len(idx))), 1.0)
+        dc._compute_analysis(Xb, y, H, None, Rd + 0.01, 1.0)
 
 
 def test_hook_cycle_obsop_applies_masks_and_defaults():
@@ -417,3 +420,51 @@ def test_cycle_with_zero_error_sd_ignores_the_observations_like_pinv_of_zero_R()
     ref = o_etkf.analysis_literal(Xb, obs['x'].values[0], o_etkf.calc_default_H(20, N, obs["system_index"].values[0, 0]),
                                   np.zeros((20, 20)), 1.21)
     assert rel_err(out['x'].values[0].T, ref) < 1e-10
+
+
+def test_diagonal_R_with_unequal_entries_single_analysis_and_cycle():
+    """A user R = diag(sd_r^2) (the reference takes pinv(R), dabench/dacycler/_etkf.py:142) through
+    `_compute_analysis` against the LITERAL formula, and a vector obs_error_sd through `cycle()` against the
+    oracle cycling with the same per-observation weights; sigma = 0 rows carry no weight (pinv)."""
+    rng = np.random.default_rng(8)
+    N, k, n_y = 60, 12, 25
+    X = 2.0 + rng.standard_normal((N, k))
+    idx = rng.choice(N, n_y, replace=False)
+    y = rng.standard_normal(n_y) + 2.0
+    sd = 0.5 + rng.random(n_y)
+    sd[3] = 0.0
+    R = np.diag(sd ** 2)
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.01))
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k, model_obj=model)
+    Hm = o_etkf.calc_default_H(n_y, N, idx)
+    ref = o_etkf.analysis_literal(X, y, Hm, R, 1.1)
+    got = dc._compute_analysis(Xb=X, Y=y, H=Hm, h=None, R=R, rho=1.1)
+    assert rel_err(got, ref) < 1e-10
+    # through cycle(): 5 cycles, stationary network, one sigma per observation
+    N, k, n_cycles, S = 256, 10, 5, 20
+    gen = dab.data.Lorenz96(system_dim=N, delta_t=0.01, store_as_jax=True)
+    nature = gen.generate(n_steps=n_cycles * S + 1)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(0, n_cycles * S + 1, S)],
+                                random_location_count=80, error_sd=1.0, random_seed=3, stationary_observers=True,
+                                store_as_jax=True).observe()
+    sdv = 0.5 + rng.random(80)
+    sdv[7] = 0.0
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.01, store_as_jax=True))
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k, model_obj=model)
+    init = nature.isel(time=0)
+    X0 = init['x'].values + rng.standard_normal((k, N))
+    init = init.assign(x=(['ensemble', 'index'], X0))
+    out = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=n_cycles, obs_error_sd=sdv,
+                   analysis_window=0.2, analysis_time_in_window=0.0)
+    w = np.where(sdv == 0.0, 0.0, 1.0 / np.where(sdv == 0.0, 1.0, sdv) ** 2)
+    Xc = X0.copy()
+    loc = obs['system_index'].values[0][0]
+    for c in range(n_cycles):
+        Xa = o_etkf.analysis_sparse(Xc, obs['x'].values[c], loc, w, 1.0)
+        assert rel_err(out['x'].values[c], Xa) < 1e-9, c
+        Xc = o_l96.rk4_forecast(Xa, S, 0.01)
+    # the same R handed over as a matrix on the cycler
+    dc2 = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k, model_obj=model, R=np.diag(sdv ** 2))
+    out2 = dc2.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=n_cycles, obs_error_sd=1.0,
+                     analysis_window=0.2, analysis_time_in_window=0.0)
+    assert np.array_equal(out2['x'].values, out['x'].values)

@@ -334,8 +334,13 @@ def test_compact_default_operators_match_the_reference_dense_ones():
     assert np.array_equal(R.dense(), o_etkf.calc_default_R(4, 1.5))
     assert ScaledIdentity.sd_of(R) == 1.5 and ScaledIdentity.sd_of(R.dense()) == 1.5
     assert ScaledIdentity.sd_of(np.zeros((3, 3))) == 0.0
+    # a diagonal R with unequal entries: one sigma per observation; off-diagonal entries are not accelerated
+    assert np.array_equal(ScaledIdentity.sd_of(np.diag([1.0, 4.0])), [1.0, 2.0])
+    assert np.array_equal(ScaledIdentity.sd_of(np.array([9.0, 4.0])), [3.0, 2.0])
     with pytest.raises(NotImplementedError):
-        ScaledIdentity.sd_of(np.diag([1.0, 2.0]))
+        ScaledIdentity.sd_of(np.array([[1.0, 0.1], [0.1, 1.0]]))
+    with pytest.raises(NotImplementedError):
+        ScaledIdentity.sd_of(np.diag([1.0, -1.0]))
     assert len(dc._calc_default_R(np.zeros(0), 1.0)) == 0          # the empty-R branch tests len(R)
 
 
