@@ -60,6 +60,7 @@ _SIGNATURES = {
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
     "dab_observe_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, C.c_int, _P, _I64, _P, _P, _P]),
     "dab_var3d_analysis_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, C.c_double, _P]),
+    "dab_var3d_analysis_b_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, C.c_double, _P, C.c_double, C.c_int, _P, _P]),
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
     "dab_etkf_transform_matrix_f64": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
@@ -183,6 +184,13 @@ class Handle:
         """3D-Var analysis for default H / R / B: xa = (xb + H^T y / sd^2) / (1 + diag(H^T H) / sd^2)."""
         self._check(self._lib.dab_var3d_analysis_f64(self._h, _ptr(xb), _ptr(xa), N, _ptr(loc), _ptr(val),
                                                      n_rows, sd, _ptr(stream)))
+
+    def var3d_analysis_b(self, xb, xa, N, loc, val, n_rows, sd, B, tol=1e-5, maxiter=1000, stream=None):
+        """3D-Var analysis with a dense user B [N][N] (device): conjugate gradients; returns the iteration count."""
+        iters = C.c_int(0)
+        self._check(self._lib.dab_var3d_analysis_b_f64(self._h, _ptr(xb), _ptr(xa), N, _ptr(loc), _ptr(val), n_rows,
+                                                       sd, _ptr(B), tol, int(maxiter), C.byref(iters), _ptr(stream)))
+        return iters.value
 
     def etkf_stats(self, X, y, idx, mask, sd, N, k, n_y, stats, stream=None):
         self._check(self._lib.dab_etkf_stats_f64(self._h, _ptr(X), _ptr(y), _ptr(idx), _ptr(mask),

@@ -132,6 +132,7 @@ struct dab_handle {
   long launches = 0;
   DevBuf s_loc, s_val, s_sw, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
+  DevBuf s_cg;                                           // conjugate-gradient vectors of dab_var3d_analysis_b_f64
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
   V5Work v5;                                             // pipelined-chain forecast kernel: job tables
@@ -357,7 +358,7 @@ int dab_destroy(dab_handle* h) {
   cudaDeviceSynchronize();
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_sw.release(); h->s_seg.release();
-  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release();
+  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release(); h->s_cg.release();
   h->v2.release();
   h->v5.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
@@ -499,6 +500,30 @@ int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, int64_t 
   DAB_CUDA(h, cudaMemcpyAsync(&bad, h->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   DAB_CUDA(h, cudaStreamSynchronize(st));
   if (bad) return fail(h, -1, "dab_var3d_analysis_f64: an observation location is out of range");
+  return 0;
+}
+
+int dab_var3d_analysis_b_f64(dab_handle* h, const double* xb, double* xa, int64_t N, const int64_t* loc,
+                             const double* val, int64_t n_rows, double obs_error_sd, const double* B,
+                             double tol, int maxiter, int* iters_out, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  DAB_ARG(h, N >= 1 && n_rows >= 0 && obs_error_sd > 0.0 && tol >= 0.0 && maxiter >= 0);
+  DAB_ARG(h, xb != nullptr && xa != nullptr && xb != xa && B != nullptr);
+  DAB_ARG(h, n_rows == 0 || (loc != nullptr && val != nullptr));
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DAB_CUDA(h, h->s_flag.reserve(sizeof(int)));
+  DAB_CUDA(h, h->s_cg.reserve(sizeof(double) * var3d_cg_workspace_doubles(N)));
+  DAB_CUDA(h, cudaMemsetAsync(h->s_flag.p, 0, sizeof(int), st));
+  int iters = 0;
+  DAB_CUDA(h, var3d_cg_launch(xb, xa, N, reinterpret_cast<const long long*>(loc), val, n_rows,
+                              1.0 / (obs_error_sd * obs_error_sd), B, tol, maxiter, h->s_cg.as<double>(),
+                              h->s_flag.as<int>(), h->sms, &iters, &h->launches, st));
+  if (iters_out) *iters_out = iters;
+  int bad = 0;
+  DAB_CUDA(h, cudaMemcpyAsync(&bad, h->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DAB_CUDA(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, -1, "dab_var3d_analysis_b_f64: an observation location is out of range");
   return 0;
 }
 

@@ -428,6 +428,22 @@ __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigne
   if (sw != nullptr) { const double s = sd[r]; sw[r] = s == 0.0 ? 0.0 : 1.0 / s; }   // pinv of a zero variance
 }
 
+// the first two stages alone: num = xb + sum_r w y_r, den = 1 + sum_r w (var3d_cg.cu takes its diagonal from them)
+cudaError_t var3d_scatter_only_launch(const double* xb, double* num, double* den, long long n, const long long* loc,
+                                      const double* val, long long n_rows, double w, int* bad, int sms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long cap = (long long)sms * 8;
+  long long g = (n + 255) / 256;
+  if (g > cap) g = cap;
+  var3d_init_kernel<<<(unsigned)g, 256, 0, st>>>(xb, n, num, den);
+  if (n_rows > 0) {
+    long long gr = (n_rows + 255) / 256;
+    if (gr > cap) gr = cap;
+    var3d_scatter_kernel<<<(unsigned)gr, 256, 0, st>>>(loc, val, n_rows, n, w, num, den, bad);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y, const double* sd,
                             long long n_y, long long N, int* loc, double* val, double* sw, int* bad, cudaStream_t st) {
   if (n_y <= 0) return cudaSuccess;

@@ -82,6 +82,13 @@ cudaError_t observe_launch(const double* state, long long N, long long n_state_t
 cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, long long n, const long long* loc,
                                   const double* val, long long n_rows, double w, int* bad, int sms,
                                   cudaStream_t st);
+cudaError_t var3d_scatter_only_launch(const double* xb, double* num, double* den, long long n, const long long* loc,
+                                      const double* val, long long n_rows, double w, int* bad, int sms, cudaStream_t st);
+// var3d_cg.cu: the same analysis with a dense user B, conjugate gradients on I + B diag(w)
+size_t var3d_cg_workspace_doubles(long long n);
+cudaError_t var3d_cg_launch(const double* xb, double* xa, long long n, const long long* loc, const double* val,
+                            long long n_rows, double w_obs, const double* B, double tol, int maxiter, double* ws,
+                            int* bad, int sms, int* iters_out, long* launches, cudaStream_t st);
 cudaError_t pack_obs_launch(const long long* idx, const unsigned char* mask, const double* y,
                             const double* sd /* nullable: per-row sigma */, long long n_y, long long N, int* loc,
                             double* val, double* sw /* 1 / sigma when sd != NULL */, int* bad, cudaStream_t st);

@@ -2,11 +2,13 @@
 
 Mirrors `dabench.dacycler.Var3D` (dabench/dacycler/_var3d.py:18-112) under `DACycler.cycle`
 (dabench/dacycler/_dacycler.py:186-290).  Accelerated contract: native `Lorenz96Model`, default H
-(index gather), default R (`obs_error_sd**2 * I`) and default B (identity,
-`DACycler._calc_default_B`).  With those the system `I + B H^T R^-1 H` the reference solves by
-conjugate gradients (tol 1e-5) is diagonal, and `dab_var3d_analysis_f64` solves it exactly; the
-forecast is the Lorenz-96 RK4 kernel with one member.  User-supplied H / R / B or another model
-raise `NotImplementedError` -- there is no CPU fallback.
+(index gather), default R (`obs_error_sd**2 * I`).  With the default B (identity,
+`DACycler._calc_default_B`) the system `I + B H^T R^-1 H` the reference solves by conjugate
+gradients (tol 1e-5) is diagonal, and `dab_var3d_analysis_f64` solves it exactly; with a
+user-supplied dense B, `dab_var3d_analysis_b_f64` runs the reference's conjugate gradients on the
+device (same start, same stopping rule; one pass over B per iteration).  The forecast is the
+Lorenz-96 RK4 kernel with one member.  User-supplied H / R or another model raise
+`NotImplementedError` -- there is no CPU fallback.
 """
 import numpy as np
 
@@ -32,9 +34,9 @@ class Var3D(DACycler):
         if self.h is not None and self.H is None:
             # dabench/dacycler/_dacycler.py:103-104
             raise ValueError('Only linear obs operators (H) are supported right now.')
-        if self.H is not None or self.R is not None or self.B is not None:
-            raise NotImplementedError('user-supplied H / R / B matrices are outside the accelerated path '
-                                      '(default index-gather H, obs_error_sd**2 * I and identity B only)')
+        if self.H is not None or self.R is not None:
+            raise NotImplementedError('user-supplied H / R matrices are outside the accelerated path '
+                                      '(default index-gather H and obs_error_sd**2 * I only)')
         gen = self._lorenz96_generator()
         if gen is None:
             raise NotImplementedError('the accelerated Var3D.cycle() needs model_obj to be a Model wrapping a '
@@ -52,7 +54,12 @@ class Var3D(DACycler):
         vals = np.ascontiguousarray(vals.reshape(len(w['obs_times']), -1))
         sysidx = np.asarray(_xr.var_array(obs_vector, 'system_index'))
         sysidx = np.ascontiguousarray(sysidx.reshape(vals.shape), dtype=np.int64)
-        return dict(x0=x0, vals=vals, sysidx=sysidx, padded=np.asarray(w['padded'], dtype=np.int64),
+        B = None
+        if self.B is not None:
+            B = np.ascontiguousarray(self.B, dtype=np.float64)
+            if B.shape != (x0.size, x0.size):
+                raise ValueError('B must be (system_dim, system_dim) = (%d, %d), got %s' % (x0.size, x0.size, B.shape))
+        return dict(x0=x0, vals=vals, sysidx=sysidx, B=B, padded=np.asarray(w['padded'], dtype=np.int64),
                     stationary=w['stationary'], n_steps=self.steps_per_window - 1,
                     model_dt=float(gen.delta_t), forcing=float(gen.forcing_term), sd=float(self.obs_error_sd),
                     state_dim=_xr.var_dims(input_state, 'x')[0])
@@ -89,11 +96,18 @@ class Var3D(DACycler):
         xa = torch.empty_like(xb)
         traj = torch.empty((max(S, 1), 1, N), dtype=torch.float64, device=dev)
         full = np.empty((n_cycles, max(S, 1), N))
+        Bd = None if p['B'] is None else torch.from_numpy(p['B']).to(dev)
+        self.cg_iterations = []                                  # per cycle, when B is user-supplied
         for c in range(n_cycles):
             loc, val = self._rows_of_cycle(p, c)
             d_loc = torch.from_numpy(loc).to(dev) if len(loc) else None
             d_val = torch.from_numpy(val).to(dev) if len(loc) else None
-            H.var3d_analysis(xb, xa, N, d_loc, d_val, len(loc), p['sd'], stream)
+            if Bd is None:
+                H.var3d_analysis(xb, xa, N, d_loc, d_val, len(loc), p['sd'], stream)
+            else:
+                # dabench/dacycler/_var3d.py:105-106: cg(A, b1, x0=xb, tol=1e-05, maxiter=1000)
+                self.cg_iterations.append(H.var3d_analysis_b(xb, xa, N, d_loc, d_val, len(loc), p['sd'], Bd,
+                                                             1e-5, 1000, stream))
             full[c, 0] = xa.cpu().numpy()
             if S > 0:
                 # members are rows: one member of N points; the next background is the last step

@@ -121,6 +121,14 @@ DAB_API int dab_observe_f64(dab_handle* h, const double* state, int64_t N, int64
  * Synchronises the stream; returns -1 if a location is out of range. */
 DAB_API int dab_var3d_analysis_f64(dab_handle* h, const double* xb, double* xa, int64_t N, const int64_t* loc,
                            const double* val, int64_t n_rows, double obs_error_sd, void* stream);
+/* The same analysis with a user-supplied background covariance B [N][N] (dev, row-major), the general case of
+ * dabench/dacycler/_var3d.py:84-110: conjugate gradients on (I + B H^T R^-1 H) xa = xb + B H^T R^-1 y from x0 = xb,
+ * stopping like jax.scipy.sparse.linalg.cg (||r||^2 <= tol^2 ||b||^2 or maxiter; the reference passes tol = 1e-5,
+ * maxiter = 1000).  H^T R^-1 H is applied as a diagonal; one pass over B per iteration.  iters_out (nullable, host)
+ * receives the iteration count.  Synchronises the stream. */
+DAB_API int dab_var3d_analysis_b_f64(dab_handle* h, const double* xb, double* xa, int64_t N, const int64_t* loc,
+                             const double* val, int64_t n_rows, double obs_error_sd, const double* B,
+                             double tol, int maxiter, int* iters_out, void* stream);
 
 /* ---- K3+K4: statistics and transform matrix (exposed for tests and for rank-parallel use) -
  * stats = [C (k*k, row-major) | g (k)] with C = Yb'^T Rinv Yb', g = Yb'^T Rinv (y - ybar)

@@ -468,3 +468,57 @@ def test_diagonal_R_with_unequal_entries_single_analysis_and_cycle():
     out2 = dc2.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=n_cycles, obs_error_sd=1.0,
                      analysis_window=0.2, analysis_time_in_window=0.0)
     assert np.array_equal(out2['x'].values, out['x'].values)
+
+
+def test_var3d_with_a_user_B_runs_the_reference_conjugate_gradients_on_the_device():
+    """Var3D with a dense user B (dabench/dacycler/_var3d.py:84-106): `dab_var3d_analysis_b_f64` against the
+    oracle's literal restatement (dense H, R, B; jax-style cg from x0 = xb, tol 1e-5) -- same iteration count, same
+    iterate -- and a short cycle through the API."""
+    rng = np.random.default_rng(21)
+    N, n_y, sd = 96, 40, 0.8
+    xb = 3.0 + rng.standard_normal(N)
+    idx = rng.choice(N, n_y, replace=True).astype(np.int64)       # some points observed twice
+    y = xb[idx] + rng.standard_normal(n_y)
+    d = np.abs(np.arange(N)[:, None] - np.arange(N)[None, :])
+    d = np.minimum(d, N - d)
+    B = 0.6 * np.exp(-(d / 3.0) ** 2) + 0.4 * np.identity(N)       # SPD, periodic correlations
+    Hm = o_etkf.calc_default_H(n_y, N, idx)
+    A = np.identity(N) + (B @ Hm.T) @ np.linalg.inv(o_etkf.calc_default_R(n_y, sd)) @ Hm
+    b1 = xb + (B @ Hm.T) @ np.linalg.inv(o_etkf.calc_default_R(n_y, sd)) @ y
+    ref, ref_it = o_var3d.cg(A, b1, xb, tol=1e-5, maxiter=1000)
+    assert np.allclose(o_var3d.analysis_literal(xb, y, Hm, o_etkf.calc_default_R(n_y, sd), B), ref, rtol=0, atol=1e-13)
+    from dataassimbench_b200._runtime import handle
+    xa = torch.empty(N, dtype=torch.float64, device='cuda')
+    it = handle().var3d_analysis_b(torch.from_numpy(xb).cuda(), xa, N, torch.from_numpy(idx).cuda(),
+                                   torch.from_numpy(y).cuda(), n_y, sd, torch.from_numpy(B).cuda(), 1e-5, 1000,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert it == ref_it and it > 1
+    assert rel_err(xa.cpu().numpy(), ref) < 1e-11
+    # tighter tolerance converges to the direct solution
+    it2 = handle().var3d_analysis_b(torch.from_numpy(xb).cuda(), xa, N, torch.from_numpy(idx).cuda(),
+                                    torch.from_numpy(y).cuda(), n_y, sd, torch.from_numpy(B).cuda(), 1e-13, 1000,
+                                    torch.cuda.current_stream().cuda_stream)
+    assert it2 >= it and rel_err(xa.cpu().numpy(), np.linalg.solve(A, b1)) < 1e-10
+    # through Var3D.cycle(): first analysis = the literal oracle's
+    Nn = 40
+    gen = dab.data.Lorenz96(system_dim=Nn, delta_t=0.01, store_as_jax=True)
+    nature = gen.generate(n_steps=61)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(0, 61, 20)], random_location_count=20,
+                                error_sd=0.5, random_seed=4, stationary_observers=True, store_as_jax=True).observe()
+    dd = np.abs(np.arange(Nn)[:, None] - np.arange(Nn)[None, :])
+    dd = np.minimum(dd, Nn - dd)
+    Bn = 0.5 * np.exp(-(dd / 2.0) ** 2) + 0.5 * np.identity(Nn)
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=Nn, delta_t=0.01, store_as_jax=True))
+    dc = dab.dacycler.Var3D(system_dim=Nn, delta_t=0.01, model_obj=model, B=Bn)
+    init = nature.isel(time=0)
+    x0 = init['x'].values + 0.5 * rng.standard_normal(Nn)
+    init = init.assign(x=(['index'], x0))
+    # (3 cycles x 0.2 trips the reference's float-arange quirk that _windows.py preserves: 2 cycles)
+    out = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=2, obs_error_sd=0.5,
+                   analysis_window=0.2, analysis_time_in_window=0.0)
+    loc = obs['system_index'].values[0][0]
+    Hn = o_etkf.calc_default_H(20, Nn, loc)
+    first = o_var3d.analysis_literal(x0, obs['x'].values[0], Hn, o_etkf.calc_default_R(20, 0.5), Bn)
+    assert rel_err(out['x'].values[0], first) < 1e-11
+    assert len(dc.cg_iterations) == 2 and all(i > 0 for i in dc.cg_iterations)
+    assert np.all(np.isfinite(out['x'].values))

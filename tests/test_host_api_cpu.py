@@ -304,7 +304,10 @@ def test_var3d_rejects_what_it_does_not_accelerate():
     model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=6))
     nature, obs, dc, init, times = _var3d_reference_recipe()
     with pytest.raises(NotImplementedError):
-        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, B=np.eye(6)).cycle(init, 0.0, obs, 2)
+        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, R=np.eye(3)).cycle(init, 0.0, obs, 2)
+    with pytest.raises(ValueError, match='B must be'):          # a user B is accelerated (CG), a misshapen one is not
+        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, B=np.eye(5))._plan(init, 0.0, obs, 2)
+    assert dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, B=2 * np.eye(6))._plan(init, 0.0, obs, 2)['B'][0, 0] == 2.0
     with pytest.raises(ValueError):
         dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, h=lambda x: x).cycle(init, 0.0, obs, 2)
     with pytest.raises(NotImplementedError):
