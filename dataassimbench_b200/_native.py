@@ -66,6 +66,7 @@ _SIGNATURES = {
     "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
     "dab_etkf_analysis_diag_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P]),
     "dab_cycler_setup": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P]),
+    "dab_cycler_setup_dev": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P]),
     "dab_cycler_setup_diag": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P]),
     "dab_etkf_cycle_host_diag_f64": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P, _P, _P, _P]),
     "dab_cycler_set_state": (C.c_int, [_P, _P, C.c_int]),
@@ -221,7 +222,12 @@ class Handle:
 
     def cycler_setup(self, cfg, obs_values, system_index, padded_time_idx, obs_error_sd=None):
         """`obs_error_sd`: None (cfg.obs_error_sd) or a host array [n_obs_times][n_obs] (diagonal R per slot)."""
-        if obs_error_sd is None:
+        if getattr(obs_values, "is_cuda", False):
+            if obs_error_sd is not None:
+                raise NotImplementedError("device-resident observations with a per-slot obs_error_sd")
+            self._check(self._lib.dab_cycler_setup_dev(self._h, C.byref(cfg), _ptr(obs_values),
+                                                       _ptr(system_index), _ptr(padded_time_idx)))
+        elif obs_error_sd is None:
             self._check(self._lib.dab_cycler_setup(self._h, C.byref(cfg), _ptr(obs_values),
                                                    _ptr(system_index), _ptr(padded_time_idx)))
         else:

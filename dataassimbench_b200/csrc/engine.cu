@@ -133,6 +133,7 @@ struct dab_handle {
   DevBuf s_loc, s_val, s_sw, s_seg, s_partial, s_stats, s_T;   // scratch of the standalone entry points
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf s_cg;                                           // conjugate-gradient vectors of dab_var3d_analysis_b_f64
+  DevBuf s_src, s_off;                                   // dab_cycler_setup_dev: row permutations and offsets
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
   V5Work v5;                                             // pipelined-chain forecast kernel: job tables
@@ -358,7 +359,7 @@ int dab_destroy(dab_handle* h) {
   cudaDeviceSynchronize();
   cycler_free(h);
   h->s_loc.release(); h->s_val.release(); h->s_sw.release(); h->s_seg.release();
-  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release(); h->s_cg.release();
+  h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release(); h->s_cg.release(); h->s_src.release(); h->s_off.release();
   h->v2.release();
   h->v5.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
@@ -637,9 +638,13 @@ int dab_etkf_analysis_diag_f64(dab_handle* h, const double* Xb, double* Xa, cons
 // `x0_host` (nullable): initial ensemble in host memory; its upload is enqueued as soon as the
 // buffers exist, so that it overlaps the host-side preparation of the observation tables.
 // `obs_sd` (nullable, host, [n_obs_times][n_obs]): per-slot sigma of a diagonal R; cfg->obs_error_sd is then ignored.
+// `obs_values_dev` (nullable, device, [n_obs_times][n_obs]): the observed values already in HBM (an Observer that
+// sampled a device trajectory): `obs_values` is then not read, the location-ordered value table is filled by a
+// kernel from the permutation the index rows give, and NaN slots of a moving network are masked on the device.
 static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
                              const int64_t* system_index, const int64_t* padded_time_idx,
-                             const double* x0_host, const double* obs_sd = nullptr) {
+                             const double* x0_host, const double* obs_sd = nullptr,
+                             const double* obs_values_dev = nullptr) {
   DAB_ARG(h, h != nullptr && cfg != nullptr);
   DAB_ARG(h, cfg->system_dim >= 4 && cfg->system_dim < (1ll << 31));
   DAB_ARG(h, cfg->ensemble_dim >= 2 && cfg->ensemble_dim <= DAB_MAX_ENSEMBLE);
@@ -649,7 +654,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   DAB_ARG(h, cfg->world >= 1 && cfg->world <= DAB_MAX_RANKS && cfg->rank >= 0 && cfg->rank < cfg->world);
   DAB_ARG(h, cfg->system_dim % cfg->world == 0);
   DAB_ARG(h, cfg->n_obs_times >= 0 && cfg->n_obs >= 0);
-  DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 || (obs_values != nullptr && system_index != nullptr));
+  DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 ||
+                 ((obs_values != nullptr || obs_values_dev != nullptr) && system_index != nullptr));
   DAB_ARG(h, cfg->n_cycles * cfg->t_pad == 0 || padded_time_idx != nullptr);
   DAB_ARG(h, cfg->world == 1 || cfg->n_steps <= l96_max_steps_per_launch());
   DAB_CUDA(h, cudaSetDevice(h->device));
@@ -707,16 +713,19 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   // from the previous time's (a stationary network builds it once); per time the values are then
   // one indexed copy.
   std::vector<int> src, lrow, tmp_o, tmp_l, count;
+  std::vector<int> src_all;                 // device-resident values: the permutations, back to back ...
+  std::vector<long long> src_base;          // ... and where the one of time t starts
+  const bool dev_vals = obs_values_dev != nullptr;
   for (long long t = 0; t < nt; ++t) {
     const int64_t* irow = system_index + t * no;
-    const double* vrow = obs_values + t * no;
+    const double* vrow = dev_vals ? nullptr : obs_values + t * no;
     const bool reuse = t > 0 && cfg->stationary &&
                        memcmp(irow, irow - no, sizeof(int64_t) * (size_t)no) == 0;
     if (!reuse) {
       tmp_o.clear(); tmp_l.clear();
       bool sorted = true;
       for (long long o = 0; o < no; ++o) {
-        if (!cfg->stationary && std::isnan(vrow[o])) continue;   // loc mask, _dacycler.py:266-268
+        if (!dev_vals && !cfg->stationary && std::isnan(vrow[o])) continue;   // loc mask, _dacycler.py:266-268
         const long long gi = irow[o];
         if (gi < 0 || gi >= cfg->system_dim)
           return fail(h, -1, "system_index[%lld][%lld] = %lld out of range", t, o, gi);
@@ -745,7 +754,12 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     const size_t nr = src.size(), base = loc.size();
     loc.resize(base + nr); val.resize(base + nr);
     memcpy(loc.data() + base, lrow.data(), sizeof(int) * nr);
-    for (size_t i = 0; i < nr; ++i) val[base + i] = vrow[src[i]];
+    if (dev_vals) {
+      if (!reuse) { src_base.push_back((long long)src_all.size()); src_all.insert(src_all.end(), src.begin(), src.end()); }
+      else src_base.push_back(src_base.back());
+    } else {
+      for (size_t i = 0; i < nr; ++i) val[base + i] = vrow[src[i]];
+    }
     if (obs_sd != nullptr) {
       swv.resize(base + nr);
       const double* srow = obs_sd + t * no;
@@ -757,7 +771,22 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   DAB_CUDA(h, c.obs_val.reserve(sizeof(double) * (val.size() + 1)));
   if (!loc.empty()) {
     DAB_CUDA(h, cudaMemcpyAsync(c.obs_loc.p, loc.data(), sizeof(int) * loc.size(), cudaMemcpyHostToDevice, h->stream));
-    DAB_CUDA(h, cudaMemcpyAsync(c.obs_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!dev_vals) {
+      DAB_CUDA(h, cudaMemcpyAsync(c.obs_val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
+    } else {
+      // the value table straight from the device-resident observations (and the NaN mask of a moving network)
+      DAB_CUDA(h, h->s_src.reserve(sizeof(int) * (src_all.size() + 1)));
+      DAB_CUDA(h, h->s_off.reserve(sizeof(long long) * 2 * ((size_t)nt + 1)));
+      std::vector<long long> offs(2 * ((size_t)nt + 1), 0);
+      for (long long t = 0; t <= nt; ++t) offs[(size_t)t] = c.csr_off[(size_t)t];
+      for (long long t = 0; t < nt; ++t) offs[(size_t)nt + 1 + (size_t)t] = src_base[(size_t)t];
+      DAB_CUDA(h, cudaMemcpyAsync(h->s_src.p, src_all.data(), sizeof(int) * src_all.size(), cudaMemcpyHostToDevice, h->stream));
+      DAB_CUDA(h, cudaMemcpyAsync(h->s_off.p, offs.data(), sizeof(long long) * offs.size(), cudaMemcpyHostToDevice, h->stream));
+      DAB_CUDA(h, pack_rows_launch(obs_values_dev, no, nt, h->s_src.as<int>(), h->s_off.as<long long>(),
+                                   h->s_off.as<long long>() + nt + 1, cfg->stationary ? 0 : 1, c.obs_loc.as<int>(),
+                                   c.obs_val.as<double>(), h->stream));
+      DAB_CUDA(h, cudaStreamSynchronize(h->stream));           // offs / src_all go out of scope
+    }
     if (c.has_sw) {
       DAB_CUDA(h, c.obs_sw.reserve(sizeof(double) * (swv.size() + 1)));
       DAB_CUDA(h, cudaMemcpyAsync(c.obs_sw.p, swv.data(), sizeof(double) * swv.size(), cudaMemcpyHostToDevice, h->stream));
@@ -880,6 +909,13 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
 int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
                      const int64_t* system_index, const int64_t* padded_time_idx) {
   return cycler_setup_impl(h, cfg, obs_values, system_index, padded_time_idx, nullptr);
+}
+
+int dab_cycler_setup_dev(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values_dev,
+                         const int64_t* system_index, const int64_t* padded_time_idx) {
+  DAB_ARG(h, h != nullptr && cfg != nullptr);
+  DAB_ARG(h, cfg->n_obs_times * cfg->n_obs == 0 || obs_values_dev != nullptr);
+  return cycler_setup_impl(h, cfg, nullptr, system_index, padded_time_idx, nullptr, nullptr, obs_values_dev);
 }
 
 int dab_cycler_setup_diag(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,

@@ -428,6 +428,37 @@ __global__ void pack_obs_kernel(const long long* __restrict__ idx, const unsigne
   if (sw != nullptr) { const double s = sd[r]; sw[r] = s == 0.0 ? 0.0 : 1.0 / s; }   // pinv of a zero variance
 }
 
+// Observation values that are already in HBM -> the cycler's location-ordered table: row i of time t is
+// values[t][src[src_base[t] + i]]; with `mask_nan` (moving observers: NaN = padded slot, the location mask of
+// dabench/dacycler/_dacycler.py:262-268) such a row gets location -1 and contributes nothing.
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const double* __restrict__ values, long long n_obs, const int* __restrict__ src,
+                 const long long* __restrict__ off, const long long* __restrict__ src_base, int mask_nan,
+                 int* __restrict__ loc, double* __restrict__ val) {
+  const long long t = blockIdx.y;
+  const long long n = off[t + 1] - off[t];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = values[t * n_obs + src[src_base[t] + i]];
+    const bool drop = mask_nan && v != v;
+    val[off[t] + i] = drop ? 0.0 : v;
+    if (drop) loc[off[t] + i] = -1;
+  }
+}
+
+cudaError_t pack_rows_launch(const double* values, long long n_obs, long long n_times, const int* src,
+                             const long long* off, const long long* src_base, int mask_nan, int* loc, double* val,
+                             cudaStream_t st) {
+  if (n_obs <= 0 || n_times <= 0) return cudaSuccess;
+  long long gx = (n_obs + 255) / 256;
+  if (gx > 64) gx = 64;
+  for (long long t0 = 0; t0 < n_times; t0 += 65535) {            // gridDim.y limit
+    const long long nt = n_times - t0 < 65535 ? n_times - t0 : 65535;
+    pack_rows_kernel<<<dim3((unsigned)gx, (unsigned)nt), 256, 0, st>>>(values + t0 * n_obs, n_obs, src, off + t0,
+                                                                      src_base + t0, mask_nan, loc, val);
+  }
+  return cudaGetLastError();
+}
+
 // the first two stages alone: num = xb + sum_r w y_r, den = 1 + sum_r w (var3d_cg.cu takes its diagonal from them)
 cudaError_t var3d_scatter_only_launch(const double* xb, double* num, double* den, long long n, const long long* loc,
                                       const double* val, long long n_rows, double w, int* bad, int sms, cudaStream_t st) {

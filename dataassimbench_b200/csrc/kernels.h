@@ -82,6 +82,9 @@ cudaError_t observe_launch(const double* state, long long N, long long n_state_t
 cudaError_t var3d_analysis_launch(const double* xb, double* xa, double* den, long long n, const long long* loc,
                                   const double* val, long long n_rows, double w, int* bad, int sms,
                                   cudaStream_t st);
+cudaError_t pack_rows_launch(const double* values, long long n_obs, long long n_times, const int* src,
+                             const long long* off, const long long* src_base, int mask_nan, int* loc, double* val,
+                             cudaStream_t st);
 cudaError_t var3d_scatter_only_launch(const double* xb, double* num, double* den, long long n, const long long* loc,
                                       const double* val, long long n_rows, double w, int* bad, int sms, cudaStream_t st);
 // var3d_cg.cu: the same analysis with a dense user B, conjugate gradients on I + B diag(w)

@@ -162,7 +162,8 @@ class ETKF(DACycler):
         if np.ndim(sd) != 0:
             sd = np.asarray(sd, dtype=np.float64)
             n_t = len(w['obs_times'])
-            n_o = int(np.size(_xr.var_array(obs_vector, 'x')) // max(n_t, 1))
+            raw_x = _xr.var_data(obs_vector, 'x')
+            n_o = int(np.prod(tuple(raw_x.shape))) // max(n_t, 1)
             if sd.shape not in ((n_o,), (n_t, n_o)):
                 raise ValueError('a vector obs_error_sd / diagonal R needs one entry per observation slot: '
                                  'shape (%d,) or (%d, %d), got %s' % (n_o, n_t, n_o, sd.shape))
@@ -175,8 +176,13 @@ class ETKF(DACycler):
         # dabench/dacycler/_etkf.py:196-199
         assert n_ens == self.ensemble_dim, (
             'cycle:: model_forecast must have dimension {}x{}').format(self.ensemble_dim, self.system_dim)
-        vals = np.asarray(_xr.var_array(obs_vector, 'x'), dtype=np.float64)
-        vals = np.ascontiguousarray(vals.reshape(len(w['obs_times']), -1))
+        raw = _xr.var_data(obs_vector, 'x')
+        if getattr(raw, 'is_cuda', False):
+            # observations sampled on the device (Observer(..., keep_on_device=True)): they stay there
+            vals = raw.reshape(len(w['obs_times']), -1).contiguous()
+        else:
+            vals = np.asarray(_xr.var_array(obs_vector, 'x'), dtype=np.float64)
+            vals = np.ascontiguousarray(vals.reshape(len(w['obs_times']), -1))
         sysidx = np.asarray(_xr.var_array(obs_vector, 'system_index'))
         sysidx = np.ascontiguousarray(sysidx.reshape(vals.shape), dtype=np.int64)
         cfg = _native.CycleConfig(
@@ -264,7 +270,13 @@ class ETKF(DACycler):
         out = torch.empty((n_cycles, k, N), dtype=torch.float64, pin_memory=True)
         dim = p['state_dim']
         if not return_forecast:
-            H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out, p['sd_slots'])
+            if getattr(p['vals'], 'is_cuda', False):
+                H.cycler_setup(cfg, p['vals'], p['sysidx'], p['padded'], p['sd_slots'])     # dab_cycler_setup_dev
+                H.cycler_set_state(p['X0'], True)
+                H.cycler_run(0, n_cycles, out)
+                H.sync()
+            else:
+                H.etkf_cycle_host(cfg, p['X0'], p['vals'], p['sysidx'], p['padded'], out, p['sd_slots'])
             return _xr.new_dataset({'x': (('cycle', 'ensemble', dim), out.numpy())})
         # The trajectories are S*k*N*8 bytes per cycle (671 MB at N=65536, k=64): they are produced in
         # blocks of cycles that fit `traj_block_bytes` of device memory and streamed to the host block

@@ -18,8 +18,11 @@ class Observer:
     def __init__(self, state_vec, random_time_density=1., random_location_density=1.,
                  random_time_count=None, random_location_count=None, times=None, locations=None,
                  stationary_observers=True, error_bias=0., error_sd=0., error_positive_only=False,
-                 random_seed=99, store_as_jax=False):
+                 random_seed=99, store_as_jax=False, keep_on_device=False):
         self.state_vec = state_vec
+        # not a reference argument: with a trajectory in HBM, leave the sampled values there too (the 'x' variable
+        # of the result is then a CUDA tensor, which ETKF.cycle() packs into its tables without a host round trip)
+        self.keep_on_device = keep_on_device
         self.random_time_density = random_time_density
         self.random_location_density = random_location_density
         self.random_time_count = random_time_count
@@ -132,7 +135,7 @@ class Observer:
             stream = torch.cuda.current_stream()
             H.observe(traj, traj.shape[1], traj.shape[0], d_pos, n_t, d_loc, stationary, d_cnt, n_obs,
                       d_err, d_val, stream=stream.cuda_stream)
-        return d_val.cpu().numpy()
+        return d_val if self.keep_on_device else d_val.cpu().numpy()
 
 
 def _is_cuda_tensor(a):

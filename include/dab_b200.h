@@ -189,6 +189,12 @@ typedef struct dab_cycle_config {
  * (`all_filtered_padded`, dabench/dacycler/_dacycler.py:259). */
 DAB_API int dab_cycler_setup(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,
                      const int64_t* system_index, const int64_t* padded_time_idx);
+/* The same with the observed values ALREADY IN HBM (obs_values_dev [n_obs_times][n_obs] dev, e.g. written by
+ * dab_observe_f64): they are packed into the cycler's location-ordered table by a kernel and never visit the host;
+ * the index table stays a host array (the Observer draws it on the host).  NaN slots of a moving network are masked
+ * on the device. */
+DAB_API int dab_cycler_setup_dev(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values_dev,
+                         const int64_t* system_index, const int64_t* padded_time_idx);
 /* The same with a diagonal R given slot by slot: obs_error_sd [n_obs_times][n_obs] host (cfg->obs_error_sd is
  * ignored; sigma == 0 gives the slot weight 0). */
 DAB_API int dab_cycler_setup_diag(dab_handle* h, const dab_cycle_config* cfg, const double* obs_values,

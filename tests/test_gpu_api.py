@@ -522,3 +522,38 @@ def test_var3d_with_a_user_B_runs_the_reference_conjugate_gradients_on_the_devic
     assert rel_err(out['x'].values[0], first) < 1e-11
     assert len(dc.cg_iterations) == 2 and all(i > 0 for i in dc.cg_iterations)
     assert np.all(np.isfinite(out['x'].values))
+
+
+@pytest.mark.parametrize("stationary", [True, False])
+def test_device_resident_observations_go_straight_into_the_cycler(stationary):
+    """Observer(keep_on_device=True) on a trajectory in HBM leaves the observed values there and ETKF.cycle() packs
+    them into its location-ordered tables with a kernel (dab_cycler_setup_dev): identical analyses to the same
+    observations taken through the host, for a stationary and for a moving (ragged, NaN-padded) network."""
+    N, k, n_cycles, S = 512, 12, 5, 20
+    gen = dab.data.Lorenz96(system_dim=N, delta_t=0.01, store_as_jax=True)
+    nature = gen.generate(n_steps=n_cycles * S + 1)
+    traj = np.ascontiguousarray(nature['x'].values)
+    coords = {'time': nature['time'].values, 'index': np.arange(N)}
+    kw = dict(times=nature['time'].values[np.arange(0, n_cycles * S + 1, S)], random_location_density=0.3, error_sd=0.8,
+              random_seed=12, stationary_observers=stationary)
+    obs_host = dab.observer.Observer(_xr.new_dataset({'x': (('time', 'index'), traj)}, coords=coords), **kw).observe()
+    obs_dev = dab.observer.Observer(_xr.new_dataset({'x': (('time', 'index'), torch.from_numpy(traj).cuda())},
+                                                    coords=coords), keep_on_device=True, **kw).observe()
+    xv = _xr.var_data(obs_dev, 'x')
+    assert xv.is_cuda and np.array_equal(xv.cpu().numpy(), obs_host['x'].values, equal_nan=True)
+    if not stationary:
+        assert np.isnan(obs_host['x'].values).any()
+    model = dab.model.Lorenz96Model(model_obj=dab.data.Lorenz96(system_dim=N, delta_t=0.01, store_as_jax=True))
+    dc = dab.dacycler.ETKF(system_dim=N, delta_t=0.01, ensemble_dim=k, model_obj=model, multiplicative_inflation=1.05)
+    rng = np.random.default_rng(2)
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), traj[0] + rng.standard_normal((k, N)))}, coords={'time': 0.0})
+    ckw = dict(input_state=init, start_time=0.0, n_cycles=n_cycles, obs_error_sd=0.8, analysis_window=0.2,
+               analysis_time_in_window=0.0)
+    a = dc.cycle(obs_vector=obs_host, **ckw)['x'].values
+    b = dc.cycle(obs_vector=obs_dev, **ckw)['x'].values
+    assert np.all(np.isfinite(a))
+    if stationary:
+        assert np.array_equal(a, b)
+    else:
+        # the host route drops NaN slots, the device route keeps them as weightless rows: same sums, other grouping
+        assert rel_err(b, a) < 1e-10
