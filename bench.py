@@ -562,7 +562,8 @@ def run_e2e_api(w, K):
                           attrs={"error_sd": w["sd"], "stationary_observers": True})
     kw = dict(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=BLOCK, obs_error_sd=w["sd"],
               analysis_window=S * dt, analysis_time_in_window=0.0)
-    out = dc.cycle(**kw)                                            # warm-up
+    out = dc.cycle(**kw)                                            # warm-up: two calls, so that torch's caching host
+    out = dc.cycle(**kw)                                            # allocator holds both result blocks the loop alternates between
     reps = max(1, min(K, 100) // BLOCK)
     t0 = time.perf_counter()
     for _ in range(reps):
