@@ -352,13 +352,15 @@ int l96_v4_slots(int sms) {
 // hist_t = A / P - 1).  The first tile of a chain and the first tile of every member it enters are fresh: first
 // useful point `pos`, window from pos - 8 S, useful [pos, g0 + A); the others continue: useful [g0, g0 + A).
 // `v4_walk` emits the jobs for one value of m (or just counts the chains when `table` is null).
-static int v4_walk(long long n, int k, int S, int m, std::vector<int>* table) {
+// chain c holds `len(c)` tiles; the table is padded to `stride` jobs per chain
+template <typename LenFn>
+static int v4_walk(long long n, int k, int S, LenFn len, int stride, std::vector<int>* table) {
   const int A = ((V4_W - 4 * S) / V4_P) * V4_P;
-  int chains = 0, in_chain = m;          // in_chain == m: the next tile opens a chain
+  int chains = 0, in_chain = 0, cur_len = 0;          // in_chain == cur_len: the next tile opens a chain
   static const bool nochain = getenv("DAB_L96_V4_NOCHAIN") != nullptr;   // experiment: every tile fresh
   auto pad = [&]() {
     if (table)
-      while ((long long)(table->size() / 4) < (long long)chains * m) {
+      while ((long long)(table->size() / 4) < (long long)chains * stride) {
         table->push_back(-1); table->push_back(0); table->push_back(0); table->push_back(0);
       }
   };
@@ -366,7 +368,7 @@ static int v4_walk(long long n, int k, int S, int m, std::vector<int>* table) {
     long long pos = 0;
     bool fresh = true;
     while (pos < n) {
-      if (in_chain == m) { pad(); ++chains; in_chain = 0; fresh = true; }
+      if (in_chain == cur_len) { pad(); cur_len = len(chains); ++chains; in_chain = 0; fresh = true; }
       const long long g0 = fresh ? pos - 8 * S : pos;
       const long long q = g0 + A < n ? g0 + A : n;
       if (table) {
@@ -387,14 +389,28 @@ static int v4_walk(long long n, int k, int S, int m, std::vector<int>* table) {
 bool l96_v4_plan(long long n, int k, int n_steps, int slots, L96V4Plan* out) {
   if (n_steps < 1 || n_steps > V4_MAX_STEPS || 12 * n_steps + 16 > V4_W || slots < 1) return false;
   const int A = ((V4_W - 4 * n_steps) / V4_P) * V4_P;
+  out->table.clear();
+  out->hist_t = A / V4_P - 1;
+  // experiment: DAB_V4_CLASS_M="a,b,c" gives the chains of the three launch-order classes (blockIdx / 148: the
+  // oldest CTA of an SM is favoured by the warp schedulers) a, b and c tiles
+  if (const char* ev = getenv("DAB_V4_CLASS_M")) {
+    int M[3] = {0, 0, 0};
+    if (sscanf(ev, "%d,%d,%d", &M[0], &M[1], &M[2]) == 3 && M[0] > 0 && M[1] > 0 && M[2] > 0) {
+      const int per = slots / 3;
+      const int stride = M[0] > M[1] ? (M[0] > M[2] ? M[0] : M[2]) : (M[1] > M[2] ? M[1] : M[2]);
+      auto len = [&](int c) { return M[c / per < 3 ? c / per : 2]; };
+      out->grid = v4_walk(n, k, n_steps, len, stride, &out->table);
+      out->jobs_per_cta = stride;
+      return out->grid <= slots;
+    }
+  }
   long long m = ceil_div_ll(n * k, (long long)slots * A);
   if (m < 1) m = 1;
-  while (m < (1 << 20) && v4_walk(n, k, n_steps, (int)m, nullptr) > slots) ++m;
+  auto fixed = [&](int) { return (int)m; };
+  while (m < (1 << 20) && v4_walk(n, k, n_steps, fixed, (int)m, nullptr) > slots) ++m;
   if (m >= (1 << 20)) return false;
-  out->table.clear();
-  out->grid = v4_walk(n, k, n_steps, (int)m, &out->table);
+  out->grid = v4_walk(n, k, n_steps, fixed, (int)m, &out->table);
   out->jobs_per_cta = (int)m;
-  out->hist_t = A / V4_P - 1;
   return true;
 }
 

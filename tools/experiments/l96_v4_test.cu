@@ -165,6 +165,7 @@ int main(int argc, char** argv) {
   g_slots = l96_v4_slots(148);
   printf("resident slots: %d\n", g_slots);
   double w = 0;
+  if (getenv("DAB_V4_SKIP_CHECK")) goto timing;
   w = fmax(w, check(1024, 4, 20, true, 1, g_slots, true));
   w = fmax(w, check(1024, 16, 20, false, 1, g_slots, true));
   w = fmax(w, check(600, 3, 7, true, 1, g_slots, true));
@@ -182,6 +183,7 @@ int main(int argc, char** argv) {
   w = fmax(w, check(1 << 20, 2, 20, true, 1, 16, true));
   printf("v4 worst %.3e %s\n", w, w < 1e-11 ? "OK" : "FAIL");
   if (argc > 1) return 0;
+timing:
   timeit(65536, 64, 20, g_slots);
   timeit(65536, 64, 20, 296);
   timeit(32768, 64, 20, g_slots);      // C3 on 2 ranks
