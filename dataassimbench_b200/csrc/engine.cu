@@ -68,15 +68,15 @@ struct V2Work {
   void release() { scr[0].release(); scr[1].release(); flags.release(); counter.release(); epoch = 0; ctr_base = 0; }
 };
 
-// job tables of the pipelined-chain forecast kernel (l96_forecast_v5.cu), one per shape, built on first use
-struct V5Work {
-  struct Entry { long long n; int k, steps, grid, rounds, hist_t; DevBuf jobs; };
+// tile and chain tables of the chained forecast kernel (l96_forecast_v6.cu), one per shape, built on first use
+struct V6Work {
+  struct Entry { long long n; int k, steps, grid, tile_stride, chain_stride, hist_t; DevBuf tiles, chains; };
   std::vector<Entry*> plans;
   Entry* find(long long n, int k, int steps) const {
     for (Entry* e : plans) if (e->n == n && e->k == k && e->steps == steps) return e;
     return nullptr;
   }
-  void release() { for (Entry* e : plans) { e->jobs.release(); delete e; } plans.clear(); }
+  void release() { for (Entry* e : plans) { e->tiles.release(); e->chains.release(); delete e; } plans.clear(); }
 };
 
 struct Cycler {
@@ -136,7 +136,7 @@ struct dab_handle {
   DevBuf s_src, s_off;                                   // dab_cycler_setup_dev: row permutations and offsets
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
-  V5Work v5;                                             // pipelined-chain forecast kernel: job tables
+  V6Work v6;                                             // chained forecast kernel: tile and chain tables
   int eig_method = kEigAuto;
   unsigned long long xchg_timeout_ns = 10000000000ull;   // statistics exchange: give up on a lost peer (DAB_XCHG_TIMEOUT_S, 0 = never)
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
@@ -237,27 +237,29 @@ static cudaError_t forecast_v3(dab_handle* h, const double* in, double* out, lon
                        out_ld, periodic, in_base, in_lo, in_hi, h->sms, h->stream);
 }
 
-// one launch of the pipelined-chain forecast kernel; the job table of a shape is planned and uploaded on first use
-static cudaError_t forecast_v5(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
+// one launch of the chained forecast kernel; the tables of a shape are planned and uploaded on first use
+static cudaError_t forecast_v6(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
                                double dt, double F, long long in_ld, long long out_ld, bool periodic,
                                long long in_base, long long in_lo, long long in_hi, cudaStream_t st) {
-  V5Work::Entry* e = h->v5.find(n, k, steps);
+  V6Work::Entry* e = h->v6.find(n, k, steps);
   if (e == nullptr) {
-    L96V5Plan plan;
-    if (!l96_v5_plan(n, k, steps, h->sms, &plan)) return cudaErrorInvalidValue;
-    e = new V5Work::Entry();
+    L96V6Plan plan;
+    if (!l96_v6_plan(n, k, steps, h->sms, &plan)) return cudaErrorInvalidValue;
+    e = new V6Work::Entry();
     e->n = n; e->k = k; e->steps = steps;
-    e->grid = plan.grid; e->rounds = plan.rounds; e->hist_t = plan.hist_t;
-    cudaError_t ce = e->jobs.reserve(plan.table.size() * sizeof(int));
+    e->grid = plan.grid; e->tile_stride = plan.tile_stride; e->chain_stride = plan.chain_stride; e->hist_t = plan.hist_t;
+    cudaError_t ce = e->tiles.reserve(plan.tiles.size() * sizeof(int));
+    if (ce == cudaSuccess) ce = e->chains.reserve(plan.chains.size() * sizeof(int));
     // ordered on the launching stream, then waited for: a plain cudaMemcpy from pageable memory may return before
     // its DMA has landed, and `st` (non-blocking) is not ordered after the default stream
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->jobs.p, plan.table.data(), plan.table.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->tiles.p, plan.tiles.data(), plan.tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->chains.p, plan.chains.data(), plan.chains.size() * sizeof(int), cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    if (ce != cudaSuccess) { e->jobs.release(); delete e; return ce; }
-    h->v5.plans.push_back(e);
+    if (ce != cudaSuccess) { e->tiles.release(); e->chains.release(); delete e; return ce; }
+    h->v6.plans.push_back(e);
   }
-  return l96_v5_launch(in, out, e->jobs.as<int>(), e->grid, e->rounds, e->hist_t, n, steps, dt, F, in_ld, out_ld,
-                       periodic, in_base, in_lo, in_hi, st);
+  return l96_v6_launch(in, out, e->tiles.as<int>(), e->chains.as<int>(), e->grid, e->tile_stride, e->chain_stride, e->hist_t,
+                       n, steps, dt, F, in_ld, out_ld, periodic, in_base, in_lo, in_hi, st);
 }
 
 // K1 over one window of `steps` <= first_steps steps: extended-layout analysis `in_ext` -> `dst`
@@ -269,13 +271,13 @@ static cudaError_t forecast_v5(dab_handle* h, const double* in, double* out, lon
 static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, double* dst, double* traj,
                                 long long traj_stride, int steps, int T, int chunks, int* n_launches) {
   const int k = c.cfg.ensemble_dim;
-  if (T >= kL96V5Code && l96_v5_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
-    cudaError_t e = forecast_v5(h, in_ext, dst, c.n_loc, k, steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false,
+  if (T >= kL96V6Code && l96_v6_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
+    cudaError_t e = forecast_v6(h, in_ext, dst, c.n_loc, k, steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false,
                                 c.halo_l, -8ll * steps, c.n_loc + 4ll * steps, h->stream);
     if (e == cudaSuccess && n_launches) ++*n_launches;
     return e;
   }
-  if (T >= kL96V5Code) T = 0;
+  if (T >= kL96V6Code) T = 0;
   if (T >= kL96V3Code && l96_v3_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
     const int chunk_steps = T - kL96V3Code;
     cudaError_t e = h->v2.reserve(c.n_loc, k, c.first_steps, chunk_steps < steps);
@@ -361,7 +363,7 @@ int dab_destroy(dab_handle* h) {
   h->s_loc.release(); h->s_val.release(); h->s_sw.release(); h->s_seg.release();
   h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release(); h->s_cg.release(); h->s_src.release(); h->s_off.release();
   h->v2.release();
-  h->v5.release();
+  h->v6.release();
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
   h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -845,7 +847,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     DAB_CUDA(h, cudaEventCreate(&e0));
     DAB_CUDA(h, cudaEventCreate(&e1));
     const int n_cand = 20;
-    const int cand[n_cand] = {kL96V5Code, kL96V3Code + 32, kL96V3Code + 10, 128, 192, 256, 320, 384, 512,
+    const int cand[n_cand] = {kL96V6Code, kL96V3Code + 32, kL96V3Code + 10, 128, 192, 256, 320, 384, 512,
                               l96_shape_code(16, 128), l96_shape_code(16, 160), l96_shape_code(16, 192),
                               l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
                               l96_shape_code(17, 160), l96_shape_code(17, 192),
@@ -861,8 +863,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
       if (chunks > 1 && c.first_steps < 2 * chunks) continue;
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
-        if (cand[ci] >= kL96V5Code) {
-          if (chunks > 1 || !l96_v5_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
+        if (cand[ci] >= kL96V6Code) {
+          if (chunks > 1 || !l96_v6_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
         } else if (cand[ci] >= kL96V3Code) {
           if (chunks > 1 || !l96_v3_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
         } else {
@@ -895,10 +897,10 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     if (v >= 1 && v <= 32) c.l96_T = kL96V3Code + v;
     else if (v == 0 && c.l96_T >= kL96V3Code) c.l96_T = 0;
   }
-  if (const char* ev = getenv("DAB_L96_V5")) {              // force (1) or forbid (0) the pipelined-chain kernel
+  if (const char* ev = getenv("DAB_L96_V6")) {              // force (1) or forbid (0) the chained kernel
     const int v = atoi(ev);
-    if (v == 1) c.l96_T = kL96V5Code;
-    else if (v == 0 && c.l96_T >= kL96V5Code) c.l96_T = 0;
+    if (v == 1) c.l96_T = kL96V6Code;
+    else if (v == 0 && c.l96_T >= kL96V6Code) c.l96_T = 0;
   }
   if (const char* ev = getenv("DAB_L96_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) c.l96_chunks = v; }
   h->launches = 0;

@@ -165,17 +165,17 @@ def run_window_through_cycler(H, X, S, forced=None, monkeypatch=None, dt=0.01):
 
 
 @pytest.mark.parametrize("N,k,S", [(40000, 8, 20), (65536, 16, 20), (30000, 12, 7), (9000, 64, 32), (262144, 6, 20)])
-def test_forecast_pipelined_chain_kernel_is_bit_identical(H, N, k, S, monkeypatch):
-    """The pipelined-chain kernel (l96_forecast_v5.cu: tiles take their left boundary from the previous tile's
+def test_forecast_chained_kernel_is_bit_identical(H, N, k, S, monkeypatch):
+    """The chained kernel (l96_forecast_v6.cu: tiles take their left boundary from the previous tile's
     history instead of recomputing a halo) against the first design, through the cycler: identical bits, and
     the oracle tolerance on a few members."""
     X, _ = make_ensemble(N, k, seed=N + S, spinup=50)
     X = X + 0.0
     # all-masked window: the analysis is Xb T with T = U + sqrt(rho)(I - U) = I at rho = 1 up to rounding, so
     # compare the two forecast kernels on the analysis the cycler itself produced (same T, same bits)
-    base, code0 = run_window_through_cycler(H, X, S, ("DAB_L96_V5", "0"), monkeypatch)
-    out, code5 = run_window_through_cycler(H, X, S, ("DAB_L96_V5", "1"), monkeypatch)
-    assert code5 == 50000 and code0 != 50000
+    base, code0 = run_window_through_cycler(H, X, S, ("DAB_L96_V6", "0"), monkeypatch)
+    out, code5 = run_window_through_cycler(H, X, S, ("DAB_L96_V6", "1"), monkeypatch)
+    assert code5 == 60000 and code0 != 60000
     assert np.array_equal(out, base)
     ref = o_l96.rk4_forecast(X[:2], S, 0.01)
     assert rel_err(out[:2], ref) < 1e-9          # the identity transform adds its own rounding

@@ -1,3 +1,8 @@
+// EXPERIMENT (not part of the product build since l96_forecast_v6.cu replaced it; tools/experiments/l96_v5_test.cu runs it):
+// correct and bit-identical to the first design; C4 6.85 ms against 6.71 ms for the design that lets the groups run
+// freely (the wavefront costs nothing by itself, but the select between the two sources of the left boundary and the
+// second, predicated history store cost every warp issue slots: profiles/forecast_probes_r02.md section 6).
+//
 // K1, fifth design -- pipelined chains: one persistent CTA per SM, three 4-warp groups that sweep ONE chain of tiles
 // together, each tile taking its left boundary from the tile before it through shared memory.
 //
@@ -36,10 +41,15 @@
 #include <cstdlib>
 #include <vector>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "../../dataassimbench_b200/csrc/common.cuh"
+#include "../../dataassimbench_b200/csrc/kernels.h"
 
 namespace dab {
+
+struct L96V5Plan {
+  int grid = 0, rounds = 0, hist_t = 0;
+  std::vector<int> table;          // [grid][3 rounds][4]: {2 member + continuing, g0, p, q}; p == q: dummy tile
+};
 
 constexpr int V5_P = 16;                          // points per thread
 constexpr int V5_TG = 128;                        // threads per group

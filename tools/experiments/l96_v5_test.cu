@@ -1,15 +1,15 @@
 // Standalone check + timing of the pipelined-chain forecast kernel (csrc/l96_forecast_v5.cu) against a plain CPU RK4
 // (textbook form), periodic and extended-layout inputs, and against the first design (csrc/l96_forecast.cu) bit for
 // bit.  Build:
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I dataassimbench_b200/csrc -o build/l96_v5_test tools/l96_v5_test.cu
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I dataassimbench_b200/csrc -o build/l96_v5_test tools/experiments/l96_v5_test.cu
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <algorithm>
-#include "../dataassimbench_b200/csrc/l96_forecast_v5.cu"
-#include "../dataassimbench_b200/csrc/l96_forecast.cu"
+#include "l96_forecast_v5.cu"
+#include "../../dataassimbench_b200/csrc/l96_forecast.cu"
 namespace dab { bool pdl_enabled() { return false; } }
 using namespace dab;
 

@@ -1,5 +1,5 @@
 """One cycler set-up and two cycles at a given shape (for ncu: the forecast kernel the cycler really launches).
-N / K / NOBS / S from the environment; DAB_L96_V5 / DAB_L96_V3 / DAB_L96_T force a forecast kernel."""
+N / K / NOBS / S from the environment; DAB_L96_V6 / DAB_L96_V3 / DAB_L96_T force a forecast kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
