@@ -70,10 +70,10 @@ struct V2Work {
 
 // tile and chain tables of the chained forecast kernel (l96_forecast_v6.cu), one per shape, built on first use
 struct V6Work {
-  struct Entry { long long n; int k, steps, grid, tile_stride, chain_stride, hist_t; DevBuf tiles, chains; };
+  struct Entry { long long n; int k, steps, variant, grid, tile_stride, chain_stride, hist_t; DevBuf tiles, chains; };
   std::vector<Entry*> plans;
-  Entry* find(long long n, int k, int steps) const {
-    for (Entry* e : plans) if (e->n == n && e->k == k && e->steps == steps) return e;
+  Entry* find(long long n, int k, int steps, int variant = 0) const {
+    for (Entry* e : plans) if (e->n == n && e->k == k && e->steps == steps && e->variant == variant) return e;
     return nullptr;
   }
   void release() { for (Entry* e : plans) { e->tiles.release(); e->chains.release(); delete e; } plans.clear(); }
@@ -238,15 +238,15 @@ static cudaError_t forecast_v3(dab_handle* h, const double* in, double* out, lon
 }
 
 // one launch of the chained forecast kernel; the tables of a shape are planned and uploaded on first use
-static cudaError_t forecast_v6(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
+static cudaError_t forecast_v6(dab_handle* h, int variant, const double* in, double* out, long long n, int k, int steps,
                                double dt, double F, long long in_ld, long long out_ld, bool periodic,
                                long long in_base, long long in_lo, long long in_hi, cudaStream_t st) {
-  V6Work::Entry* e = h->v6.find(n, k, steps);
+  V6Work::Entry* e = h->v6.find(n, k, steps, variant);
   if (e == nullptr) {
     L96V6Plan plan;
-    if (!l96_v6_plan(n, k, steps, h->sms, &plan)) return cudaErrorInvalidValue;
+    if (!l96_v6_plan(n, k, steps, h->sms, variant, &plan)) return cudaErrorInvalidValue;
     e = new V6Work::Entry();
-    e->n = n; e->k = k; e->steps = steps;
+    e->n = n; e->k = k; e->steps = steps; e->variant = variant;
     e->grid = plan.grid; e->tile_stride = plan.tile_stride; e->chain_stride = plan.chain_stride; e->hist_t = plan.hist_t;
     cudaError_t ce = e->tiles.reserve(plan.tiles.size() * sizeof(int));
     if (ce == cudaSuccess) ce = e->chains.reserve(plan.chains.size() * sizeof(int));
@@ -259,7 +259,7 @@ static cudaError_t forecast_v6(dab_handle* h, const double* in, double* out, lon
     h->v6.plans.push_back(e);
   }
   return l96_v6_launch(in, out, e->tiles.as<int>(), e->chains.as<int>(), e->grid, e->tile_stride, e->chain_stride, e->hist_t,
-                       n, steps, dt, F, in_ld, out_ld, periodic, in_base, in_lo, in_hi, st);
+                       variant, n, steps, dt, F, in_ld, out_ld, periodic, in_base, in_lo, in_hi, st);
 }
 
 // K1 over one window of `steps` <= first_steps steps: extended-layout analysis `in_ext` -> `dst`
@@ -271,8 +271,8 @@ static cudaError_t forecast_v6(dab_handle* h, const double* in, double* out, lon
 static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, double* dst, double* traj,
                                 long long traj_stride, int steps, int T, int chunks, int* n_launches) {
   const int k = c.cfg.ensemble_dim;
-  if (T >= kL96V6Code && l96_v6_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr)) {
-    cudaError_t e = forecast_v6(h, in_ext, dst, c.n_loc, k, steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false,
+  if (T >= kL96V6Code && l96_v6_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr, T - kL96V6Code)) {
+    cudaError_t e = forecast_v6(h, T - kL96V6Code, in_ext, dst, c.n_loc, k, steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false,
                                 c.halo_l, -8ll * steps, c.n_loc + 4ll * steps, h->stream);
     if (e == cudaSuccess && n_launches) ++*n_launches;
     return e;
@@ -847,6 +847,8 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     DAB_CUDA(h, cudaEventCreate(&e0));
     DAB_CUDA(h, cudaEventCreate(&e1));
     const int n_cand = 20;
+    // (the 6 x 64-thread build of the chained kernel, kL96V6Code + 1, was measured at every bench shape and never
+    // won: it stays reachable through DAB_L96_V6=2)
     const int cand[n_cand] = {kL96V6Code, kL96V3Code + 32, kL96V3Code + 10, 128, 192, 256, 320, 384, 512,
                               l96_shape_code(16, 128), l96_shape_code(16, 160), l96_shape_code(16, 192),
                               l96_shape_code(16, 224), l96_shape_code(16, 256), l96_shape_code(17, 128),
@@ -864,7 +866,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
       const int longest = (c.first_steps + chunks - 1) / chunks;
       for (int ci = 0; ci < n_cand; ++ci) {
         if (cand[ci] >= kL96V6Code) {
-          if (chunks > 1 || !l96_v6_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
+          if (chunks > 1 || !l96_v6_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false, cand[ci] - kL96V6Code)) continue;
         } else if (cand[ci] >= kL96V3Code) {
           if (chunks > 1 || !l96_v3_eligible(c.ext[0].as<double>(), c.xb[1], c.n_loc, c.ld_e, c.n_loc, c.halo_l, c.first_steps, false)) continue;
         } else {
@@ -899,7 +901,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   }
   if (const char* ev = getenv("DAB_L96_V6")) {              // force (1) or forbid (0) the chained kernel
     const int v = atoi(ev);
-    if (v == 1) c.l96_T = kL96V6Code;
+    if (v == 1 || v == 2) c.l96_T = kL96V6Code + v - 1;      // 1: 3 groups x 128 threads, 2: 6 groups x 64 threads
     else if (v == 0 && c.l96_T >= kL96V6Code) c.l96_T = 0;
   }
   if (const char* ev = getenv("DAB_L96_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) c.l96_chunks = v; }

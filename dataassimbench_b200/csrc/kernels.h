@@ -33,21 +33,22 @@ cudaError_t l96_v3_launch(const double* in, double* out, double* scratch0, doubl
                           double dt, double F, long long in_ld, long long out_ld, bool periodic,
                           long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st);
 
-// K1, chains handed out inside the SM  l96_forecast_v6.cu (shape code 60000): one persistent 384-thread CTA per SM,
-// three 4-warp groups, each sweeping its own chain; chains of decreasing length from a shared-memory dispenser.
+// K1, chains handed out inside the SM  l96_forecast_v6.cu (shape code 60000 + variant): one persistent 384-thread CTA
+// per SM; variant 0 = three 4-warp groups on 2048-point tiles, variant 1 = six 2-warp groups on 1024-point tiles; each
+// group sweeps its own chain; chains of decreasing length from a shared-memory dispenser.
 constexpr int kL96V6Code = 60000;
 struct L96V6Plan {
-  int grid = 0, tile_stride = 0, chain_stride = 0, hist_t = 0;
+  int grid = 0, variant = 0, tile_stride = 0, chain_stride = 0, hist_t = 0;
   std::vector<int> tiles;          // [grid][tile_stride][4]: {2 member + continuing, g0, p, q} in sweep order
   std::vector<int> chains;         // [grid][chain_stride]: n_chains, first tile of every chain, n_tiles
 };
 bool l96_v6_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
-                     long long in_base, int n_steps, bool traj);
-bool l96_v6_plan(long long n, int k, int n_steps, int ctas, L96V6Plan* out);
+                     long long in_base, int n_steps, bool traj, int variant);
+bool l96_v6_plan(long long n, int k, int n_steps, int ctas, int variant, L96V6Plan* out);
 cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, const int* chains_dev, int grid,
-                          int tile_stride, int chain_stride, int hist_t, long long n, int n_steps, double dt, double F,
-                          long long in_ld, long long out_ld, bool periodic, long long in_base, long long in_lo,
-                          long long in_hi, cudaStream_t st);
+                          int tile_stride, int chain_stride, int hist_t, int variant, long long n, int n_steps,
+                          double dt, double F, long long in_ld, long long out_ld, bool periodic, long long in_base,
+                          long long in_lo, long long in_hi, cudaStream_t st);
 
 // Lorenz-63 members [k][3]  l63_forecast.cu
 cudaError_t l63_forecast_launch(const double* x_in, double* x_out, double* traj, long long k, int n_steps,

@@ -29,8 +29,8 @@
 // bit-identical.
 //
 // ptxas keeps the RK4 coefficients in uniform registers (full-rate DFMA: see l96_forecast.cu) only where it can
-// prove the warp converged; the trip count of the tile loop differs from group to group, so every pass starts with a
-// one-warp named barrier (`bar.sync id, 32`), which costs a few cycles and restores that proof.
+// prove the warp converged; the trip count of the tile loop differs from group to group, so every pass starts with
+// the group's barrier, which restores that proof.
 //
 // Requirements (l96_v6_eligible): even n and row strides, 16-byte aligned rows, no trajectory output.
 #include <cstdlib>
@@ -41,13 +41,13 @@
 
 namespace dab {
 
+// Two builds: 3 groups x 128 threads (tiles of 2048 points: the large shapes) and 6 groups x 64 threads (tiles of 1024
+// points: slabs of a grid-sharded run, where an SM gets only a few thousand points and finer tiles balance better).
 constexpr int V6_P = 16;                          // points per thread
-constexpr int V6_TG = 128;                        // threads per group
-constexpr int V6_G = 3;                           // groups per CTA
-constexpr int V6_W = V6_P * V6_TG;                // points per tile
-constexpr int V6_STAGE = V6_W + 2 * (V6_W / 16);  // padded staging doubles (16-byte pairs stay aligned, LDS.128 conflict-free)
 constexpr int V6_MAX_STEPS = 32;                  // history entries: 4 per step
-constexpr int V6_GROUP_DOUBLES = 8 * V6_TG + 2 * V6_TG + 2 * V6_STAGE + 2 * 4 * V6_TG * 2;   // shared memory of a group
+__host__ __device__ constexpr int v6_tile(int TG) { return V6_P * TG; }                                  // points per tile
+__host__ __device__ constexpr int v6_stage(int TG) { return v6_tile(TG) + 2 * (v6_tile(TG) / 16); }     // padded staging doubles (16-byte pairs stay aligned, LDS.128 conflict-free)
+__host__ __device__ constexpr int v6_group_doubles(int TG) { return 8 * TG + 2 * TG + 2 * v6_stage(TG) + 2 * 4 * TG * 2; }   // shared memory of a group
 
 struct L96V6Args {
   const double* in;
@@ -66,7 +66,8 @@ struct L96V6Args {
 };
 
 __device__ __forceinline__ unsigned v6_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void v6_group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(V6_TG) : "memory"); }
+template <int TG>
+__device__ __forceinline__ void v6_group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TG) : "memory"); }
 
 __device__ __forceinline__ int v6_wrap(int g, int n) {      // ring coordinate of g (any distance from [0, n))
   if ((unsigned)g < (unsigned)n) return g;
@@ -76,34 +77,37 @@ __device__ __forceinline__ int v6_wrap(int g, int n) {      // ring coordinate o
   return g < 0 ? g + n : g;
 }
 
-// cp.async (L2 path) of a tile into a group's staging buffer: 1024 16-byte pairs, thread t takes pairs t, t + 128, ...
+// cp.async (L2 path) of a tile into a group's staging buffer: 8 TG 16-byte pairs, thread t takes pairs t, t + TG, ...
+template <int TG>
 __device__ __forceinline__ void v6_prefetch(const L96V6Args& a, const int4 jb, double* stage, int t) {
   const double* row = a.in + (long long)(jb.x >> 1) * a.in_ld + a.in_base;
   int lo = a.in_lo, hi = a.in_hi;
   if (a.periodic) { lo = 0; hi = a.n; }
   const int g0 = jb.y;
-  // pair index q = t + 128 i -> element e = 2 q = 2 t + 256 i; padded position e + 2 (e >> 4) = 2 t + 2 (t >> 3) + 288 i
+  // pair index q = t + TG i -> element e = 2 q = 2 t + 2 TG i; padded position e + 2 (e >> 4) = 2 t + 2 (t >> 3) + (2 TG + TG / 4) i
+  constexpr int DSTEP = (2 * TG + TG / 4) * 8;       // bytes
   const unsigned dst0 = v6_smem(stage + 2 * t + 2 * (t >> 3));
-  if (g0 >= lo && g0 + V6_W <= hi) {
+  if (g0 >= lo && g0 + v6_tile(TG) <= hi) {
     const double* src = row + g0 + 2 * t;
 #pragma unroll
-    for (int i = 0; i < V6_W / (2 * V6_TG); ++i)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 288 * 8 * i), "l"(src + 256 * i) : "memory");
+    for (int i = 0; i < 8; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + DSTEP * i), "l"(src + 2 * TG * i) : "memory");
   } else {
 #pragma unroll 1
-    for (int i = 0; i < V6_W / (2 * V6_TG); ++i) {
-      int g = g0 + 2 * t + 256 * i;
+    for (int i = 0; i < 8; ++i) {
+      int g = g0 + 2 * t + 2 * TG * i;
       if (a.periodic) g = v6_wrap(g, a.n);
       else g = g < lo ? lo : (g > hi - 2 ? hi - 2 : g);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 288 * 8 * i), "l"(row + g) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + DSTEP * i), "l"(row + g) : "memory");
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(V6_G * V6_TG, 1)
+template <int TG, int G>
+__global__ void __launch_bounds__(G * TG, 1)
 l96_v6_kernel(const L96V6Args a) {
-  constexpr int P = V6_P, T = V6_TG;
+  constexpr int P = V6_P, T = TG, V6_G = G, V6_STAGE = v6_stage(TG), V6_GROUP_DOUBLES = v6_group_doubles(TG);
   extern __shared__ __align__(16) double smem[];
   const int grp = threadIdx.x / T;                      // 0..2
   const int t = threadIdx.x - grp * T;                  // thread of the group
@@ -136,12 +140,12 @@ l96_v6_kernel(const L96V6Args a) {
   pdl_launch_dependents();
   if (ti < 0) return;
   int4 cur = __ldg(tiles + ti);
-  v6_prefetch(a, cur, st_in, t);
+  v6_prefetch<TG>(a, cur, st_in, t);
 
   for (int n_local = 0;; ++n_local) {
-    // a one-warp named barrier: tells ptxas the warp is converged at the top of every pass of this loop, whose trip
-    // count differs from group to group (without it the RK4 coefficients leave the uniform registers)
-    asm volatile("bar.sync %0, 32;" ::"r"(V6_G + 1 + (int)(threadIdx.x >> 5)) : "memory");
+    // a barrier at the top of every pass tells ptxas the warps are converged in this loop, whose trip count differs
+    // from group to group (without it the RK4 coefficients leave the uniform registers)
+    v6_group_sync<TG>(grp);
     // ---- the next tile of this group: the chain's next one, or the first tile of the next chain from the dispenser
     if (t == 0) {
       int nx = ti + 1;
@@ -157,7 +161,7 @@ l96_v6_kernel(const L96V6Args a) {
     }
     // ---- this tile: staging -> registers (blocked: thread owns 16 consecutive points)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    v6_group_sync(grp);
+    v6_group_sync<TG>(grp);
     double s[P], xh[P], xd[P], acc[P];
 #pragma unroll
     for (int i = 0; i < P; i += 2) {
@@ -191,8 +195,8 @@ l96_v6_kernel(const L96V6Args a) {
     for (int step = 0; step < a.n_steps; ++step) {
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
-        v6_group_sync(grp);
-        if (step == 0 && st == 1 && ti_next >= 0) v6_prefetch(a, nxt, st_in, t);   // every thread left st_in a barrier ago
+        v6_group_sync<TG>(grp);
+        if (step == 0 && st == 1 && ti_next >= 0) v6_prefetch<TG>(a, nxt, st_in, t);   // every thread left st_in a barrier ago
         const double2 L = *reinterpret_cast<const double2*>(Lp + st * STG);
         const double R = e_first[buf * T + tr];
         buf ^= 1;
@@ -236,15 +240,15 @@ l96_v6_kernel(const L96V6Args a) {
     // ---- registers -> staging -> coalesced 16-byte stores of the still-valid points [p, q)
 #pragma unroll
     for (int i = 0; i < P; i += 2) *reinterpret_cast<double2*>(st_out + 18 * t + i) = make_double2(s[i], s[i + 1]);
-    v6_group_sync(grp);
+    v6_group_sync<TG>(grp);
     {
       double* dst = a.out + (long long)(cur.x >> 1) * a.out_ld + cur.y + 2 * t;
       const double* srcs = st_out + 2 * t + 2 * (t >> 3);
-      const int e_lo = cur.z - cur.y - 2 * t, e_hi = cur.w - cur.y - 2 * t;   // pair 256 i is stored iff e_lo <= 256 i < e_hi
+      const int e_lo = cur.z - cur.y - 2 * t, e_hi = cur.w - cur.y - 2 * t;   // pair 2 T i is stored iff e_lo <= 2 T i < e_hi
 #pragma unroll
-      for (int i = 0; i < V6_W / (2 * T); ++i) {
-        if (256 * i >= e_lo && 256 * i < e_hi)
-          *reinterpret_cast<double2*>(dst + 256 * i) = *reinterpret_cast<const double2*>(srcs + 288 * i);
+      for (int i = 0; i < 8; ++i) {
+        if (2 * T * i >= e_lo && 2 * T * i < e_hi)
+          *reinterpret_cast<double2*>(dst + 2 * T * i) = *reinterpret_cast<const double2*>(srcs + (2 * T + T / 4) * i);
       }
     }
     if (ti_next < 0) break;
@@ -253,27 +257,34 @@ l96_v6_kernel(const L96V6Args a) {
 }
 
 // ------------------------------------------------------------------------------------------ host side
+static bool v6_shape(int variant, int* tg, int* g) {
+  if (variant == 0) { *tg = 128; *g = 3; return true; }
+  if (variant == 1) { *tg = 64; *g = 6; return true; }
+  return false;
+}
+
 bool l96_v6_eligible(const double* in, const double* out, long long n, long long in_ld, long long out_ld,
-                     long long in_base, int n_steps, bool traj) {
-  if (traj || n_steps < 1 || n_steps > V6_MAX_STEPS || 12 * n_steps + 16 > V6_W) return false;
+                     long long in_base, int n_steps, bool traj, int variant) {
+  int tg, g;
+  if (!v6_shape(variant, &tg, &g)) return false;
+  if (traj || n_steps < 1 || n_steps > V6_MAX_STEPS || 12 * n_steps + 16 > v6_tile(tg)) return false;
   if ((n & 1) || (in_ld & 1) || (out_ld & 1) || (in_base & 1)) return false;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
   if (n < 4 || n + 12ll * n_steps >= (1ll << 30)) return false;
   return true;
 }
 
-static size_t v6_smem_bytes() {
-  return (size_t)V6_G * (size_t)V6_GROUP_DOUBLES * sizeof(double);
-}
-
 // The flattened (member, position) space is cut into `ctas` equal contiguous ranges (even boundaries); inside a
 // range, member by member, into chains: a fresh tile (first useful point `pos`, window from pos - 8 S, useful
 // [pos, g0 + A)) followed by continuing tiles (window from g0, useful [g0, g0 + A)), A = W - 4 S rounded down to
 // whole threads.  Chain lengths are guided: ceil(tiles left in the range / (2 G)), at least one.
-bool l96_v6_plan(long long n, int k, int n_steps, int ctas, L96V6Plan* out) {
-  if (n_steps < 1 || n_steps > V6_MAX_STEPS || 12 * n_steps + 16 > V6_W || ctas < 1) return false;
+bool l96_v6_plan(long long n, int k, int n_steps, int ctas, int variant, L96V6Plan* out) {
+  int tg, G;
+  if (!v6_shape(variant, &tg, &G)) return false;
+  const int W = v6_tile(tg);
+  if (n_steps < 1 || n_steps > V6_MAX_STEPS || 12 * n_steps + 16 > W || ctas < 1) return false;
   const int S = n_steps;
-  const int A = ((V6_W - 4 * S) / V6_P) * V6_P;
+  const int A = ((W - 4 * S) / V6_P) * V6_P;
   const long long total = n * (long long)k;
   long long per = (ceil_div_ll(total, ctas) + 1) & ~1ll;                // points per CTA, even
   if (per < 2) per = 2;
@@ -291,7 +302,7 @@ bool l96_v6_plan(long long n, int k, int n_steps, int ctas, L96V6Plan* out) {
       const long long seg_end = ((long long)(mem + 1) * n < hi ? n : hi - (long long)mem * n);
       while (pos < seg_end) {
         const long long left_tiles = ceil_div_ll(left_pts, A);
-        long long len = ceil_div_ll(left_tiles, 2 * V6_G);
+        long long len = ceil_div_ll(left_tiles, 2 * G);
         if (len < 1) len = 1;
         ch.push_back((int)(tl.size() / 4));
         bool fresh = true;
@@ -311,6 +322,7 @@ bool l96_v6_plan(long long n, int k, int n_steps, int ctas, L96V6Plan* out) {
     if (ch.size() > max_chains) max_chains = ch.size();
   }
   out->grid = grid;
+  out->variant = variant;
   out->tile_stride = (int)max_tiles;
   out->chain_stride = (int)max_chains + 1;
   out->hist_t = A / V6_P - 1;
@@ -325,10 +337,22 @@ bool l96_v6_plan(long long n, int k, int n_steps, int ctas, L96V6Plan* out) {
   return true;
 }
 
+template <int TG, int G>
+static cudaError_t v6_launch_t(const L96V6Args& a, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)G * (size_t)v6_group_doubles(TG) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(l96_v6_kernel<TG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_chain(true, l96_v6_kernel<TG, G>, dim3((unsigned)grid), dim3(G * TG), smem, st, a);
+}
+
 cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, const int* chains_dev, int grid,
-                          int tile_stride, int chain_stride, int hist_t, long long n, int n_steps, double dt, double F,
-                          long long in_ld, long long out_ld, bool periodic, long long in_base, long long in_lo,
-                          long long in_hi, cudaStream_t st) {
+                          int tile_stride, int chain_stride, int hist_t, int variant, long long n, int n_steps,
+                          double dt, double F, long long in_ld, long long out_ld, bool periodic, long long in_base,
+                          long long in_lo, long long in_hi, cudaStream_t st) {
   L96V6Args a{};
   a.in = in; a.out = out;
   a.in_ld = in_ld; a.out_ld = out_ld; a.in_base = in_base;
@@ -338,13 +362,8 @@ cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, c
   a.tile_stride = tile_stride; a.chain_stride = chain_stride;
   a.n_steps = n_steps; a.hist_t = hist_t;
   a.dt = dt; a.h2 = 0.5 * dt; a.h3 = dt / 3.0; a.h6 = dt / 6.0; a.h2F = a.h2 * F; a.dtF = dt * F;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(l96_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v6_smem_bytes());
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  return launch_chain(true, l96_v6_kernel, dim3((unsigned)grid), dim3(V6_G * V6_TG), v6_smem_bytes(), st, a);
+  if (variant == 1) return v6_launch_t<64, 6>(a, grid, st);
+  return v6_launch_t<128, 3>(a, grid, st);
 }
 
 }  // namespace dab

@@ -33,7 +33,7 @@ static void cpu_rk4(std::vector<double>& x, long long N, int steps, double dt, d
   }
 }
 
-static int g_slots = 444;
+static int g_slots = 444, g_variant = 0;
 
 // world ranks emulated one after the other: rank r owns columns [r n_loc, (r+1) n_loc) and gets the
 // extended layout [8S | slab | 4S] cut from the ring
@@ -54,7 +54,7 @@ static double check(long long N, int k, int S, bool periodic, int world, int slo
   const size_t in_elems = periodic ? (size_t)k * N : (size_t)k * ld_e;
   cudaMalloc(&d_in, in_elems * 8); cudaMalloc(&d_out, (size_t)k * n_loc * 8); cudaMalloc(&d_out1, (size_t)k * n_loc * 8);
   L96V6Plan plan;
-  if (!l96_v6_plan(n_loc, k, S, slots, &plan)) { printf("plan failed\n"); return 1e9; }
+  if (!l96_v6_plan(n_loc, k, S, slots, g_variant, &plan)) { printf("plan failed\n"); return 1e9; }
   int *d_jobs, *d_chains; cudaMalloc(&d_jobs, plan.tiles.size() * 4); cudaMalloc(&d_chains, plan.chains.size() * 4);
   cudaMemcpy(d_jobs, plan.tiles.data(), plan.tiles.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_chains, plan.chains.data(), plan.chains.size() * 4, cudaMemcpyHostToDevice);
@@ -73,7 +73,7 @@ static double check(long long N, int k, int S, bool periodic, int world, int slo
     cudaMemcpy(d_in, hin.data(), in_elems * 8, cudaMemcpyHostToDevice);
     cudaMemset(d_out, 0xff, (size_t)k * n_loc * 8);
     cudaMemset(d_out1, 0xff, (size_t)k * n_loc * 8);
-    cudaError_t e = l96_v6_launch(d_in, d_out, d_jobs, d_chains, plan.grid, plan.tile_stride, plan.chain_stride, plan.hist_t, n_loc, S, dt, F,
+    cudaError_t e = l96_v6_launch(d_in, d_out, d_jobs, d_chains, plan.grid, plan.tile_stride, plan.chain_stride, plan.hist_t, g_variant, n_loc, S, dt, F,
                                   periodic ? N : ld_e, n_loc, periodic, periodic ? 0 : 8 * S, periodic ? 0 : -8ll * S,
                                   periodic ? 0 : n_loc + 4ll * S, 0);
     if (e != cudaSuccess) { printf("launch: %s\n", cudaGetErrorString(e)); return 1e9; }
@@ -108,7 +108,7 @@ static void timeit(long long N, int k, int S, int slots) {
   for (size_t i = 0; i < h.size(); ++i) h[i] = 8.0 + 2.0 * sin(0.01 * i);
   cudaMemcpy(d_in, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
   L96V6Plan plan;
-  if (!l96_v6_plan(N, k, S, slots, &plan)) { printf("plan failed\n"); return; }
+  if (!l96_v6_plan(N, k, S, slots, g_variant, &plan)) { printf("plan failed\n"); return; }
   int *d_jobs, *d_chains; cudaMalloc(&d_jobs, plan.tiles.size() * 4); cudaMalloc(&d_chains, plan.chains.size() * 4);
   cudaMemcpy(d_jobs, plan.tiles.data(), plan.tiles.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_chains, plan.chains.data(), plan.chains.size() * 4, cudaMemcpyHostToDevice);
@@ -116,7 +116,7 @@ static void timeit(long long N, int k, int S, int slots) {
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
     cudaEventRecord(e0);
-    l96_v6_launch(d_in, d_out, d_jobs, d_chains, plan.grid, plan.tile_stride, plan.chain_stride, plan.hist_t, N, S, dt, F, ld_e, N, false, 8 * S,
+    l96_v6_launch(d_in, d_out, d_jobs, d_chains, plan.grid, plan.tile_stride, plan.chain_stride, plan.hist_t, g_variant, N, S, dt, F, ld_e, N, false, 8 * S,
                   -8ll * S, N + 4ll * S, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -129,6 +129,8 @@ static void timeit(long long N, int k, int S, int slots) {
 
 int main(int argc, char** argv) {
   g_slots = 148;
+  if (getenv("V6_VARIANT")) g_variant = atoi(getenv("V6_VARIANT"));
+  printf("variant %d\n", g_variant);
   
   double w = 0;
   if (getenv("DAB_SKIP_CHECK")) goto timing;
