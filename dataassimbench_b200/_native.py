@@ -63,6 +63,7 @@ _SIGNATURES = {
     "dab_var3d_analysis_b_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, C.c_double, _P, C.c_double, C.c_int, _P, _P]),
     "dab_etkf_stats_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P, _P]),
     "dab_etkf_transform_matrix_f64": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
+    "dab_debug_l96_chain_plan": (C.c_int, [_I64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _I64, _P, _I64]),
     "dab_etkf_analysis_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I64, C.c_int, _I64, _P]),
     "dab_etkf_analysis_diag_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_double, _I64, C.c_int, _I64, _P]),
     "dab_cycler_setup": (C.c_int, [_P, C.POINTER(CycleConfig), _P, _P, _P]),

@@ -416,6 +416,20 @@ static int forecast_plain(dab_handle* h, const double* x_in, double* x_out, doub
   return 0;
 }
 
+// Host-only: the tile / chain tables the chained forecast kernel (l96_forecast_v6.cu) would be launched with, so that
+// the tiling logic can be checked without a GPU (tests/test_cabi_cpu.py).  dims_out = {grid, tile_stride, chain_stride,
+// hist_t}; tiles_out / chains_out receive the tables if they are large enough (sizes in ints), else only dims_out.
+int dab_debug_l96_chain_plan(int64_t n, int k, int n_steps, int ctas, int variant, int* dims_out, int* tiles_out,
+                             int64_t tiles_cap, int* chains_out, int64_t chains_cap) {
+  if (!dims_out || n < 4 || k < 1) return -1;
+  L96V6Plan plan;
+  if (!l96_v6_plan(n, k, n_steps, ctas, variant, &plan)) return -1;
+  dims_out[0] = plan.grid; dims_out[1] = plan.tile_stride; dims_out[2] = plan.chain_stride; dims_out[3] = plan.hist_t;
+  if (tiles_out && (int64_t)plan.tiles.size() <= tiles_cap) memcpy(tiles_out, plan.tiles.data(), plan.tiles.size() * sizeof(int));
+  if (chains_out && (int64_t)plan.chains.size() <= chains_cap) memcpy(chains_out, plan.chains.data(), plan.chains.size() * sizeof(int));
+  return 0;
+}
+
 int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj,
                          int64_t N, int k, int n_steps, double dt, double F, void* stream) {
   DAB_ARG(h, h != nullptr);

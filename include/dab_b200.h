@@ -146,6 +146,14 @@ DAB_API int dab_etkf_stats_f64(dab_handle* h, const double* X, const double* y, 
 DAB_API int dab_etkf_transform_matrix_f64(dab_handle* h, const double* stats, int k, double rho,
                                   int empty_R, double* T, double* lam, int* sweeps, void* stream);
 
+/* Host-only debugging aid (no device needed): the tile and chain tables of the chained forecast kernel for a shape
+ * (csrc/l96_forecast_v6.cu: how the rows are cut into tiles that hand their left boundary to the next tile).
+ * dims_out[4] = {grid, tile_stride, chain_stride, hist_t}; tiles_out [grid][tile_stride][4] = {2 member + continuing,
+ * window start g0, first useful point p, end q}; chains_out [grid][chain_stride] = n_chains, the index of every chain's
+ * first tile, n_tiles.  The tables are written only if the capacities (in ints) suffice. */
+DAB_API int dab_debug_l96_chain_plan(int64_t n, int k, int n_steps, int ctas, int variant, int* dims_out, int* tiles_out,
+                             int64_t tiles_cap, int* chains_out, int64_t chains_cap);
+
 /* ---- single analysis --------------------------------------------------------------------
  * Replaces ETKF._cycle_obsop + ETKF._compute_analysis (dabench/dacycler/_etkf.py:94-213) for
  * the default operators (H = index gather, R = sd^2 I).

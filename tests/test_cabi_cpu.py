@@ -1,6 +1,8 @@
 """CPU-side checks of the drop-in boundary: the in-tree library loads, exports every symbol
 include/dab_b200.h declares, and fails loudly (no CPU fallback) without a CUDA device."""
 import ctypes
+
+import numpy as np
 import os
 import re
 import shutil
@@ -97,3 +99,49 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     else:
         assert "create rc" in out.stdout and "handle null" in out.stdout
         assert "no CPU fallback" in out.stdout or "CUDA" in out.stdout
+
+
+@pytest.mark.parametrize("n,k,S,ctas,variant", [
+    (65536, 64, 20, 148, 0), (4194304, 4, 20, 148, 0), (8192, 64, 20, 148, 1), (65536, 4, 19, 5, 0), (600, 3, 7, 148, 0),
+    (36, 10, 20, 148, 0), (65536, 4, 1, 3, 1), (1048576, 2, 32, 16, 0), (40, 20, 20, 7, 1)])
+def test_chained_forecast_plan_covers_every_point_once(n, k, S, ctas, variant):
+    """The host-side tiling of the chained forecast kernel (csrc/l96_forecast_v6.cu), checked without a GPU: every grid
+    point of every member is stored by exactly one tile; a fresh tile keeps 8 S points of halo on its left and 4 S of
+    stale points on its right inside its window; a continuing tile starts exactly where its predecessor's window
+    advanced to (so that the boundary history it reads is its left neighbour's), in the same chain and member."""
+    import ctypes as C
+    lib = _native.load()
+    dims = (C.c_int * 4)()
+    assert lib.dab_debug_l96_chain_plan(n, k, S, ctas, variant, dims, None, 0, None, 0) == 0
+    grid, ts, cs, hist_t = list(dims)
+    tiles = np.zeros(grid * ts * 4, dtype=np.int32)
+    chains = np.zeros(grid * cs, dtype=np.int32)
+    assert lib.dab_debug_l96_chain_plan(n, k, S, ctas, variant, dims, tiles.ctypes.data, tiles.size, chains.ctypes.data,
+                                        chains.size) == 0
+    W = 2048 if variant == 0 else 1024
+    A = ((W - 4 * S) // 16) * 16
+    assert hist_t == A // 16 - 1 and 1 <= grid <= ctas
+    tiles = tiles.reshape(grid, ts, 4)
+    chains = chains.reshape(grid, cs)
+    cover = np.zeros((k, n), dtype=np.int32)
+    for b in range(grid):
+        nc = chains[b, 0]
+        starts = chains[b, 1:nc + 2]
+        assert nc >= 1 and starts[0] == 0 and np.all(np.diff(starts) >= 1) and starts[-1] <= ts
+        for c in range(nc):
+            prev = None
+            for ti in range(starts[c], starts[c + 1]):
+                x, g0, p, q = (int(v) for v in tiles[b, ti])
+                mem, cont = x >> 1, x & 1
+                assert 0 <= mem < k and 0 <= p < q <= n
+                if cont:
+                    assert prev is not None and ti > starts[c]            # only inside a chain
+                    assert prev[0] == mem and g0 == prev[1] + A and p == g0   # window advanced by A, same member
+                else:
+                    assert ti == starts[c] or prev[0] != mem               # a chain or a member starts fresh
+                    assert g0 == p - 8 * S
+                assert q <= g0 + W - 4 * S                                 # inside the still-valid part of the window
+                assert p % 2 == 0 and q % 2 == 0 and g0 % 2 == 0
+                cover[mem, p:q] += 1
+                prev = (mem, g0)
+    assert cover.min() == 1 and cover.max() == 1
