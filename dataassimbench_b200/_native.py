@@ -87,6 +87,7 @@ _SIGNATURES = {
     "dab_cycler_background_ptr": (_P, [_P]),
     "dab_cycler_kernel_launches": (C.c_int, [_P]),
     "dab_cycler_forecast_shape": (C.c_int, [_P]),
+    "dab_cycler_compact_contractions": (C.c_int, [_P]),
     "dab_cycler_set_profiling": (C.c_int, [_P, C.c_int]),
     "dab_cycler_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "dab_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -258,6 +259,10 @@ class Handle:
         """(shape code, launches per window) the autotuner picked for the forecast kernel."""
         v = self._lib.dab_cycler_forecast_shape(self._h)
         return v // 10, v % 10
+
+    def cycler_compact_contractions(self):
+        """Contractions since setup that read the compact Yb the forecast kernels wrote (no gather)."""
+        return self._lib.dab_cycler_compact_contractions(self._h)
 
     def cycler_update(self, cycle, out_analysis_dev=None):
         self._check(self._lib.dab_cycler_update(self._h, cycle, _ptr(out_analysis_dev)))

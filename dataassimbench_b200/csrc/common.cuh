@@ -40,6 +40,22 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 bool pdl_enabled();   // engine.cu: DAB_PDL != "0"
 
+// Forecast kernels: write the observed columns of a finished tile into the compact Yb row of `member` (kernels.h:
+// ObsEmit).  The tile's values sit in shared memory, element e (window-relative) at tile[pad(e)]; [p, q) is the range
+// of slab columns the tile stores; g0 the slab column of window position 0.  Every thread of the group / CTA calls it
+// (tid of nthreads).  The candidate rows are those of the 64-column blocks that meet [p, q): no dependent search.
+template <typename Pad>
+__device__ __forceinline__ void emit_observed(const int* __restrict__ loc, const int* __restrict__ row_start, int n_rows,
+                                              double* __restrict__ yb_row, const double* tile, Pad pad, long long g0,
+                                              long long p, long long q, int tid, int nthreads) {
+  if (q <= p) return;
+  const int r_lo = row_start[p >> 6], r_hi = row_start[((q - 1) >> 6) + 1];
+  for (int r = r_lo + tid; r < r_hi && r < n_rows; r += nthreads) {
+    const long long c = loc[r];
+    if (c >= p && c < q) yb_row[r] = tile[pad((int)(c - g0))];
+  }
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_chain(bool chain, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                        cudaStream_t st, Args... args) {

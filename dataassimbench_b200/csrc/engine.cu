@@ -91,9 +91,17 @@ struct Cycler {
   DevBuf ext[2];                           // extended-layout analysis buffers
   DevBuf obs_loc, obs_val, obs_sw, seg, partial, stats, T, lam, info;
   bool has_sw = false;                     // obs_sw holds 1 / sigma per row (diagonal R with unequal entries)
+  // compact observation-space ensemble written by the forecast kernel (ObsEmit, kernels.h): stationary network whose
+  // every observation time has the same location-ordered rows
+  DevBuf yb, row_start;
+  bool emit_ok = false;                    // the network qualifies (decided at setup)
+  bool yb_valid = false;                   // yb holds the observed columns of the CURRENT background
+  long long emit_rows = 0, emit_loc_off = 0, ldy = 0;
+  int n_compact = 0;                       // contractions since setup that read yb
   std::vector<long long> csr_off;          // [n_obs_times + 1]
   std::vector<int> n_seg;                  // per cycle
   std::vector<long long> n_rows;           // per cycle
+  std::vector<long long> seg_begin;        // per cycle: offset of its rows in obs_val when it has exactly one segment, else -1
   int max_grid = 1;
   int l96_T = 0;                           // autotuned CTA width of the forecast kernel (0 = heuristic)
   int l96_chunks = 1;                      // autotuned number of launches one window is split into
@@ -134,6 +142,10 @@ struct dab_handle {
   DevBuf s_flag;                                         // device-side argument check of dab_observe_f64
   DevBuf s_cg;                                           // conjugate-gradient vectors of dab_var3d_analysis_b_f64
   DevBuf s_src, s_off;                                   // dab_cycler_setup_dev: row permutations and offsets
+  // DAB_YB_EMIT=1 at set-up: stationary networks take the compact-Yb route (forecast kernels emit the observed
+  // columns, etkf_contract_dense.cu contracts them).  Off by default: at C3 the contraction gains 3.5 us and the
+  // forecast loses 4.5 (profiles/yb_emit_r02.md); larger shapes do not fit a CTA's rows in shared memory.
+  bool yb_emit = false;
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
   V6Work v6;                                             // chained forecast kernel: tile and chain tables
@@ -216,6 +228,7 @@ static void cycler_free(dab_handle* h) {
   }
   c.xb_bytes = 0;
   c.obs_loc.release(); c.obs_val.release(); c.obs_sw.release(); c.seg.release(); c.partial.release();
+  c.yb.release(); c.row_start.release();
   c.stats.release(); c.T.release(); c.lam.release(); c.info.release();
   c.xchg.release(); c.xchg_ctr.release(); c.sse_partial.release();
   c.ready = false;
@@ -224,7 +237,8 @@ static void cycler_free(dab_handle* h) {
 // one launch of the persistent forecast kernel (workspace reserved by the caller)
 static cudaError_t forecast_v3(dab_handle* h, const double* in, double* out, long long n, int k, int steps,
                                int chunk_steps, double dt, double F, long long in_ld, long long out_ld,
-                               bool periodic, long long in_base, long long in_lo, long long in_hi) {
+                               bool periodic, long long in_base, long long in_lo, long long in_hi,
+                               const ObsEmit* emit = nullptr) {
   V2Work& w = h->v2;
   if (++w.epoch == 0) {                       // 2^32 launches: start the flags over
     cudaError_t e = cudaMemsetAsync(w.flags.p, 0, w.flags.bytes, h->stream);
@@ -234,13 +248,14 @@ static cudaError_t forecast_v3(dab_handle* h, const double* in, double* out, lon
   return l96_v3_launch(in, out, w.scr[0].as<double>(), w.scr[1].as<double>(),
                        periodic ? n : l96_v3_scratch_ld(n, steps), w.flags.as<unsigned>(), w.epoch,
                        w.counter.as<unsigned long long>(), &w.ctr_base, n, k, steps, chunk_steps, dt, F, in_ld,
-                       out_ld, periodic, in_base, in_lo, in_hi, h->sms, h->stream);
+                       out_ld, periodic, in_base, in_lo, in_hi, h->sms, h->stream, emit);
 }
 
 // one launch of the chained forecast kernel; the tables of a shape are planned and uploaded on first use
 static cudaError_t forecast_v6(dab_handle* h, int variant, const double* in, double* out, long long n, int k, int steps,
                                double dt, double F, long long in_ld, long long out_ld, bool periodic,
-                               long long in_base, long long in_lo, long long in_hi, cudaStream_t st) {
+                               long long in_base, long long in_lo, long long in_hi, cudaStream_t st,
+                               const ObsEmit* emit = nullptr) {
   V6Work::Entry* e = h->v6.find(n, k, steps, variant);
   if (e == nullptr) {
     L96V6Plan plan;
@@ -259,7 +274,7 @@ static cudaError_t forecast_v6(dab_handle* h, int variant, const double* in, dou
     h->v6.plans.push_back(e);
   }
   return l96_v6_launch(in, out, e->tiles.as<int>(), e->chains.as<int>(), e->grid, e->tile_stride, e->chain_stride, e->hist_t,
-                       variant, n, steps, dt, F, in_ld, out_ld, periodic, in_base, in_lo, in_hi, st);
+                       variant, n, steps, dt, F, in_ld, out_ld, periodic, in_base, in_lo, in_hi, st, emit);
 }
 
 // K1 over one window of `steps` <= first_steps steps: extended-layout analysis `in_ext` -> `dst`
@@ -268,13 +283,18 @@ static cudaError_t forecast_v6(dab_handle* h, int variant, const double* in, dou
 // (useful fraction 88 % -> 94 % at 20 -> 10 steps, 2048-point tiles) and quantise into waves more
 // finely, at the price of one more pass over the (L2- or HBM-resident) state per chunk.  Chunk j
 // with `rem` steps still to go writes the slab plus the 8 rem / 4 rem halo the rest needs.
+// `emit` (nullable): also write the observed columns of the result into the compact Yb; *emitted says whether the
+// launch form used could do it (a window cut into several launches does not).
 static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, double* dst, double* traj,
-                                long long traj_stride, int steps, int T, int chunks, int* n_launches) {
+                                long long traj_stride, int steps, int T, int chunks, int* n_launches,
+                                const ObsEmit* emit = nullptr, bool* emitted = nullptr) {
   const int k = c.cfg.ensemble_dim;
+  if (emitted) *emitted = false;
   if (T >= kL96V6Code && l96_v6_eligible(in_ext, dst, c.n_loc, c.ld_e, c.n_loc, c.halo_l, steps, traj != nullptr, T - kL96V6Code)) {
     cudaError_t e = forecast_v6(h, T - kL96V6Code, in_ext, dst, c.n_loc, k, steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc, false,
-                                c.halo_l, -8ll * steps, c.n_loc + 4ll * steps, h->stream);
+                                c.halo_l, -8ll * steps, c.n_loc + 4ll * steps, h->stream, emit);
     if (e == cudaSuccess && n_launches) ++*n_launches;
+    if (e == cudaSuccess && emitted) *emitted = emit != nullptr;
     return e;
   }
   if (T >= kL96V6Code) T = 0;
@@ -283,8 +303,9 @@ static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, 
     cudaError_t e = h->v2.reserve(c.n_loc, k, c.first_steps, chunk_steps < steps);
     if (e != cudaSuccess) return e;
     e = forecast_v3(h, in_ext, dst, c.n_loc, k, steps, chunk_steps, c.cfg.model_dt, c.cfg.forcing, c.ld_e, c.n_loc,
-                    false, c.halo_l, -8ll * steps, c.n_loc + 4ll * steps);
+                    false, c.halo_l, -8ll * steps, c.n_loc + 4ll * steps, emit);
     if (e == cudaSuccess && n_launches) ++*n_launches;
+    if (e == cudaSuccess && emitted) *emitted = emit != nullptr;
     return e;
   }
   if (T >= kL96V3Code) T = 0;                 // not eligible (odd sizes, trajectory wanted): first design, heuristic shape
@@ -303,10 +324,12 @@ static cudaError_t forecast_ext(dab_handle* h, Cycler& c, const double* in_ext, 
       out = c.chunk_ext[j & 1].as<double>() + (c.halo_l - 8 * rem);
       out_ld = c.ld_e;
     }
+    const bool last = rem == 0;
     cudaError_t e = l96_forecast_launch(src, out, traj, n2, k, sj, c.cfg.model_dt, c.cfg.forcing, c.ld_e, out_ld,
                                         false, c.halo_l - 8ll * rem, -8ll * sj, n2 + 4ll * sj, traj_stride,
-                                        h->sms, T, h->stream);
+                                        h->sms, T, h->stream, last ? emit : nullptr);
     if (e != cudaSuccess) return e;
+    if (last && emitted) *emitted = emit != nullptr;
     if (n_launches) ++*n_launches;
     src = c.chunk_ext[j & 1].as<double>();
     done += sj;
@@ -783,6 +806,36 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     }
     c.csr_off[(size_t)t + 1] = (long long)loc.size();
   }
+  // ---- compact Yb written by the forecast kernels: a stationary network whose observation times all have the same
+  // rows (one permutation built, reused by every time), at most 2^31 rows, values not NaN-masked on the device
+  c.emit_ok = false; c.yb_valid = false; c.n_compact = 0;
+  bool want_emit = h->yb_emit;
+  if (const char* ev = getenv("DAB_YB_EMIT")) want_emit = atoi(ev) != 0;        // read per set-up: tests switch it
+  if (want_emit && cfg->stationary && nt > 0 && !src.empty() && c.n_loc < (1ll << 31)) {
+    bool same = true;
+    const long long nr0 = c.csr_off[1] - c.csr_off[0];
+    for (long long t = 1; t < nt && same; ++t)
+      same = (c.csr_off[(size_t)t + 1] - c.csr_off[(size_t)t]) == nr0 &&
+             memcmp(system_index + t * no, system_index, sizeof(int64_t) * (size_t)no) == 0;
+    bool ascending = true;
+    for (size_t i = 1; i < (size_t)nr0 && ascending; ++i) ascending = loc[i] > loc[i - 1];      // strictly: one row per column
+    int dgrid = 0, drc = 0;
+    if (same && ascending && nr0 > 0 && contract_dense_plan(nr0, k, h->sms, &dgrid, &drc)) {
+      const size_t nblk = (size_t)(c.n_loc >> 6) + 3;
+      std::vector<int> rs(nblk, (int)nr0);
+      size_t r = 0;
+      for (size_t b = 0; b < nblk; ++b) {
+        while (r < (size_t)nr0 && (long long)loc[r] < (long long)b * 64) ++r;
+        rs[b] = (int)r;
+      }
+      c.emit_rows = nr0; c.emit_loc_off = 0; c.ldy = (nr0 + 1) & ~1ll;
+      DAB_CUDA(h, c.row_start.reserve(sizeof(int) * nblk));
+      DAB_CUDA(h, cudaMemcpyAsync(c.row_start.p, rs.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice, h->stream));
+      DAB_CUDA(h, c.yb.reserve(sizeof(double) * (size_t)k * c.ldy));
+      DAB_CUDA(h, cudaStreamSynchronize(h->stream));            // rs goes out of scope
+      c.emit_ok = true;
+    }
+  }
   DAB_CUDA(h, c.obs_loc.reserve(sizeof(int) * (loc.size() + 1)));
   DAB_CUDA(h, c.obs_val.reserve(sizeof(double) * (val.size() + 1)));
   if (!loc.empty()) {
@@ -813,6 +866,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
   std::vector<long long> seg((size_t)cfg->n_cycles * tp * 3 + 3, 0);
   c.n_seg.assign((size_t)cfg->n_cycles, 0);
   c.n_rows.assign((size_t)cfg->n_cycles, 0);
+  c.seg_begin.assign((size_t)cfg->n_cycles, -1);
   long long max_rows = 0;
   for (int cy = 0; cy < cfg->n_cycles; ++cy) {
     long long rows = 0;
@@ -829,6 +883,7 @@ static int cycler_setup_impl(dab_handle* h, const dab_cycle_config* cfg, const d
     }
     c.n_seg[(size_t)cy] = ns;
     c.n_rows[(size_t)cy] = rows;
+    c.seg_begin[(size_t)cy] = ns == 1 ? seg[((size_t)cy * tp) * 3] : -1;
     if (rows > max_rows) max_rows = rows;
   }
   DAB_CUDA(h, c.seg.reserve(sizeof(long long) * seg.size()));
@@ -945,6 +1000,7 @@ int dab_cycler_set_state(dab_handle* h, const double* x, int is_host) {
   DAB_ARG(h, h != nullptr && h->cyc.ready && x != nullptr);
   DAB_CUDA(h, cudaSetDevice(h->device));
   Cycler& c = h->cyc;
+  c.yb_valid = false;                      // the compact copy belonged to the background this call replaces
   DAB_CUDA(h, cudaMemcpyAsync(c.xb[c.cur], x, sizeof(double) * (size_t)c.cfg.ensemble_dim * c.n_loc,
                               is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
   return 0;
@@ -972,10 +1028,21 @@ int dab_cycler_stats(dab_handle* h, int cycle) {
   const int grid = contract_grid(rows, h->sms);
   const int ns = c.n_seg[(size_t)cycle] > 0 ? c.n_seg[(size_t)cycle] : 1;
   prof_mark(h, PROF_START);
-  DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
-                              c.has_sw ? c.obs_sw.as<double>() : nullptr,
-                              c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
-                              c.partial.as<double>(), grid, true, h->stream));
+  int dgrid = 0, drc = 0;
+  const long long seg_begin = c.seg_begin[(size_t)cycle];
+  if (c.yb_valid && c.n_seg[(size_t)cycle] == 1 && rows == c.emit_rows && seg_begin >= 0 &&
+      contract_dense_plan(rows, k, h->sms, &dgrid, &drc) && dgrid == grid) {
+    // the forecast that made this background also wrote its observed columns, compact: no gather
+    ++c.n_compact;
+    DAB_CUDA(h, contract_dense_launch(c.yb.as<double>(), c.ldy, k, c.obs_val.as<double>() + seg_begin,
+                                      c.has_sw ? c.obs_sw.as<double>() + seg_begin : nullptr, rows, grid, drc,
+                                      c.partial.as<double>(), true, h->stream));
+  } else {
+    DAB_CUDA(h, contract_launch(c.xb[c.cur], c.n_loc, k, c.obs_loc.as<int>(), c.obs_val.as<double>(),
+                                c.has_sw ? c.obs_sw.as<double>() : nullptr,
+                                c.seg.as<long long>() + (size_t)cycle * tp * 3, ns, rows,
+                                c.partial.as<double>(), grid, true, h->stream));
+  }
   prof_mark(h, PROF_CONTRACT);
   const double r_inv = c.has_sw ? 1.0 : r_inv_of(c.cfg.obs_error_sd);
   if (stats_exchange_ready(c)) {
@@ -1013,6 +1080,7 @@ double* dab_cycler_stats_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cy
 void* dab_cycler_stream(dab_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 double* dab_cycler_background_ptr(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.xb[h->cyc.cur] : nullptr; }
 int dab_cycler_kernel_launches(dab_handle* h) { return h ? (int)h->launches : 0; }
+int dab_cycler_compact_contractions(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.n_compact : 0; }
 int dab_cycler_forecast_shape(dab_handle* h) { return (h && h->cyc.ready) ? h->cyc.l96_T * 10 + h->cyc.l96_chunks : 0; }
 
 // eig (K4) + transform (K5, fused halo exchange) + forecast (K1).  The analysis of this cycle is
@@ -1070,12 +1138,22 @@ static int cycler_update(dab_handle* h, int cycle, double* out_host, double* out
   const int S = c.cfg.n_steps;
   double* nxt = c.xb[c.cur ^ 1];
   const long long traj_stride = (long long)k * c.n_loc;
+  if (S == 0 || S > c.first_steps) c.yb_valid = false;
   if (S == 0) {
     DAB_CUDA(h, cudaMemcpy2DAsync(nxt, sizeof(double) * c.n_loc, xa, sizeof(double) * c.ld_e,
                                   sizeof(double) * c.n_loc, k, cudaMemcpyDeviceToDevice, h->stream));
   } else if (S <= c.first_steps) {
     int nl = 0;
-    DAB_CUDA(h, forecast_ext(h, c, c.ext[eb].as<double>(), nxt, out_traj, traj_stride, S, c.l96_T, c.l96_chunks, &nl));
+    ObsEmit emit;
+    bool emitted = false;
+    if (c.emit_ok) {
+      emit.loc = c.obs_loc.as<int>() + c.emit_loc_off; emit.row_start = c.row_start.as<int>();
+      emit.yb = c.yb.as<double>(); emit.ldy = c.ldy; emit.n_rows = (int)c.emit_rows;
+    }
+    c.yb_valid = false;
+    DAB_CUDA(h, forecast_ext(h, c, c.ext[eb].as<double>(), nxt, out_traj, traj_stride, S, c.l96_T, c.l96_chunks, &nl,
+                             c.emit_ok ? &emit : nullptr, &emitted));
+    c.yb_valid = emitted;
     h->launches += nl;
   } else {
     // long window on one rank: first chunk from the extended buffer, the rest periodic.

@@ -9,6 +9,18 @@ namespace dab {
 
 constexpr int kMaxRanks = 8;
 
+// Optional second output of the forecast kernels: the observed columns of the forecast, compact and in the cycler's
+// location order, Yb[k][ldy] -- what the contraction of the NEXT analysis reads (etkf_contract_dense.cu) instead of
+// gathering from the state.  Stationary networks only: the rows whose column lies in a tile's stored range [p, q)
+// are a contiguous run, found through `row_start` (first row with column >= 64 c).  yb == nullptr: off.
+struct ObsEmit {
+  const int* loc = nullptr;        // [n_rows] slab-local columns, ascending
+  const int* row_start = nullptr;  // [n_cols / 64 + 2]
+  double* yb = nullptr;
+  long long ldy = 0;
+  int n_rows = 0;
+};
+
 // K1  l96_forecast.cu
 int l96_max_steps_per_launch();
 // CTA shape code of the forecast kernel (`forced_T`): T alone = 8 points per thread; 1000 * c + T with
@@ -19,7 +31,7 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
                                 long long traj_stride, int sms, int forced_T /* 0 = heuristic */,
-                                cudaStream_t st);
+                                cudaStream_t st, const ObsEmit* emit = nullptr);
 
 // K1, persistent CTA-tile design  l96_forecast_v3.cu (shape code 30000 + steps per chunk)
 constexpr int kL96V3Code = 30000;
@@ -31,7 +43,8 @@ cudaError_t l96_v3_launch(const double* in, double* out, double* scratch0, doubl
                           unsigned* flags, unsigned epoch, unsigned long long* counter, unsigned long long* ctr_base,
                           long long n, int k, int n_steps, int chunk_steps,
                           double dt, double F, long long in_ld, long long out_ld, bool periodic,
-                          long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st);
+                          long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st,
+                          const ObsEmit* emit = nullptr);
 
 // K1, chains handed out inside the SM  l96_forecast_v6.cu (shape code 60000 + variant): one persistent 384-thread CTA
 // per SM; variant 0 = three 4-warp groups on 2048-point tiles, variant 1 = six 2-warp groups on 1024-point tiles; each
@@ -48,7 +61,7 @@ bool l96_v6_plan(long long n, int k, int n_steps, int ctas, int variant, L96V6Pl
 cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, const int* chains_dev, int grid,
                           int tile_stride, int chain_stride, int hist_t, int variant, long long n, int n_steps,
                           double dt, double F, long long in_ld, long long out_ld, bool periodic, long long in_base,
-                          long long in_lo, long long in_hi, cudaStream_t st);
+                          long long in_lo, long long in_hi, cudaStream_t st, const ObsEmit* emit = nullptr);
 
 // Lorenz-63 members [k][3]  l63_forecast.cu
 cudaError_t l63_forecast_launch(const double* x_in, double* x_out, double* traj, long long k, int n_steps,
@@ -73,6 +86,10 @@ struct StatsPush {
   int world;                             // <= 1: no exchange, results go to `stats`
   unsigned int* done_ctr;                // local, zero: CTAs of the launch that have pushed
 };
+// K3 on the compact Yb the forecast kernels emit  etkf_contract_dense.cu
+bool contract_dense_plan(long long n_rows, int k, int sms, int* grid_out, int* rc_out);
+cudaError_t contract_dense_launch(const double* Yb, long long ldy, int k, const double* obs_val, const double* obs_sw,
+                                  long long n_rows, int grid, int rc, double* partial, bool chain, cudaStream_t st);
 cudaError_t stats_reduce_launch(const double* partial, int n_part, int k, double r_inv, double* stats,
                                 const StatsPush* push /* nullable */, cudaStream_t st);
 cudaError_t stats_gather_launch(const unsigned long long* flags, unsigned long long seq, const double* slots,

@@ -4,6 +4,7 @@
 // "its output is visible" (== epoch of this launch).
 #pragma once
 #include "common.cuh"
+#include "kernels.h"
 
 namespace dab {
 
@@ -33,6 +34,7 @@ struct L96V2Args {
   unsigned long long* counter;        // job dispenser: monotonic over launches, this launch starts at ctr_base
   unsigned long long ctr_base;
   double h2, h3, h6, dt, h2F, dtF;    // RK4 coefficients as uniform operands (see l96_forecast.cu)
+  ObsEmit emit;                       // optional compact copy of the observed columns of the LAST chunk (kernels.h)
 };
 
 __device__ __forceinline__ unsigned v2_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

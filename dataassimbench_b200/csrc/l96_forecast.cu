@@ -41,6 +41,7 @@ struct L96Args {
   // (uniform registers): a DFMA with three distinct REGISTER operands issues every 3 cycles (two
   // register-file banks, tools/l96_probe2.cu: 65 % of the FP64 rate), with one uniform operand every 2.
   double h2, h3, h6, h2F, dtF;
+  ObsEmit emit;              // optional compact copy of the observed columns (kernels.h)
 };
 
 // -DDAB_L96_TRACE (debug builds, tools/build_timing.sh): every CTA records {start, loaded, computed,
@@ -76,6 +77,20 @@ l96_rk4_window_kernel(const L96Args a) {
 #ifdef DAB_L96_TRACE
   if (g_l96_trace && threadIdx.x == 0) g_l96_trace[8 * blockIdx.x + 4] = smid();
 #endif
+  // candidate rows of the compact observation copy (ObsEmit): the observation tables are static, so their columns are
+  // fetched now -- before the wait, behind the tile load -- and the store phase finds them in shared memory
+  int* s_cols = reinterpret_cast<int*>(stage + phys<P>(T * P));
+  int r_lo = 0, r_hi = 0;
+  if (a.emit.yb != nullptr) {
+    long long lo = tile_start, hi = tile_start + a.useful;
+    if (hi > a.n) hi = a.n;
+    if (hi > lo) {
+      r_lo = a.emit.row_start[lo >> 6]; r_hi = a.emit.row_start[((hi - 1) >> 6) + 1];
+      if (r_hi > a.emit.n_rows) r_hi = a.emit.n_rows;
+      if (r_hi - r_lo > T * P + 128) r_hi = r_lo + T * P + 128;      // cannot happen for one row per column
+      for (int r = r_lo + t; r < r_hi; r += T) s_cols[r - r_lo] = a.emit.loc[r];
+    }
+  }
   pdl_wait();                 // the input is the previous kernel's output (transform or forecast chunk)
   pdl_launch_dependents();
 
@@ -185,6 +200,13 @@ l96_rk4_window_kernel(const L96Args a) {
     const long long g = g0 + e;
     if (g >= out_lo && g < out_hi) out_row[g] = stage[phys<P>(e)];
   }
+  if (a.emit.yb != nullptr) {
+    double* yb_row = a.emit.yb + (long long)member * a.emit.ldy;
+    for (int r = r_lo + t; r < r_hi; r += T) {
+      const long long c = s_cols[r - r_lo];
+      if (c >= out_lo && c < out_hi) yb_row[r] = stage[phys<P>((int)(c - g0))];
+    }
+  }
   L96_TRACE(3);
 }
 
@@ -199,16 +221,17 @@ namespace dab {
 // ------------------------------------------------------------------------------------------
 // Host-side launch planning.  A launch advances at most `max_steps_per_launch` steps (halo =
 // 12 points per step must stay a modest fraction of the tile); longer windows are chunked.
-static size_t l96_smem_bytes(int T, int P) {
+// + the tile's candidate observation columns (ObsEmit): at most W + 128 ints, fetched while the tile loads
+static size_t l96_smem_bytes(int T, int P, bool emit) {
   const int W = T * P;
-  return ((size_t)(W + W / P) + 6 * (size_t)T) * sizeof(double);
+  return ((size_t)(W + W / P) + 6 * (size_t)T) * sizeof(double) + (emit ? (size_t)(W + 128) * sizeof(int) : 0);
 }
 
 int l96_max_steps_per_launch() { return 32; }
 
 template <int P, int MAXT, int MINB>
 static cudaError_t launch_pb(const L96Args& a, int k, int T, bool periodic, cudaStream_t st) {
-  const size_t smem = l96_smem_bytes(T, P);
+  const size_t smem = l96_smem_bytes(T, P, a.emit.yb != nullptr);
   dim3 grid((unsigned)((long long)a.tiles_per_member * k));
   if (periodic) {
     cudaFuncSetAttribute(l96_rk4_window_kernel<P, true, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -271,7 +294,7 @@ static bool l96_plan(long long n, int k, int steps, int sms, int P, int t_max, i
 cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, long long n, int k,
                                 int n_steps, double dt, double F, long long in_ld, long long out_ld,
                                 bool periodic, long long in_base, long long in_lo, long long in_hi,
-                                long long traj_stride, int sms, int forced_T, cudaStream_t st) {
+                                long long traj_stride, int sms, int forced_T, cudaStream_t st, const ObsEmit* emit) {
   // CTA shape code: plain T = 8 points per thread; 1000 * c + T with c = 12 / 16 points per thread,
   // c = 17: 16 points per thread in the 170-register build (kernels.h: l96_shape_code).
   if (const char* ev = getenv("DAB_L96_T")) {            // experiment/test knob: force the CTA shape
@@ -301,6 +324,7 @@ cudaError_t l96_forecast_launch(const double* in, double* out, double* traj, lon
   a.n_steps = n_steps; a.halo_l = 8 * n_steps; a.useful = useful; a.tiles_per_member = tiles;
   a.dt = dt; a.F = F;
   a.h2 = 0.5 * dt; a.h3 = dt / 3.0; a.h6 = dt / 6.0; a.h2F = a.h2 * F; a.dtF = dt * F;
+  if (emit != nullptr) a.emit = *emit;
   if (P == 12) return launch_p<12>(a, k, T, periodic, dense, st);
   if (P == 16) return launch_p<16>(a, k, T, periodic, dense, st);
   return launch_p<8>(a, k, T, periodic, dense, st);

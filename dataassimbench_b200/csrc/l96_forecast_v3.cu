@@ -233,6 +233,9 @@ l96_v3_kernel(const L96V2Args a) {
         if (256 * i >= e_lo && 256 * i < e_hi)
           *reinterpret_cast<double2*>(dst + 256 * i) = *reinterpret_cast<const double2*>(srcs + 288 * i);
       }
+      if (last && a.emit.yb != nullptr)
+        emit_observed(a.emit.loc, a.emit.row_start, a.emit.n_rows, a.emit.yb + (long long)cur.m * a.emit.ldy, st_out,
+                      [](int e) { return e + 2 * (e >> 4); }, cur.g0, cur.p, cur.q, t, T);
     }
     __syncthreads();            // every thread's stores are issued (and st_out, the edge arrays are free again)
     if (t == 0) v3_release(a, n);   // the barrier above ordered the CTA's stores before thread 0's fence
@@ -278,8 +281,10 @@ cudaError_t l96_v3_launch(const double* in, double* out, double* scratch0, doubl
                           unsigned* flags, unsigned epoch, unsigned long long* counter, unsigned long long* ctr_base,
                           long long n, int k, int n_steps, int chunk_steps,
                           double dt, double F, long long in_ld, long long out_ld, bool periodic,
-                          long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st) {
+                          long long in_base, long long in_lo, long long in_hi, int sms, cudaStream_t st,
+                          const ObsEmit* emit) {
   L96V2Args a{};
+  if (emit != nullptr) a.emit = *emit;
   a.in = in; a.out = out; a.scratch[0] = scratch0; a.scratch[1] = scratch1;
   a.in_ld = in_ld; a.out_ld = out_ld; a.scr_ld = scr_ld;
   a.in_base = in_base; a.in_lo = (int)in_lo; a.in_hi = (int)in_hi;

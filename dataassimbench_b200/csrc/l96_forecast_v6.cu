@@ -63,6 +63,7 @@ struct L96V6Args {
   int n_steps;
   int hist_t;                   // the thread whose last two points are the next tile's left boundary
   double h2, h3, h6, dt, h2F, dtF;    // RK4 coefficients as uniform operands (see l96_forecast.cu)
+  ObsEmit emit;                 // optional compact copy of the observed columns (kernels.h)
 };
 
 __device__ __forceinline__ unsigned v6_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -104,6 +105,17 @@ __device__ __forceinline__ void v6_prefetch(const L96V6Args& a, const int4 jb, d
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// candidate rows of a tile's stored range [p, q) = [jb.z, jb.w): at most the tile's width + 126
+__device__ __forceinline__ void v6_rows(const ObsEmit& em, const int4 jb, int* lo, int* hi) {
+  int l = 0, h = 0;
+  if (jb.w > jb.z) {
+    l = __ldg(em.row_start + (jb.z >> 6));
+    h = __ldg(em.row_start + ((jb.w - 1) >> 6) + 1);
+    if (h > em.n_rows) h = em.n_rows;
+  }
+  *lo = l; *hi = h;
+}
+
 template <int TG, int G>
 __global__ void __launch_bounds__(G * TG, 1)
 l96_v6_kernel(const L96V6Args a) {
@@ -141,6 +153,14 @@ l96_v6_kernel(const L96V6Args a) {
   if (ti < 0) return;
   int4 cur = __ldg(tiles + ti);
   v6_prefetch<TG>(a, cur, st_in, t);
+  // compact observation copy (ObsEmit): the candidate rows of a tile -- those of the 64-column blocks its stored range
+  // [p, q) meets -- are known one tile ahead (r_lo, r_hi: fetched next to the tile's descriptor), and their columns are
+  // copied into shared memory while the tile computes; thread t copies and later reads rows r_lo + t + T i only, so
+  // its own cp.async.wait_group is all the ordering the copy needs
+  const bool emit = a.emit.yb != nullptr;
+  int* s_cols = reinterpret_cast<int*>(smem + (size_t)V6_G * V6_GROUP_DOUBLES) + grp * (v6_tile(TG) + 128);
+  int r_lo = 0, r_hi = 0, nr_lo = 0, nr_hi = 0;
+  if (emit) v6_rows(a.emit, cur, &r_lo, &r_hi);
 
   for (int n_local = 0;; ++n_local) {
     // a barrier at the top of every pass tells ptxas the warps are converged in this loop, whose trip count differs
@@ -167,6 +187,11 @@ l96_v6_kernel(const L96V6Args a) {
     for (int i = 0; i < P; i += 2) {
       const double2 v = *reinterpret_cast<const double2*>(st_in + 18 * t + i);
       s[i] = v.x; s[i + 1] = v.y;
+    }
+    if (emit) {
+      for (int r = r_lo + t; r < r_hi; r += T)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(v6_smem(s_cols + (r - r_lo))), "l"(a.emit.loc + r) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const int ti_next = s_nxt[grp][0], te_next = s_nxt[grp][1];
     int4 nxt = cur;
@@ -196,7 +221,10 @@ l96_v6_kernel(const L96V6Args a) {
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
         v6_group_sync<TG>(grp);
-        if (step == 0 && st == 1 && ti_next >= 0) v6_prefetch<TG>(a, nxt, st_in, t);   // every thread left st_in a barrier ago
+        if (step == 0 && st == 1 && ti_next >= 0) {
+          v6_prefetch<TG>(a, nxt, st_in, t);   // every thread left st_in a barrier ago
+          if (emit) v6_rows(a.emit, nxt, &nr_lo, &nr_hi);
+        }
         const double2 L = *reinterpret_cast<const double2*>(Lp + st * STG);
         const double R = e_first[buf * T + tr];
         buf ^= 1;
@@ -250,9 +278,18 @@ l96_v6_kernel(const L96V6Args a) {
         if (2 * T * i >= e_lo && 2 * T * i < e_hi)
           *reinterpret_cast<double2*>(dst + 2 * T * i) = *reinterpret_cast<const double2*>(srcs + (2 * T + T / 4) * i);
       }
+      if (emit) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");     // the columns (and, long since, the next tile)
+        double* yb_row = a.emit.yb + (long long)(cur.x >> 1) * a.emit.ldy;
+        for (int r = r_lo + t; r < r_hi; r += T) {
+          const int c = s_cols[r - r_lo];
+          const int e = c - cur.y;
+          if (c >= cur.z && c < cur.w) yb_row[r] = st_out[e + 2 * (e >> 4)];
+        }
+      }
     }
     if (ti_next < 0) break;
-    cur = nxt; ti = ti_next; te = te_next;
+    cur = nxt; ti = ti_next; te = te_next; r_lo = nr_lo; r_hi = nr_hi;
   }
 }
 
@@ -339,10 +376,11 @@ bool l96_v6_plan(long long n, int k, int n_steps, int ctas, int variant, L96V6Pl
 
 template <int TG, int G>
 static cudaError_t v6_launch_t(const L96V6Args& a, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)G * (size_t)v6_group_doubles(TG) * sizeof(double);
+  const size_t smem_max = (size_t)G * ((size_t)v6_group_doubles(TG) * sizeof(double) + (size_t)(v6_tile(TG) + 128) * sizeof(int));
+  const size_t smem = a.emit.yb != nullptr ? smem_max : (size_t)G * (size_t)v6_group_doubles(TG) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(l96_v6_kernel<TG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(l96_v6_kernel<TG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -352,8 +390,9 @@ static cudaError_t v6_launch_t(const L96V6Args& a, int grid, cudaStream_t st) {
 cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, const int* chains_dev, int grid,
                           int tile_stride, int chain_stride, int hist_t, int variant, long long n, int n_steps,
                           double dt, double F, long long in_ld, long long out_ld, bool periodic, long long in_base,
-                          long long in_lo, long long in_hi, cudaStream_t st) {
+                          long long in_lo, long long in_hi, cudaStream_t st, const ObsEmit* emit) {
   L96V6Args a{};
+  if (emit != nullptr) a.emit = *emit;
   a.in = in; a.out = out;
   a.in_ld = in_ld; a.out_ld = out_ld; a.in_base = in_base;
   a.in_lo = (int)in_lo; a.in_hi = (int)in_hi;

@@ -252,6 +252,10 @@ DAB_API int dab_cycler_kernel_launches(dab_handle* h);
  * (shape code: CTA width for 8 points per thread, 1000 * c + width with c = 12/16/17 for 12 / 16 /
  * 16-in-170-registers points per thread; 0 = untuned heuristic). */
 DAB_API int dab_cycler_forecast_shape(dab_handle* h);           /* kernels launched since setup */
+/* How many contractions since setup read the compact observation-space ensemble the forecast kernels wrote
+ * (stationary networks; DAB_YB_EMIT=0 at setup switches the route off) instead of gathering H Xb from the state
+ * (ETKF._apply_obsop, dabench/dacycler/_etkf.py:82-92). */
+DAB_API int dab_cycler_compact_contractions(dab_handle* h);
 
 /* Measurement aids (bench.py): per-kernel CUDA-event timing on the cycler's stream.
  * ms_out[5]/count_out[5]: contraction, reduction, eigensolver, transform, forecast. */

@@ -570,3 +570,29 @@ def test_cycler_scores_analyses_on_device(H, N, k):
     got = metrics.rmse_from_sse(sse.cpu().numpy(), N)
     ref = np.array([metrics.rmse(out[c].numpy().mean(axis=0), truth[c]) for c in range(n_cycles)])
     assert np.max(np.abs(got - ref) / ref) < 1e-12
+
+
+@pytest.mark.parametrize("forced", [("DAB_L96_V6", "1"), ("DAB_L96_V6", "2"), ("DAB_L96_V3", "20"), ("DAB_L96_T", "256"), None])
+@pytest.mark.parametrize("N,k,n_obs", [(8192, 16, 2500), (40000, 64, 40000), (65536, 8, 3)])
+def test_cycler_compact_yb_matches_gather(H, N, k, n_obs, forced, monkeypatch):
+    """Stationary networks: the forecast kernels also write the observed columns into a compact Yb and the next
+    contraction reads that (etkf_contract_dense.cu) instead of gathering from the state.  Same experiment with the
+    route switched off (DAB_YB_EMIT=0, the default: measured slower at C3, profiles/yb_emit_r02.md): the summation
+    order of the statistics differs, nothing else."""
+    n_cycles, S, sd, rho = 4, 20, 1.0, 1.02
+    case = cycler_case(N, k, n_obs, n_cycles, S, sd, rho, True, seed=N + k + n_obs)
+    if forced is not None:
+        if forced[0] != "DAB_L96_V6":
+            monkeypatch.setenv("DAB_L96_V6", "0")
+        if forced[0] == "DAB_L96_T":
+            monkeypatch.setenv("DAB_L96_V3", "0")
+        monkeypatch.setenv(*forced)
+    monkeypatch.setenv("DAB_YB_EMIT", "0")
+    base, base_final, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, True)
+    assert H.cycler_compact_contractions() == 0
+    monkeypatch.setenv("DAB_YB_EMIT", "1")
+    out, final, _ = run_gpu_cycler(H, case, N, k, n_cycles, sd, rho, True)
+    # the first background came from set_state; networks of < 64 unsorted rows keep their order and the gather
+    assert H.cycler_compact_contractions() >= (n_cycles - 2 if n_obs >= 64 else 0)
+    assert np.all(np.isfinite(base))
+    assert rel_err(out, base) < 1e-11 and rel_err(final, base_final) < 1e-11
