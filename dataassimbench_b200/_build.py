@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdab_b200.so")
-SOURCES = ["engine.cu", "l96_forecast.cu", "l96_forecast_v3.cu", "l96_forecast_v6.cu", "l63_forecast.cu", "etkf_contract.cu", "etkf_contract_dense.cu", "etkf_eig.cu", "etkf_ns.cu", "etkf_transform.cu", "etkf_batched.cu", "var3d_cg.cu", "fp64_peak.cu"]
+SOURCES = ["engine.cu", "l96_forecast.cu", "l96_forecast_v3.cu", "l96_forecast_v6.cu", "l63_forecast.cu", "sqg_forecast.cu", "etkf_contract.cu", "etkf_contract_dense.cu", "etkf_eig.cu", "etkf_ns.cu", "etkf_transform.cu", "etkf_batched.cu", "var3d_cg.cu", "fp64_peak.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

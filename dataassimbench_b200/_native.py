@@ -57,6 +57,8 @@ _SIGNATURES = {
     "dab_set_pdl": (C.c_int, [C.c_int]),
     "dab_l96_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, _P]),
     "dab_l63_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "dab_sqg_setup": (C.c_int, [_P, _P]),
+    "dab_sqg_forecast_c128": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
     "dab_observe_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, C.c_int, _P, _I64, _P, _P, _P]),
     "dab_var3d_analysis_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, C.c_double, _P]),
@@ -98,6 +100,14 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+
+
+class SqgConfig(C.Structure):
+    """dab_sqg_config (include/dab_b200.h)."""
+    _fields_ = [("n", C.c_int32), ("ekman", C.c_int32), ("symmetric", C.c_int32), ("reserved", C.c_int32),
+                ("delta_t", C.c_double), ("inv_tdiab", C.c_double), ("r", C.c_double),
+                ("kx", C.c_void_p), ("ly", C.c_void_p), ("hovermu", C.c_void_p), ("tanhmu", C.c_void_p),
+                ("sinhmu", C.c_void_p), ("ksqlsq", C.c_void_p), ("hyperdiff", C.c_void_p), ("pvspec_eq", C.c_void_p)]
 
 
 def load():
@@ -171,6 +181,25 @@ class Handle:
     def l63_forecast(self, x_in, x_out, traj, k, n_steps, dt, sigma=10.0, rho=28.0, beta=8.0 / 3.0, stream=None):
         self._check(self._lib.dab_l63_forecast_f64(self._h, _ptr(x_in), _ptr(x_out), _ptr(traj), k, n_steps,
                                                    dt, sigma, rho, beta, _ptr(stream)))
+
+    def sqg_setup(self, n, delta_t, inv_tdiab, r, ekman, symmetric, kx, ly, hovermu, tanhmu, sinhmu, ksqlsq,
+                  hyperdiff, pvspec_eq):
+        """Tables of the surface-QG generator (host arrays; copied to the device by the call)."""
+        import numpy as np
+        f8 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        arrs = [f8(kx), f8(ly), f8(hovermu), f8(tanhmu), f8(sinhmu), f8(ksqlsq), f8(hyperdiff),
+                np.ascontiguousarray(np.asarray(pvspec_eq, dtype=np.complex128))]
+        nk = n // 2 + 1
+        assert arrs[0].shape == (nk,) and arrs[1].shape == (n,) and arrs[7].shape == (2, n, nk)
+        assert all(a.shape == (n, nk) for a in arrs[2:7])
+        cfg = SqgConfig(n=n, ekman=int(ekman), symmetric=int(symmetric), reserved=0, delta_t=delta_t,
+                        inv_tdiab=inv_tdiab, r=r, **{name: a.ctypes.data for name, a in zip(
+                            ("kx", "ly", "hovermu", "tanhmu", "sinhmu", "ksqlsq", "hyperdiff", "pvspec_eq"), arrs)})
+        self._check(self._lib.dab_sqg_setup(self._h, C.byref(cfg)))
+
+    def sqg_forecast(self, spec_in, spec_out, traj_grid, members, n_steps, stream=None):
+        self._check(self._lib.dab_sqg_forecast_c128(self._h, _ptr(spec_in), _ptr(spec_out), _ptr(traj_grid),
+                                                    int(members), int(n_steps), stream))
 
     def obs_gather(self, X, idx, mask, Yb, N, k, n_y, stream=None):
         self._check(self._lib.dab_obs_gather_f64(self._h, _ptr(X), _ptr(idx), _ptr(mask), _ptr(Yb),

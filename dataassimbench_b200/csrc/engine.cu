@@ -149,6 +149,7 @@ struct dab_handle {
   DevBuf ns_ws;                                          // Newton-Schulz scratch of K4 (L2-resident)
   V2Work v2;                                             // persistent forecast kernel: scratch, flags, dispenser
   V6Work v6;                                             // chained forecast kernel: tile and chain tables
+  SqgState* sqg = nullptr;                               // surface-QG generator: tables, DFT matrices, workspaces
   int eig_method = kEigAuto;
   unsigned long long xchg_timeout_ns = 10000000000ull;   // statistics exchange: give up on a lost peer (DAB_XCHG_TIMEOUT_S, 0 = never)
   DevBuf b_x0, b_val, b_idx, b_pad, b_rho, b_out, b_mean, b_fin;   // batched small-problem path
@@ -387,6 +388,7 @@ int dab_destroy(dab_handle* h) {
   h->s_partial.release(); h->s_stats.release(); h->s_T.release(); h->ns_ws.release(); h->s_flag.release(); h->s_cg.release(); h->s_src.release(); h->s_off.release();
   h->v2.release();
   h->v6.release();
+  sqg_destroy(h->sqg); h->sqg = nullptr;
   h->b_x0.release(); h->b_val.release(); h->b_idx.release(); h->b_pad.release(); h->b_rho.release();
   h->b_out.release(); h->b_mean.release(); h->b_fin.release();
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
@@ -479,6 +481,36 @@ int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_out, doubl
   DAB_CUDA(h, l63_forecast_launch(x_in, x_out, traj, k, n_steps, dt, sigma, rho, beta,
                                   static_cast<cudaStream_t>(stream)));
   h->launches++;
+  return 0;
+}
+
+int dab_sqg_setup(dab_handle* h, const dab_sqg_config* cfg) {
+  DAB_ARG(h, h != nullptr && cfg != nullptr);
+  DAB_ARG(h, cfg->n >= 4 && cfg->n % 4 == 0 && cfg->n <= 4096);
+  DAB_ARG(h, cfg->kx && cfg->ly && cfg->hovermu && cfg->tanhmu && cfg->sinhmu && cfg->ksqlsq && cfg->hyperdiff && cfg->pvspec_eq);
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  DAB_CUDA(h, cudaDeviceSynchronize());
+  sqg_destroy(h->sqg); h->sqg = nullptr;
+  SqgTables t;
+  t.n = cfg->n; t.ekman = cfg->ekman; t.symmetric = cfg->symmetric;
+  t.delta_t = cfg->delta_t; t.inv_tdiab = cfg->inv_tdiab; t.r = cfg->r;
+  t.kx = cfg->kx; t.ly = cfg->ly; t.hovermu = cfg->hovermu; t.tanhmu = cfg->tanhmu; t.sinhmu = cfg->sinhmu;
+  t.ksqlsq = cfg->ksqlsq; t.hyperdiff = cfg->hyperdiff; t.pvspec_eq = cfg->pvspec_eq;
+  DAB_CUDA(h, sqg_setup(&h->sqg, t));
+  return 0;
+}
+
+int dab_sqg_forecast_c128(dab_handle* h, const double* spec_in, double* spec_out, double* traj_grid, int members,
+                          int n_steps, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  if (h->sqg == nullptr) return fail(h, -1, "dab_sqg_forecast_c128: call dab_sqg_setup first");
+  DAB_ARG(h, members >= 0 && n_steps >= 0);
+  DAB_ARG(h, members == 0 || (spec_in != nullptr && spec_out != nullptr));
+  if (members == 0) return 0;
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  int nl = 0;
+  DAB_CUDA(h, sqg_forecast(h->sqg, spec_in, spec_out, traj_grid, members, n_steps, static_cast<cudaStream_t>(stream), &nl));
+  h->launches += nl;
   return 0;
 }
 

@@ -67,6 +67,21 @@ cudaError_t l96_v6_launch(const double* in, double* out, const int* tiles_dev, c
 cudaError_t l63_forecast_launch(const double* x_in, double* x_out, double* traj, long long k, int n_steps,
                                 double dt, double sigma, double rho, double beta, cudaStream_t st);
 
+// Surface-QG turbulence members [k][2][N][N/2+1] complex  sqg_forecast.cu.  Every table is the caller's (host
+// pointers, copied at setup): the Python mirror builds them as SQGTurb.__init__ does (dabench/data/_sqgturb.py:83-248).
+struct SqgTables {
+  int n = 0, ekman = 0, symmetric = 1;
+  double delta_t = 0.0, inv_tdiab = 0.0, r = 0.0;
+  const double *kx = nullptr, *ly = nullptr;                                  // [N/2+1], [N]
+  const double *hovermu = nullptr, *tanhmu = nullptr, *sinhmu = nullptr, *ksqlsq = nullptr, *hyperdiff = nullptr;   // [N][N/2+1]
+  const double* pvspec_eq = nullptr;                                          // [2][N][N/2+1] complex
+};
+struct SqgState;
+cudaError_t sqg_setup(SqgState** out, const SqgTables& t);
+void sqg_destroy(SqgState* s);
+cudaError_t sqg_forecast(SqgState* s, const double* spec_in, double* spec_out, double* traj, int members, int n_steps,
+                         cudaStream_t st, int* n_launches);
+
 // K2/K3  etkf_contract.cu
 int contract_k8(int k);
 int contract_grid(long long n_rows, int sms);

@@ -1,0 +1,458 @@
+// Surface-QG turbulence ensemble forecast behind the forecast plugin point (second half).
+//
+// Replaces, for all members at once, SQGTurb.integrate -> lax.scan(SQGTurb._rk4) -> SQGTurb.rhs
+// (dabench/data/_sqgturb.py:441-504, :345-364, :506-548) with its helpers _invert (:258-270), _specpad (:293-309),
+// _xyderiv_dealias (:334-343), _spectrunc (:311-325) and the final `ifft2(values)` (:496).
+//
+// Design.  The state is tiny (2 x N x (N/2+1) complex, N = 96 by default) and every RK stage needs ten 2-D real FFTs
+// on the 3N/2 dealiasing grid of which only N x (N/2+1) inputs are non-zero and only N x N/2 outputs are kept.  At
+// that size a radix FFT is latency- and launch-bound, while the pruned transforms written as products with constant
+// DFT matrices are FP64 GEMMs with all members batched into the long dimension -- work the FP64 pipe does at its
+// peak rate.  Per RK stage:
+//   prep      spectral state -> the 8 fields i k psi, i l psi, i k q, i l q (two levels each) on the non-zero block
+//             of the padded spectrum, including the 2.25 factor and the conjugated Nyquist column       (elementwise)
+//   gemm b    inverse transform along y:  [2M x 2N] constant  x  [2N x members 8 (N/2+1)]
+//   gemm c    inverse c2r transform along x, per (member, field):  [M x (N/2+1)] x [(N/2+1) x M], real and imaginary
+//             parts as two accumulated products
+//   jacobian  psi_x q_y - psi_y q_x on the M x M grid                                                    (elementwise)
+//   gemm d    forward r2c along x, truncated to N/2 columns:  [members 2 M x M] x [M x N]
+//   gemm e    forward transform along y, truncated to N rows:  [2N x M] x [M x N/2], two accumulated products
+//   update    tendency (thermal relaxation, Ekman terms, -J), RK4 bookkeeping in the reference's order, hyperdiffusion
+//             factor after the fourth stage, and the next stage's prep in the same kernel                  (elementwise)
+// All members of an ensemble share every launch.  The GEMM is one kernel (64 x 64 x 16 tiles, 4 x 4 outputs per
+// thread, register prefetch of the next k-tile): FP64 FMA is the bound, shared-memory traffic is 1 LDS.128 per 8
+// DFMAs.  M = 3N/2 and every table come from the caller (the Python mirror builds them the way the reference's
+// __init__ does, including its float32 / complex64 casts), so the kernels hold no physics constants.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dab {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ batched GEMM
+// C[b] = A1[b] B1[b] (+ A2[b] B2[b]); every operand row-major with unit column stride, its own row and batch stride
+struct GemmOp { const double* p; long long rs, bs; };
+struct GemmArgs {
+  GemmOp A[2], B[2];
+  double* C; long long c_rs, c_bs;
+  int m, n, K, nseg;
+};
+
+constexpr int GB = 64, GK = 16, GLD = GB + 2;
+
+__global__ void __launch_bounds__(256)
+sqg_gemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) double As[GK][GLD];
+  __shared__ __align__(16) double Bs[GK][GLD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * GB, j0 = blockIdx.x * GB;
+  const long long b = blockIdx.z;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  // loader coordinates: A tile 64 rows x 16 k (k fastest), B tile 16 k x 64 columns (column fastest)
+  const int a_k = tid & 15, a_i = tid >> 4;       // + 16 rows per pass
+  const int b_j = tid & 63, b_k = tid >> 6;       // + 4 k per pass
+  const int kt = (g.K + GK - 1) / GK;
+  const int total = kt * g.nseg;
+  double ra[4], rb[4];
+  auto fetch = [&](int it) {
+    const int seg = it / kt, k0 = (it - seg * kt) * GK;
+    const double* A = g.A[seg].p + b * g.A[seg].bs;
+    const double* B = g.B[seg].p + b * g.B[seg].bs;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int i = i0 + a_i + 16 * p, k = k0 + a_k;
+      ra[p] = (i < g.m && k < g.K) ? A[(long long)i * g.A[seg].rs + k] : 0.0;
+      const int kb = k0 + b_k + 4 * p, j = j0 + b_j;
+      rb[p] = (kb < g.K && j < g.n) ? B[(long long)kb * g.B[seg].rs + j] : 0.0;
+    }
+  };
+  fetch(0);
+  for (int it = 0; it < total; ++it) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { As[a_k][a_i + 16 * p] = ra[p]; Bs[b_k + 4 * p][b_j] = rb[p]; }
+    __syncthreads();
+    if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][4 * ty]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][4 * ty + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx + 2]);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+  }
+  double* C = g.C + b * g.c_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i0 + 4 * ty + i;
+    if (r >= g.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j0 + 4 * tx + j;
+      if (c < g.n) C[(long long)r * g.c_rs + c] = acc[i][j];
+    }
+  }
+}
+
+cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, GemmOp B1, double* C, long long c_rs,
+                 long long c_bs, const GemmOp* A2 = nullptr, const GemmOp* B2 = nullptr) {
+  GemmArgs g{};
+  g.A[0] = A1; g.B[0] = B1; g.nseg = 1;
+  if (A2 != nullptr) { g.A[1] = *A2; g.B[1] = *B2; g.nseg = 2; }
+  g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.m = m; g.n = n; g.K = K;
+  dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB), (unsigned)batch);
+  sqg_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ elementwise kernels
+struct SqgDev {
+  int N, NK, M, nm;                  // grid, N/2+1, 3N/2, members
+  int ekman, symmetric;
+  double dt, inv_tdiab, r;
+  const double *kx, *ly;             // [NK], [N]: imaginary parts of ik_pad / il_pad on the non-zero block
+  const double *hovermu, *tanhmu, *sinhmu, *ksqlsq, *hyperdiff;   // [N][NK]
+  const double2* pveq;               // [2][N][NK]
+  double2 *x, *xs, *acc;             // state, stage state, RK accumulator: [nm][2][N][NK]
+  double* spec8;                     // [2 (re, im)][N][nm][8][NK]
+  const double* jst;                 // [nm][2][2N][N/2]
+  double* st2;                       // nullable: [2][N][nm][2][NK] new state for the trajectory transform
+};
+
+__device__ __forceinline__ double2 cmul_r(double a, double2 z) { return make_double2(a * z.x, a * z.y); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cdiv_r(double2 z, double a) { return make_double2(z.x / a, z.y / a); }
+
+// _invert, _sqgturb.py:258-270, at one wavenumber
+__device__ __forceinline__ void sqg_invert(const SqgDev& d, int rc, double2 q0, double2 q1, double2* p0, double2* p1) {
+  const double hov = d.hovermu[rc], th = d.tanhmu[rc], sh = d.sinhmu[rc];
+  *p0 = cmul_r(hov, csub(cdiv_r(q1, sh), cdiv_r(q0, th)));
+  *p1 = cmul_r(hov, csub(cdiv_r(q1, th), cdiv_r(q0, sh)));
+}
+
+// the non-zero block of ik_pad * specpad(z), il_pad * specpad(z) at (r, c): 2.25 z (conjugated in the Nyquist
+// column, _sqgturb.py:304-308) times i kx / i ly
+__device__ __forceinline__ void sqg_store_fields(const SqgDev& d, int m, int r, int c, int which0, int lev, double2 z) {
+  double2 v = make_double2(2.25 * z.x, 2.25 * z.y);
+  if (c == d.NK - 1) v.y = -v.y;
+  const double kx = d.kx[c], ly = d.ly[r];
+  const long long ld = (long long)d.nm * 8 * d.NK;
+  const long long im_off = (long long)d.N * ld;
+  const long long base = (long long)r * ld + ((long long)m * 8) * d.NK + c;
+  const long long fx = base + (long long)(which0 * 2 + lev) * d.NK, fy = base + (long long)((which0 + 1) * 2 + lev) * d.NK;
+  d.spec8[fx] = -kx * v.y; d.spec8[fx + im_off] = kx * v.x;      // i kx (a + i b) = -kx b + i kx a
+  d.spec8[fy] = -ly * v.y; d.spec8[fy + im_off] = ly * v.x;
+}
+
+// stage: -1 = first prep of a forecast (xs = x); 0..3 = finish RK stage `stage` from the Jacobian in jst, then
+// prepare the next stage (do_prep = 0 after the very last stage)
+__global__ void __launch_bounds__(128)
+sqg_stage_kernel(const SqgDev d, int stage, int do_prep) {
+  const long long per = (long long)d.N * d.NK;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * d.nm) return;
+  const int m = (int)(idx / per);
+  const int rc = (int)(idx - (long long)m * per);
+  const int r = rc / d.NK, c = rc - r * d.NK;
+  const long long i0 = ((long long)m * 2) * per + rc, i1 = i0 + per;
+  double2 s0, s1;                                           // the state the next rhs is evaluated at
+  if (stage < 0) {
+    s0 = d.x[i0]; s1 = d.x[i1];
+    d.xs[i0] = s0; d.xs[i1] = s1;
+  } else {
+    const double2 x0 = d.x[i0], x1 = d.x[i1], e0 = d.xs[i0], e1 = d.xs[i1];
+    // Jacobian spectrum, truncated (_spectrunc, :311-325): the Nyquist column is zero
+    double2 j0 = make_double2(0.0, 0.0), j1 = j0;
+    const int Nh = d.N / 2;
+    if (c < Nh) {
+      const long long jb = (((long long)m * 2) * 2 * d.N + r) * Nh + c, lev = (long long)2 * d.N * Nh, im = (long long)d.N * Nh;
+      j0 = make_double2(d.jst[jb], d.jst[jb + im]);
+      j1 = make_double2(d.jst[jb + lev], d.jst[jb + lev + im]);
+    }
+    // rhs, :530-545
+    double2 t0 = csub(cmul_r(d.inv_tdiab, csub(d.pveq[rc], e0)), j0);
+    double2 t1 = csub(cmul_r(d.inv_tdiab, csub(d.pveq[per + rc], e1)), j1);
+    if (d.ekman) {
+      double2 p0, p1;
+      sqg_invert(d, rc, e0, e1, &p0, &p1);
+      const double rk = d.r * d.ksqlsq[rc];
+      t0 = cadd(t0, cmul_r(rk, p0));
+      if (d.symmetric) t1 = cadd(t1, cmul_r(-1.0 * rk, p1));
+    }
+    const double2 k0 = cmul_r(d.dt, t0), k1 = cmul_r(d.dt, t1);
+    // _rk4, :345-364: y = x + (k1 + 2 k2 + 2 k3 + k4) / 6, summed left to right
+    if (stage == 0) {
+      d.acc[i0] = k0; d.acc[i1] = k1;
+      s0 = cadd(x0, cmul_r(0.5, k0)); s1 = cadd(x1, cmul_r(0.5, k1));
+    } else if (stage < 3) {
+      d.acc[i0] = cadd(d.acc[i0], cmul_r(2.0, k0)); d.acc[i1] = cadd(d.acc[i1], cmul_r(2.0, k1));
+      const double w = stage == 1 ? 0.5 : 1.0;
+      s0 = cadd(x0, cmul_r(w, k0)); s1 = cadd(x1, cmul_r(w, k1));
+    } else {
+      const double hd = d.hyperdiff[rc];
+      s0 = cmul_r(hd, cadd(x0, cdiv_r(cadd(d.acc[i0], k0), 6.0)));
+      s1 = cmul_r(hd, cadd(x1, cdiv_r(cadd(d.acc[i1], k1), 6.0)));
+      d.x[i0] = s0; d.x[i1] = s1;
+      if (d.st2 != nullptr) {
+        const long long ld = (long long)d.nm * 2 * d.NK, im = (long long)d.N * ld;
+        const long long o = (long long)r * ld + ((long long)m * 2) * d.NK + c;
+        d.st2[o] = s0.x; d.st2[o + im] = s0.y;
+        d.st2[o + d.NK] = s1.x; d.st2[o + d.NK + im] = s1.y;
+      }
+    }
+    d.xs[i0] = s0; d.xs[i1] = s1;
+  }
+  if (!do_prep) return;
+  double2 p0, p1;
+  sqg_invert(d, rc, s0, s1, &p0, &p1);
+  sqg_store_fields(d, m, r, c, 0, 0, p0);
+  sqg_store_fields(d, m, r, c, 0, 1, p1);
+  sqg_store_fields(d, m, r, c, 2, 0, s0);
+  sqg_store_fields(d, m, r, c, 2, 1, s1);
+}
+
+// F [nm][8][M][M] (field = which * 2 + level) -> J [nm][2][M][M] = psi_x q_y - psi_y q_x
+__global__ void __launch_bounds__(256)
+sqg_jacobian_kernel(const double* __restrict__ F, double* __restrict__ J, long long mm, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long ml = idx / mm, p = idx - ml * mm;
+  const long long m = ml >> 1, lev = ml & 1;
+  const double* f = F + (m * 8 + lev) * mm + p;
+  J[idx] = f[0] * f[6 * mm] - f[2 * mm] * f[4 * mm];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+struct SqgState {
+  int N = 0, NK = 0, M = 0;
+  SqgDev dev{};
+  std::vector<void*> owned;            // tables and constant matrices
+  double *Wb = nullptr, *Cc = nullptr, *Sc = nullptr, *Df = nullptr, *We1 = nullptr, *We2 = nullptr;
+  double *Wt = nullptr, *Ct = nullptr, *St = nullptr;
+  // per-ensemble workspaces (grow with the member count)
+  int cap = 0;
+  double *x = nullptr, *xs = nullptr, *acc = nullptr, *spec8 = nullptr, *yst = nullptr, *F = nullptr, *J = nullptr,
+         *G = nullptr, *jst = nullptr, *st2 = nullptr, *yt = nullptr;
+};
+
+static cudaError_t upload(SqgState* s, const std::vector<double>& v, double** out) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sizeof(double) * (v.empty() ? 1 : v.size()));
+  if (e != cudaSuccess) return e;
+  s->owned.push_back(p);
+  *out = static_cast<double*>(p);
+  return cudaMemcpy(p, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice);
+}
+
+static void free_work(SqgState* s) {
+  double** w[] = {&s->x, &s->xs, &s->acc, &s->spec8, &s->yst, &s->F, &s->J, &s->G, &s->jst, &s->st2, &s->yt};
+  for (double** p : w) { if (*p) cudaFree(*p); *p = nullptr; }
+  s->cap = 0;
+}
+
+void sqg_destroy(SqgState* s) {
+  if (s == nullptr) return;
+  free_work(s);
+  for (void* p : s->owned) cudaFree(p);
+  delete s;
+}
+
+// cos / sin of 2 pi a b / n with the argument reduced exactly (a b mod n in integers)
+static inline void unit(long long a, long long b, long long n, double* c, double* s) {
+  long long q = (a * b) % n;
+  if (q < 0) q += n;
+  const double ang = 2.0 * M_PI * (double)q / (double)n;
+  *c = cos(ang); *s = sin(ang);
+}
+
+cudaError_t sqg_setup(SqgState** out, const SqgTables& t) {
+  SqgState* s = new SqgState();
+  const int N = t.n, Nh = N / 2, NK = Nh + 1, M = 3 * N / 2;
+  s->N = N; s->NK = NK; s->M = M;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](const double* src, size_t n, const double** dst) {
+    if (e != cudaSuccess) return;
+    std::vector<double> v(src, src + n);
+    double* p = nullptr;
+    e = upload(s, v, &p);
+    *dst = p;
+  };
+  const size_t per = (size_t)N * NK;
+  up(t.kx, NK, &s->dev.kx); up(t.ly, N, &s->dev.ly);
+  up(t.hovermu, per, &s->dev.hovermu); up(t.tanhmu, per, &s->dev.tanhmu); up(t.sinhmu, per, &s->dev.sinhmu);
+  up(t.ksqlsq, per, &s->dev.ksqlsq); up(t.hyperdiff, per, &s->dev.hyperdiff);
+  const double* pveq = nullptr;
+  up(t.pvspec_eq, 4 * per, &pveq);
+  s->dev.pveq = reinterpret_cast<const double2*>(pveq);
+  s->dev.N = N; s->dev.NK = NK; s->dev.M = M;
+  s->dev.ekman = t.ekman; s->dev.symmetric = t.symmetric;
+  s->dev.dt = t.delta_t; s->dev.inv_tdiab = t.inv_tdiab; s->dev.r = t.r;
+  auto wave = [&](int r) { return r < Nh ? r : r - N; };        // signed wavenumber of kept row r (both grids)
+  // gemm b: [Yr; Yi] = [[Wr, -Wi], [Wi, Wr]] [Ar; Ai], W[y][r] = exp(+2 pi i y l_r / M)
+  {
+    std::vector<double> W((size_t)2 * M * 2 * N);
+    for (int y = 0; y < M; ++y)
+      for (int r = 0; r < N; ++r) {
+        double c, sn; unit(y, wave(r), M, &c, &sn);
+        W[(size_t)y * 2 * N + r] = c;            W[(size_t)y * 2 * N + N + r] = -sn;
+        W[(size_t)(M + y) * 2 * N + r] = sn;     W[(size_t)(M + y) * 2 * N + N + r] = c;
+      }
+    if (e == cudaSuccess) e = upload(s, W, &s->Wb);
+  }
+  // gemm c: f[y][x] = sum_c Yr[y][c] Cc[c][x] + Yi[y][c] Sc[c][x]; weights 1 (c = 0) / 2, 1 / M^2, Sc = -w sin
+  {
+    std::vector<double> C((size_t)NK * M), S((size_t)NK * M);
+    const double nrm = 1.0 / ((double)M * (double)M);
+    for (int c = 0; c < NK; ++c)
+      for (int x = 0; x < M; ++x) {
+        double cs, sn; unit(c, x, M, &cs, &sn);
+        const double w = (c == 0 ? 1.0 : 2.0) * nrm;
+        C[(size_t)c * M + x] = w * cs; S[(size_t)c * M + x] = -w * sn;
+      }
+    if (e == cudaSuccess) e = upload(s, C, &s->Cc);
+    if (e == cudaSuccess) e = upload(s, S, &s->Sc);
+  }
+  // gemm d: G[y][kc] = sum_x J[y][x] cos, G[y][Nh + kc] = -sum_x J[y][x] sin  (exp(-2 pi i kc x / M))
+  {
+    std::vector<double> D((size_t)M * N);
+    for (int x = 0; x < M; ++x)
+      for (int kc = 0; kc < Nh; ++kc) {
+        double cs, sn; unit(kc, x, M, &cs, &sn);
+        D[(size_t)x * N + kc] = cs; D[(size_t)x * N + Nh + kc] = -sn;
+      }
+    if (e == cudaSuccess) e = upload(s, D, &s->Df);
+  }
+  // gemm e: [Jr; Ji] = [Vr; Vi] Gr + [-Vi; Vr] Gi, V[r][y] = exp(-2 pi i l_r y / M)
+  {
+    std::vector<double> E1((size_t)2 * N * M), E2((size_t)2 * N * M);
+    for (int r = 0; r < N; ++r)
+      for (int y = 0; y < M; ++y) {
+        double cs, sn; unit(wave(r), y, M, &cs, &sn);
+        E1[(size_t)r * M + y] = cs;  E1[(size_t)(N + r) * M + y] = -sn;
+        E2[(size_t)r * M + y] = sn;  E2[(size_t)(N + r) * M + y] = cs;
+      }
+    if (e == cudaSuccess) e = upload(s, E1, &s->We1);
+    if (e == cudaSuccess) e = upload(s, E2, &s->We2);
+  }
+  // trajectory: irfft2 on the N grid (the Nyquist column counts once, its imaginary part is ignored: sin(pi x) = 0)
+  {
+    std::vector<double> W((size_t)2 * N * 2 * N), C((size_t)NK * N), S((size_t)NK * N);
+    for (int y = 0; y < N; ++y)
+      for (int r = 0; r < N; ++r) {
+        double c, sn; unit(y, wave(r), N, &c, &sn);
+        W[(size_t)y * 2 * N + r] = c;            W[(size_t)y * 2 * N + N + r] = -sn;
+        W[(size_t)(N + y) * 2 * N + r] = sn;     W[(size_t)(N + y) * 2 * N + N + r] = c;
+      }
+    const double nrm = 1.0 / ((double)N * (double)N);
+    for (int c = 0; c < NK; ++c)
+      for (int x = 0; x < N; ++x) {
+        double cs, sn; unit(c, x, N, &cs, &sn);
+        const double w = ((c == 0 || c == Nh) ? 1.0 : 2.0) * nrm;
+        C[(size_t)c * N + x] = w * cs; S[(size_t)c * N + x] = (c == 0 || c == Nh) ? 0.0 : -w * sn;
+      }
+    if (e == cudaSuccess) e = upload(s, W, &s->Wt);
+    if (e == cudaSuccess) e = upload(s, C, &s->Ct);
+    if (e == cudaSuccess) e = upload(s, S, &s->St);
+  }
+  if (e != cudaSuccess) { sqg_destroy(s); return e; }
+  *out = s;
+  return cudaSuccess;
+}
+
+static cudaError_t reserve_work(SqgState* s, int nm) {
+  if (nm <= s->cap) return cudaSuccess;
+  free_work(s);
+  const size_t N = s->N, NK = s->NK, M = s->M, per = 2 * N * NK;
+  struct { double** p; size_t n; } w[] = {
+      {&s->x, 2 * per * nm}, {&s->xs, 2 * per * nm}, {&s->acc, 2 * per * nm},
+      {&s->spec8, 2 * N * nm * 8 * NK}, {&s->yst, 2 * M * nm * 8 * NK}, {&s->F, (size_t)nm * 8 * M * M},
+      {&s->J, (size_t)nm * 2 * M * M}, {&s->G, (size_t)nm * 2 * M * N}, {&s->jst, (size_t)nm * 2 * 2 * N * (N / 2)},
+      {&s->st2, 2 * N * nm * 2 * NK}, {&s->yt, 2 * N * nm * 2 * NK}};
+  for (auto& b : w) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(b.p), sizeof(double) * b.n);
+    if (e != cudaSuccess) { free_work(s); return e; }
+  }
+  s->cap = nm;
+  return cudaSuccess;
+}
+
+// spec_in / spec_out: [members][2][N][N/2+1] complex128 (device; may alias); traj: nullable [n_steps][members][2][N][N]
+cudaError_t sqg_forecast(SqgState* s, const double* spec_in, double* spec_out, double* traj, int nm, int n_steps,
+                         cudaStream_t st, int* n_launches) {
+  cudaError_t e = reserve_work(s, nm);
+  if (e != cudaSuccess) return e;
+  const int N = s->N, Nh = N / 2, NK = s->NK, M = s->M;
+  const size_t state_bytes = sizeof(double) * 2 * 2 * N * NK * (size_t)nm;
+  e = cudaMemcpyAsync(s->x, spec_in, state_bytes, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  SqgDev d = s->dev;
+  d.nm = nm;
+  d.x = reinterpret_cast<double2*>(s->x); d.xs = reinterpret_cast<double2*>(s->xs); d.acc = reinterpret_cast<double2*>(s->acc);
+  d.spec8 = s->spec8; d.jst = s->jst; d.st2 = traj != nullptr ? s->st2 : nullptr;
+  const long long pts = (long long)nm * N * NK;
+  const unsigned sgrid = (unsigned)((pts + 127) / 128);
+  const long long ld8 = (long long)nm * 8 * NK, ld2 = (long long)nm * 2 * NK;
+  const long long mm = (long long)M * M, jtot = (long long)nm * 2 * mm;
+  int nl = 0;
+  if (n_steps > 0) {
+    sqg_stage_kernel<<<sgrid, 128, 0, st>>>(d, -1, 1); ++nl;
+  }
+  for (int step = 0; step < n_steps; ++step) {
+    for (int stage = 0; stage < 4; ++stage) {
+      // b: along y
+      e = gemm(st, 1, 2 * M, (int)ld8, 2 * N, {s->Wb, 2 * N, 0}, {s->spec8, ld8, 0}, s->yst, ld8, 0);
+      if (e != cudaSuccess) return e;
+      // c: along x, batch = (member, field)
+      {
+        GemmOp a2{s->yst + (long long)M * ld8, ld8, NK}, b2{s->Sc, M, 0};
+        e = gemm(st, nm * 8, M, M, NK, {s->yst, ld8, NK}, {s->Cc, M, 0}, s->F, M, mm, &a2, &b2);
+        if (e != cudaSuccess) return e;
+      }
+      sqg_jacobian_kernel<<<(unsigned)((jtot + 255) / 256), 256, 0, st>>>(s->F, s->J, mm, jtot);
+      // d: forward along x, all (member, level, y) rows at once
+      e = gemm(st, 1, nm * 2 * M, N, M, {s->J, M, 0}, {s->Df, N, 0}, s->G, N, 0);
+      if (e != cudaSuccess) return e;
+      // e: forward along y, batch = (member, level)
+      {
+        GemmOp a2{s->We2, M, 0}, b2{s->G + Nh, N, (long long)M * N};
+        e = gemm(st, nm * 2, 2 * N, Nh, M, {s->We1, M, 0}, {s->G, N, (long long)M * N}, s->jst, Nh, (long long)2 * N * Nh, &a2, &b2);
+        if (e != cudaSuccess) return e;
+      }
+      const bool last = step == n_steps - 1 && stage == 3;
+      sqg_stage_kernel<<<sgrid, 128, 0, st>>>(d, stage, last ? 0 : 1);
+      nl += 6;
+    }
+    if (traj != nullptr) {
+      double* out = traj + (size_t)step * nm * 2 * N * N;
+      e = gemm(st, 1, 2 * N, (int)ld2, 2 * N, {s->Wt, 2 * N, 0}, {s->st2, ld2, 0}, s->yt, ld2, 0);
+      if (e != cudaSuccess) return e;
+      GemmOp a2{s->yt + (long long)N * ld2, ld2, NK}, b2{s->St, N, 0};
+      e = gemm(st, nm * 2, N, N, NK, {s->yt, ld2, NK}, {s->Ct, N, 0}, out, N, (long long)N * N, &a2, &b2);
+      if (e != cudaSuccess) return e;
+      nl += 2;
+    }
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(spec_out, s->x, state_bytes, cudaMemcpyDeviceToDevice, st);
+  if (n_launches) *n_launches = nl;
+  return e;
+}
+
+}  // namespace dab

@@ -83,6 +83,30 @@ DAB_API int dab_l96_forecast_f64(dab_handle* h, const double* x_in, double* x_ou
 DAB_API int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_out, double* traj, int64_t k,
                          int n_steps, double dt, double sigma, double rho, double beta, void* stream);
 
+/* Surface quasi-geostrophic turbulence members through the same plugin point: replaces SQGTurb.integrate ->
+ * lax.scan(SQGTurb._rk4) -> SQGTurb.rhs (dabench/data/_sqgturb.py:441-504, :345-364, :506-548; helpers _invert
+ * :258-270, _specpad :293-309, _xyderiv_dealias :334-343, _spectrunc :311-325) for all members at once, FP64,
+ * dealiased (the reference's only working branch).  The 2-D transforms on the 3N/2 grid are pruned DFTs done as
+ * FP64 matrix products with all members batched (csrc/sqg_forecast.cu).
+ * dab_sqg_setup copies the generator's constant tables (HOST pointers; built by the caller exactly as
+ * SQGTurb.__init__ builds them, :150-248, float32 / complex64 casts included) and the DFT matrices to the device:
+ *   n            grid points per direction (multiple of 4: the 3n/2 grid must be even)
+ *   kx [n/2+1]   imag(ik_pad[0, :n/2+1]);  ly [n]  imag(il[:, 0]) (= il_pad on the rows _specpad fills)
+ *   hovermu, tanhmu, sinhmu, ksqlsq, hyperdiff   [n][n/2+1];  pvspec_eq [2][n][n/2+1] complex128
+ *   delta_t, inv_tdiab (= 1 / tdiab as the reference rounds it), r; ekman = (r >= 1e-10); symmetric
+ * dab_sqg_forecast_c128 advances `members` spectral states by n_steps RK4 steps:
+ *   spec_in, spec_out  dev [members][2][n][n/2+1] complex128 (re, im interleaved; may alias)
+ *   traj_grid          nullable dev [n_steps][members][2][n][n] real: irfft2 of the state after step 1..n_steps
+ *                      (the rows of the reference's `values`, which start one step past x0, :489-496) */
+typedef struct dab_sqg_config {
+  int32_t n, ekman, symmetric, reserved;
+  double delta_t, inv_tdiab, r;
+  const double *kx, *ly, *hovermu, *tanhmu, *sinhmu, *ksqlsq, *hyperdiff, *pvspec_eq;
+} dab_sqg_config;
+DAB_API int dab_sqg_setup(dab_handle* h, const dab_sqg_config* cfg);
+DAB_API int dab_sqg_forecast_c128(dab_handle* h, const double* spec_in, double* spec_out, double* traj_grid,
+                          int members, int n_steps, void* stream);
+
 /* ---- K2: observation operator as a gather ----------------------------------------------
  * Replaces the dense one-hot H (DACycler._calc_default_H, dabench/dacycler/_dacycler.py:58-66),
  * its masking (dabench/dacycler/_etkf.py:202-203) and ETKF._apply_obsop `H @ Xb`

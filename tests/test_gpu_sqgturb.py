@@ -1,0 +1,73 @@
+"""Surface-QG ensemble forecast on the GPU (dab_sqg_forecast_c128, csrc/sqg_forecast.cu) against the NumPy oracle
+(oracle/sqgturb.py).  FP64 on both sides with the same tables; the device does its pruned transforms as DFT matrix
+products, the oracle as FFTs: agreement to <= 1e-10 of the field's magnitude over a few RK4 steps."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import sqgturb as o_sqg
+from dataassimbench_b200.data import SQGTurb
+from test_sqgturb_cpu import DEFAULT_PV, reference_observer_draws
+
+
+def members(N, k, seed):
+    rng = np.random.default_rng(seed)
+    x, y = np.meshgrid(np.arange(N) * 2 * np.pi / N, np.arange(N) * 2 * np.pi / N)
+    pv = 300.0 * rng.standard_normal((k, 2, N, N))
+    pv[:, 1] += 2000.0 * (np.sin(x / 2) ** 40 * np.sin(y) ** 20)         # the blob of the reference's own test
+    pv -= pv.mean(axis=(2, 3), keepdims=True)
+    return pv
+
+
+@pytest.mark.parametrize("N,k,n_steps,r", [(16, 1, 3, 0.0), (32, 5, 4, 0.0), (64, 3, 2, 1.0e-6), (96, 4, 3, 0.0),
+                                           (40, 2, 2, 5.0e-7)])
+def test_sqg_forecast_matches_oracle(N, k, n_steps, r):
+    pv = members(N, k, seed=N + k)
+    g = SQGTurb(pv=pv[0], precision='double', r=r)
+    T = o_sqg.tables(N, 'double', r=r)
+    spec0 = np.fft.rfft2(pv)                                              # [k, 2, N, N/2+1]
+    spec, traj = g.forecast_members(spec0, n_steps, return_grid_traj=True)
+    traj = traj.cpu().numpy()
+    assert spec.shape == spec0.shape and traj.shape == (n_steps, k, 2, N, N)
+    for m in range(k):
+        ref_spec, ref_vals, _ = o_sqg.integrate(T, spec0[m], n_steps)
+        scale = np.abs(ref_spec).max()
+        assert np.abs(spec[m] - ref_spec).max() / scale < 1e-10
+        assert np.abs(traj[:, m] - ref_vals).max() / np.abs(ref_vals).max() < 1e-10
+    # a device-resident ensemble goes in and out without leaving the GPU, and zero steps is the identity
+    dev = torch.from_numpy(spec0).cuda()
+    out = g.forecast_members(dev, n_steps)
+    assert out.is_cuda and np.array_equal(out.cpu().numpy(), spec)
+    assert np.array_equal(g.forecast_members(spec0, 0), spec0)
+
+
+def test_sqg_generate_reproduces_the_reference_observer_golden():
+    """SQGTurb().generate(n_steps=10) through the package, sampled where the reference's seeded Observer samples it
+    (tests/observer_base_test.py:240-261)."""
+    g = SQGTurb()
+    ds = g.generate(n_steps=10)
+    pv = np.asarray(ds['pv'].values)
+    assert pv.shape == (11, 2, 96, 96) and ds.attrs['system_dim'] == 18432
+    assert np.allclose(np.asarray(ds['time'].values), np.arange(11) * 900.0)
+    tsel, count, lev, xx, yy, err = reference_observer_draws(96, 11)
+    assert pv[tsel[0]][lev[44], xx[44], yy[44]] + err[0, 0, 44] == pytest.approx(2128.20749725)
+    ref, _ = o_sqg.generate(np.load(DEFAULT_PV), 10, precision='single')  # float32 FFT path of the reference
+    assert np.abs(pv - ref).max() / np.abs(ref).max() < 2e-5
+    # the generator keeps the reference's bookkeeping: final spectral state and clock
+    assert g.t == 9000.0 and g.pvspec.shape == (2, 96, 49)
+
+
+def test_sqg_forecast_needs_setup_and_valid_sizes():
+    from dataassimbench_b200 import _native
+    h = _native.Handle(0)
+    try:
+        with pytest.raises(_native.DabError):
+            h.sqg_forecast(torch.zeros(4, device='cuda'), torch.zeros(4, device='cuda'), None, 1, 1, None)
+    finally:
+        h.close()
+    with pytest.raises(ValueError):
+        SQGTurb(pv=np.zeros((2, 6, 6)))           # 3N/2 odd
