@@ -19,9 +19,9 @@
 //   gemm e    forward transform along y, truncated to N rows:  [2N x M] x [M x N/2], two accumulated products
 //   update    tendency (thermal relaxation, Ekman terms, -J), RK4 bookkeeping in the reference's order, hyperdiffusion
 //             factor after the fourth stage, and the next stage's prep in the same kernel                  (elementwise)
-// All members of an ensemble share every launch.  The GEMM is one kernel (64 x 64 x 16 tiles, 4 x 4 outputs per
-// thread, register prefetch of the next k-tile): FP64 FMA is the bound, shared-memory traffic is 1 LDS.128 per 8
-// DFMAs.  M = 3N/2 and every table come from the caller (the Python mirror builds them the way the reference's
+// All members of an ensemble share every launch.  The GEMM is one kernel on the FP64 tensor pipe (DMMA.8x8x4, see
+// sqg_gemm_kernel): a first version with 4 x 4 outputs per thread on DFMA was shared-memory-bound at 20 % of peak
+// (1 LDS.128 per 4 DFMAs).  M = 3N/2 and every table come from the caller (the Python mirror builds them the way the reference's
 // __init__ does, including its float32 / complex64 casts), so the kernels hold no physics constants.
 #include <cmath>
 #include <vector>
@@ -42,35 +42,43 @@ struct GemmArgs {
   int m, n, K, nseg;
 };
 
-constexpr int GB = 64, GK = 16, GLD = GB + 2;
+// One CTA = 4 warps (2 x 2) on a (16 WT) x (16 WT) tile of C, k-tiles of 16; a warp owns WT x WT DMMA.8x8x4 tiles
+// (WT A fragments + WT B fragments per k-step for WT^2 DMMAs).  A is staged as [row][k] with row stride 20, B as
+// [k][column] with row stride 16 WT + 4: both = 4 mod 16, which spreads the 32 8-byte words of a fragment load over
+// all banks (no conflicts), and the staging stores are contiguous per half-warp.  The next k-tile is fetched into
+// registers while the current one is multiplied.  WT is picked per product so that the padded tile grid wastes the
+// least work (N = 96: every dimension but the long batched one is a multiple of 48).
+constexpr int GK = 16, LDA = GK + 4;
 
-__global__ void __launch_bounds__(256)
+template <int WT>
+__global__ void __launch_bounds__(128)
 sqg_gemm_kernel(const GemmArgs g) {
-  __shared__ __align__(16) double As[GK][GLD];
-  __shared__ __align__(16) double Bs[GK][GLD];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int i0 = blockIdx.y * GB, j0 = blockIdx.x * GB;
+  constexpr int BT = 16 * WT, LDB = BT + 4, NP = 2 * WT;     // NP = BT * GK / 128 elements per thread and operand
+  __shared__ __align__(16) double As[BT * LDA];
+  __shared__ __align__(16) double Bs[GK * LDB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, fr = lane & 3;
+  const int m_base = (warp >> 1) * 8 * WT, n_base = (warp & 1) * 8 * WT;
+  const int i0 = blockIdx.y * BT, j0 = blockIdx.x * BT;
   const long long b = blockIdx.z;
-  double acc[4][4];
+  double acc[WT][WT][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < WT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  // loader coordinates: A tile 64 rows x 16 k (k fastest), B tile 16 k x 64 columns (column fastest)
-  const int a_k = tid & 15, a_i = tid >> 4;       // + 16 rows per pass
-  const int b_j = tid & 63, b_k = tid >> 6;       // + 4 k per pass
+    for (int j = 0; j < WT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   const int kt = (g.K + GK - 1) / GK;
   const int total = kt * g.nseg;
-  double ra[4], rb[4];
+  double ra[NP], rb[NP];
   auto fetch = [&](int it) {
     const int seg = it / kt, k0 = (it - seg * kt) * GK;
     const double* A = g.A[seg].p + b * g.A[seg].bs;
     const double* B = g.B[seg].p + b * g.B[seg].bs;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int i = i0 + a_i + 16 * p, k = k0 + a_k;
+    for (int p = 0; p < NP; ++p) {
+      const int idx = tid + 128 * p;
+      const int i = i0 + (idx >> 4), k = k0 + (idx & 15);
       ra[p] = (i < g.m && k < g.K) ? A[(long long)i * g.A[seg].rs + k] : 0.0;
-      const int kb = k0 + b_k + 4 * p, j = j0 + b_j;
+      const int kb = k0 + idx / BT, j = j0 + idx % BT;
       rb[p] = (kb < g.K && j < g.n) ? B[(long long)kb * g.B[seg].rs + j] : 0.0;
     }
   };
@@ -78,31 +86,38 @@ sqg_gemm_kernel(const GemmArgs g) {
   for (int it = 0; it < total; ++it) {
     __syncthreads();
 #pragma unroll
-    for (int p = 0; p < 4; ++p) { As[a_k][a_i + 16 * p] = ra[p]; Bs[b_k + 4 * p][b_j] = rb[p]; }
+    for (int p = 0; p < NP; ++p) {
+      const int idx = tid + 128 * p;
+      As[(idx >> 4) * LDA + (idx & 15)] = ra[p];
+      Bs[(idx / BT) * LDB + idx % BT] = rb[p];
+    }
     __syncthreads();
+    const int k0 = (it % kt) * GK;
+    const int rem = g.K - k0;
+    const int ksteps = rem >= GK ? GK / 4 : (rem + 3) >> 2;     // a ragged last k-tile only pays for its own k-steps
     if (it + 1 < total) fetch(it + 1);
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double av[WT], bv[WT];
 #pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][4 * ty]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][4 * ty + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx + 2]);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+      for (int i = 0; i < WT; ++i) av[i] = As[(m_base + 8 * i + fm) * LDA + 4 * ks + fr];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < WT; ++j) bv[j] = Bs[(4 * ks + fr) * LDB + n_base + 8 * j + fm];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < WT; ++i)
+#pragma unroll
+        for (int j = 0; j < WT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
     }
   }
   double* C = g.C + b * g.c_bs;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i0 + 4 * ty + i;
+  for (int i = 0; i < WT; ++i) {
+    const int r = i0 + m_base + 8 * i + fm;
     if (r >= g.m) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = j0 + 4 * tx + j;
-      if (c < g.n) C[(long long)r * g.c_rs + c] = acc[i][j];
+    for (int j = 0; j < WT; ++j) {
+      const int c = j0 + n_base + 8 * j + 2 * fr;
+      if (c < g.n) C[(long long)r * g.c_rs + c] = acc[i][j][0];
+      if (c + 1 < g.n) C[(long long)r * g.c_rs + c + 1] = acc[i][j][1];
     }
   }
 }
@@ -113,8 +128,18 @@ cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, Gem
   g.A[0] = A1; g.B[0] = B1; g.nseg = 1;
   if (A2 != nullptr) { g.A[1] = *A2; g.B[1] = *B2; g.nseg = 2; }
   g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.m = m; g.n = n; g.K = K;
-  dim3 grid((unsigned)((n + GB - 1) / GB), (unsigned)((m + GB - 1) / GB), (unsigned)batch);
-  sqg_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  // tile edge with the least padded work, weighted by the fragment loads a DMMA costs at that warp tile
+  // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured, 48 beats 32 by 20 % at equal padding
+  int best = 64;
+  double best_cost = -1.0;
+  for (int bt : {64, 48, 32}) {
+    const double w = (double)((m + bt - 1) / bt) * bt * (double)((n + bt - 1) / bt) * bt * (1.0 + 8.0 / bt);
+    if (best_cost < 0.0 || w < best_cost) { best = bt; best_cost = w; }
+  }
+  dim3 grid((unsigned)((n + best - 1) / best), (unsigned)((m + best - 1) / best), (unsigned)batch);
+  if (best == 64) sqg_gemm_kernel<4><<<grid, 128, 0, st>>>(g);
+  else if (best == 48) sqg_gemm_kernel<3><<<grid, 128, 0, st>>>(g);
+  else sqg_gemm_kernel<2><<<grid, 128, 0, st>>>(g);
   return cudaGetLastError();
 }
 

@@ -1,3 +1,3 @@
-from ._model import Model, Lorenz96Model, Lorenz63Model
+from ._model import Model, Lorenz96Model, Lorenz63Model, SQGTurbModel
 
-__all__ = ["Model", "Lorenz96Model", "Lorenz63Model"]
+__all__ = ["Model", "Lorenz96Model", "Lorenz63Model", "SQGTurbModel"]

@@ -46,3 +46,22 @@ class Lorenz63Model(Model):
     def forecast(self, state_vec, n_steps=2):
         new_vec = self.model_obj.generate(x0=_xr.var_array(state_vec, 'x'), n_steps=n_steps)
         return new_vec.isel(time=-1), new_vec
+
+
+class SQGTurbModel(Model):
+    """Wraps a `data.SQGTurb` generator behind the same plugin point: `state_vec` holds the gridded potential
+    vorticity `pv[level, x, y]`; the generator itself steps in spectral space (dabench/data/_sqgturb.py:441-504), so
+    the wrapper transforms in (`fft2_2dto1d`, :420-426) and `generate` transforms out.  The returned trajectory keeps
+    the reference's scan quirk: its first row is one step past `state_vec`."""
+
+    def __init__(self, system_dim=None, delta_t=None, model_obj=None):
+        if model_obj is None:
+            from ..data import SQGTurb
+            model_obj = SQGTurb(delta_t=delta_t or 900)
+        super().__init__(system_dim=system_dim or model_obj.system_dim,
+                         delta_t=delta_t or model_obj.delta_t, model_obj=model_obj)
+
+    def forecast(self, state_vec, n_steps=2):
+        x0 = self.model_obj.fft2_2dto1d(_xr.var_array(state_vec, 'pv'))
+        new_vec = self.model_obj.generate(x0=x0, n_steps=n_steps)
+        return new_vec.isel(time=-1), new_vec

@@ -71,3 +71,23 @@ def test_sqg_forecast_needs_setup_and_valid_sizes():
         h.close()
     with pytest.raises(ValueError):
         SQGTurb(pv=np.zeros((2, 6, 6)))           # 3N/2 odd
+
+
+def test_sqg_model_forecast_plugin_contract():
+    """model.SQGTurbModel: gridded state in, (last state, trajectory) out -- the Model.forecast contract
+    (dabench/model/_model.py:10-32) around the spectral generator."""
+    import dataassimbench_b200 as dab
+    from dataassimbench_b200 import _xr
+    N = 32
+    pv = members(N, 1, seed=5)[0]
+    gen = dab.data.SQGTurb(pv=pv, precision='double')
+    model = dab.model.SQGTurbModel(model_obj=gen)
+    assert model.system_dim == 2 * N * N and model.delta_t == 900
+    state = _xr.new_dataset({'pv': (('level', 'x', 'y'), pv)},
+                            coords={'level': np.arange(2), 'x': np.arange(N), 'y': np.arange(N)})
+    last, traj = model.forecast(state, n_steps=3)
+    ref, _ = o_sqg.generate(pv, 3, precision='double')
+    got = _xr.var_array(traj, 'pv')
+    assert got.shape == (4, 2, N, N)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-10
+    assert np.array_equal(_xr.var_array(last, 'pv'), got[-1])
