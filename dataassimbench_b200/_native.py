@@ -59,6 +59,7 @@ _SIGNATURES = {
     "dab_l63_forecast_f64": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "dab_sqg_setup": (C.c_int, [_P, _P]),
     "dab_sqg_forecast_c128": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "dab_sqg_forecast_grid_f64": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "dab_obs_gather_f64": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_int, _I64, _P]),
     "dab_observe_f64": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, C.c_int, _P, _I64, _P, _P, _P]),
     "dab_var3d_analysis_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64, C.c_double, _P]),
@@ -200,6 +201,10 @@ class Handle:
     def sqg_forecast(self, spec_in, spec_out, traj_grid, members, n_steps, stream=None):
         self._check(self._lib.dab_sqg_forecast_c128(self._h, _ptr(spec_in), _ptr(spec_out), _ptr(traj_grid),
                                                     int(members), int(n_steps), stream))
+
+    def sqg_forecast_grid(self, grid_in, grid_out, spec_out, traj_grid, members, n_steps, stream=None):
+        self._check(self._lib.dab_sqg_forecast_grid_f64(self._h, _ptr(grid_in), _ptr(grid_out), _ptr(spec_out),
+                                                        _ptr(traj_grid), int(members), int(n_steps), stream))
 
     def obs_gather(self, X, idx, mask, Yb, N, k, n_y, stream=None):
         self._check(self._lib.dab_obs_gather_f64(self._h, _ptr(X), _ptr(idx), _ptr(mask), _ptr(Yb),

@@ -509,7 +509,21 @@ int dab_sqg_forecast_c128(dab_handle* h, const double* spec_in, double* spec_out
   if (members == 0) return 0;
   DAB_CUDA(h, cudaSetDevice(h->device));
   int nl = 0;
-  DAB_CUDA(h, sqg_forecast(h->sqg, spec_in, spec_out, traj_grid, members, n_steps, static_cast<cudaStream_t>(stream), &nl));
+  DAB_CUDA(h, sqg_forecast(h->sqg, spec_in, nullptr, spec_out, nullptr, traj_grid, members, n_steps, static_cast<cudaStream_t>(stream), &nl));
+  h->launches += nl;
+  return 0;
+}
+
+int dab_sqg_forecast_grid_f64(dab_handle* h, const double* grid_in, double* grid_out, double* spec_out, double* traj_grid,
+                              int members, int n_steps, void* stream) {
+  DAB_ARG(h, h != nullptr);
+  if (h->sqg == nullptr) return fail(h, -1, "dab_sqg_forecast_grid_f64: call dab_sqg_setup first");
+  DAB_ARG(h, members >= 0 && n_steps >= 0);
+  DAB_ARG(h, members == 0 || (grid_in != nullptr && grid_out != nullptr));
+  if (members == 0) return 0;
+  DAB_CUDA(h, cudaSetDevice(h->device));
+  int nl = 0;
+  DAB_CUDA(h, sqg_forecast(h->sqg, nullptr, grid_in, spec_out, grid_out, traj_grid, members, n_steps, static_cast<cudaStream_t>(stream), &nl));
   h->launches += nl;
   return 0;
 }

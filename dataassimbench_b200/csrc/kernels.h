@@ -79,8 +79,8 @@ struct SqgTables {
 struct SqgState;
 cudaError_t sqg_setup(SqgState** out, const SqgTables& t);
 void sqg_destroy(SqgState* s);
-cudaError_t sqg_forecast(SqgState* s, const double* spec_in, double* spec_out, double* traj, int members, int n_steps,
-                         cudaStream_t st, int* n_launches);
+cudaError_t sqg_forecast(SqgState* s, const double* spec_in, const double* grid_in, double* spec_out, double* grid_out,
+                         double* traj, int members, int n_steps, cudaStream_t st, int* n_launches);
 
 // K2/K3  etkf_contract.cu
 int contract_k8(int k);

@@ -38,7 +38,7 @@ namespace {
 struct GemmOp { const double* p; long long rs, bs; };
 struct GemmArgs {
   GemmOp A[2], B[2];
-  double* C; long long c_rs, c_bs;
+  double* C; long long c_rs, c_bs, c_cs;      // C alone may have a column stride (interleaved complex output)
   int m, n, K, nseg;
 };
 
@@ -116,18 +116,18 @@ sqg_gemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < WT; ++j) {
       const int c = j0 + n_base + 8 * j + 2 * fr;
-      if (c < g.n) C[(long long)r * g.c_rs + c] = acc[i][j][0];
-      if (c + 1 < g.n) C[(long long)r * g.c_rs + c + 1] = acc[i][j][1];
+      if (c < g.n) C[(long long)r * g.c_rs + c * g.c_cs] = acc[i][j][0];
+      if (c + 1 < g.n) C[(long long)r * g.c_rs + (c + 1) * g.c_cs] = acc[i][j][1];
     }
   }
 }
 
 cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, GemmOp B1, double* C, long long c_rs,
-                 long long c_bs, const GemmOp* A2 = nullptr, const GemmOp* B2 = nullptr) {
+                 long long c_bs, const GemmOp* A2 = nullptr, const GemmOp* B2 = nullptr, long long c_cs = 1) {
   GemmArgs g{};
   g.A[0] = A1; g.B[0] = B1; g.nseg = 1;
   if (A2 != nullptr) { g.A[1] = *A2; g.B[1] = *B2; g.nseg = 2; }
-  g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.m = m; g.n = n; g.K = K;
+  g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.c_cs = c_cs; g.m = m; g.n = n; g.K = K;
   // tile edge with the least padded work, weighted by the fragment loads a DMMA costs at that warp tile
   // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured, 48 beats 32 by 20 % at equal padding
   int best = 64;
@@ -250,6 +250,22 @@ sqg_stage_kernel(const SqgDev d, int stage, int do_prep) {
   sqg_store_fields(d, m, r, c, 2, 1, s1);
 }
 
+// state [nm][2][N][NK] complex -> the [2 (re, im)][N][nm][2][NK] layout of the trajectory transform
+__global__ void __launch_bounds__(128)
+sqg_pack_kernel(const double2* __restrict__ x, double* __restrict__ st2, int N, int NK, int nm) {
+  const long long per = (long long)N * NK;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * nm) return;
+  const int m = (int)(idx / per);
+  const int rc = (int)(idx - (long long)m * per);
+  const int r = rc / NK, c = rc - r * NK;
+  const long long ld = (long long)nm * 2 * NK, im = (long long)N * ld;
+  const long long o = (long long)r * ld + ((long long)m * 2) * NK + c;
+  const double2 s0 = x[((long long)m * 2) * per + rc], s1 = x[((long long)m * 2 + 1) * per + rc];
+  st2[o] = s0.x; st2[o + im] = s0.y;
+  st2[o + NK] = s1.x; st2[o + NK + im] = s1.y;
+}
+
 // F [nm][8][M][M] (field = which * 2 + level) -> J [nm][2][M][M] = psi_x q_y - psi_y q_x
 __global__ void __launch_bounds__(256)
 sqg_jacobian_kernel(const double* __restrict__ F, double* __restrict__ J, long long mm, long long total) {
@@ -270,10 +286,11 @@ struct SqgState {
   std::vector<void*> owned;            // tables and constant matrices
   double *Wb = nullptr, *Cc = nullptr, *Sc = nullptr, *Df = nullptr, *We1 = nullptr, *We2 = nullptr;
   double *Wt = nullptr, *Ct = nullptr, *St = nullptr;
+  double *Dg = nullptr, *Vg1 = nullptr, *Vg2 = nullptr;     // rfft2 on the N grid (gridded states in)
   // per-ensemble workspaces (grow with the member count)
   int cap = 0;
   double *x = nullptr, *xs = nullptr, *acc = nullptr, *spec8 = nullptr, *yst = nullptr, *F = nullptr, *J = nullptr,
-         *G = nullptr, *jst = nullptr, *st2 = nullptr, *yt = nullptr;
+         *G = nullptr, *jst = nullptr, *st2 = nullptr, *yt = nullptr, *gg = nullptr;
 };
 
 static cudaError_t upload(SqgState* s, const std::vector<double>& v, double** out) {
@@ -286,7 +303,7 @@ static cudaError_t upload(SqgState* s, const std::vector<double>& v, double** ou
 }
 
 static void free_work(SqgState* s) {
-  double** w[] = {&s->x, &s->xs, &s->acc, &s->spec8, &s->yst, &s->F, &s->J, &s->G, &s->jst, &s->st2, &s->yt};
+  double** w[] = {&s->x, &s->xs, &s->acc, &s->spec8, &s->yst, &s->F, &s->J, &s->G, &s->jst, &s->st2, &s->yt, &s->gg};
   for (double** p : w) { if (*p) cudaFree(*p); *p = nullptr; }
   s->cap = 0;
 }
@@ -395,6 +412,25 @@ cudaError_t sqg_setup(SqgState** out, const SqgTables& t) {
     if (e == cudaSuccess) e = upload(s, C, &s->Ct);
     if (e == cudaSuccess) e = upload(s, S, &s->St);
   }
+  // rfft2 on the N grid: along x  G[y][c] = sum_x f[y][x] exp(-2 pi i c x / N), c = 0 .. N/2 (real | imaginary
+  // halves of a row), then along y  X[r][c] = sum_y exp(-2 pi i l_r y / N) G[y][c]
+  {
+    std::vector<double> D((size_t)N * 2 * NK), V1((size_t)2 * N * N), V2((size_t)2 * N * N);
+    for (int x = 0; x < N; ++x)
+      for (int c = 0; c < NK; ++c) {
+        double cs, sn; unit(c, x, N, &cs, &sn);
+        D[(size_t)x * 2 * NK + c] = cs; D[(size_t)x * 2 * NK + NK + c] = -sn;
+      }
+    for (int r = 0; r < N; ++r)
+      for (int y = 0; y < N; ++y) {
+        double cs, sn; unit(wave(r), y, N, &cs, &sn);
+        V1[(size_t)r * N + y] = cs;  V1[(size_t)(N + r) * N + y] = -sn;
+        V2[(size_t)r * N + y] = sn;  V2[(size_t)(N + r) * N + y] = cs;
+      }
+    if (e == cudaSuccess) e = upload(s, D, &s->Dg);
+    if (e == cudaSuccess) e = upload(s, V1, &s->Vg1);
+    if (e == cudaSuccess) e = upload(s, V2, &s->Vg2);
+  }
   if (e != cudaSuccess) { sqg_destroy(s); return e; }
   *out = s;
   return cudaSuccess;
@@ -408,7 +444,7 @@ static cudaError_t reserve_work(SqgState* s, int nm) {
       {&s->x, 2 * per * nm}, {&s->xs, 2 * per * nm}, {&s->acc, 2 * per * nm},
       {&s->spec8, 2 * N * nm * 8 * NK}, {&s->yst, 2 * M * nm * 8 * NK}, {&s->F, (size_t)nm * 8 * M * M},
       {&s->J, (size_t)nm * 2 * M * M}, {&s->G, (size_t)nm * 2 * M * N}, {&s->jst, (size_t)nm * 2 * 2 * N * (N / 2)},
-      {&s->st2, 2 * N * nm * 2 * NK}, {&s->yt, 2 * N * nm * 2 * NK}};
+      {&s->st2, 2 * N * nm * 2 * NK}, {&s->yt, 2 * N * nm * 2 * NK}, {&s->gg, (size_t)nm * 2 * N * 2 * NK}};
   for (auto& b : w) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(b.p), sizeof(double) * b.n);
     if (e != cudaSuccess) { free_work(s); return e; }
@@ -417,24 +453,41 @@ static cudaError_t reserve_work(SqgState* s, int nm) {
   return cudaSuccess;
 }
 
-// spec_in / spec_out: [members][2][N][N/2+1] complex128 (device; may alias); traj: nullable [n_steps][members][2][N][N]
-cudaError_t sqg_forecast(SqgState* s, const double* spec_in, double* spec_out, double* traj, int nm, int n_steps,
-                         cudaStream_t st, int* n_launches) {
+// spec_in / spec_out: [members][2][N][N/2+1] complex128 (device; may alias); grid_in / grid_out: [members][2][N][N]
+// real (the state enters as rfft2(grid_in) when spec_in is null; grid_out = irfft2 of the final state); spec_out and
+// grid_out are both optional; traj: nullable [n_steps][members][2][N][N]
+cudaError_t sqg_forecast(SqgState* s, const double* spec_in, const double* grid_in, double* spec_out, double* grid_out,
+                         double* traj, int nm, int n_steps, cudaStream_t st, int* n_launches) {
   cudaError_t e = reserve_work(s, nm);
   if (e != cudaSuccess) return e;
   const int N = s->N, Nh = N / 2, NK = s->NK, M = s->M;
   const size_t state_bytes = sizeof(double) * 2 * 2 * N * NK * (size_t)nm;
-  e = cudaMemcpyAsync(s->x, spec_in, state_bytes, cudaMemcpyDeviceToDevice, st);
-  if (e != cudaSuccess) return e;
+  int nl = 0;
+  if (spec_in != nullptr) {
+    e = cudaMemcpyAsync(s->x, spec_in, state_bytes, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+  } else {
+    // rfft2: rows (member, level, y) x [N] times [N x 2 NK], then per (member, level) the y transform, the real and
+    // the imaginary rows written straight into the interleaved complex state
+    e = gemm(st, 1, nm * 2 * N, 2 * NK, N, {grid_in, N, 0}, {s->Dg, 2 * NK, 0}, s->gg, 2 * NK, 0);
+    if (e != cudaSuccess) return e;
+    const long long gb = (long long)N * 2 * NK, xb = (long long)N * NK * 2;
+    for (int ri = 0; ri < 2; ++ri) {
+      GemmOp a2{s->Vg2 + (size_t)ri * N * N, N, 0}, b2{s->gg + NK, 2 * NK, gb};
+      e = gemm(st, nm * 2, N, NK, N, {s->Vg1 + (size_t)ri * N * N, N, 0}, {s->gg, 2 * NK, gb}, s->x + ri, 2 * NK, xb, &a2, &b2, 2);
+      if (e != cudaSuccess) return e;
+    }
+    nl += 3;
+  }
   SqgDev d = s->dev;
   d.nm = nm;
   d.x = reinterpret_cast<double2*>(s->x); d.xs = reinterpret_cast<double2*>(s->xs); d.acc = reinterpret_cast<double2*>(s->acc);
-  d.spec8 = s->spec8; d.jst = s->jst; d.st2 = traj != nullptr ? s->st2 : nullptr;
+  const bool want_grid = traj != nullptr || (grid_out != nullptr && n_steps > 0);
+  d.spec8 = s->spec8; d.jst = s->jst; d.st2 = want_grid ? s->st2 : nullptr;
   const long long pts = (long long)nm * N * NK;
   const unsigned sgrid = (unsigned)((pts + 127) / 128);
   const long long ld8 = (long long)nm * 8 * NK, ld2 = (long long)nm * 2 * NK;
   const long long mm = (long long)M * M, jtot = (long long)nm * 2 * mm;
-  int nl = 0;
   if (n_steps > 0) {
     sqg_stage_kernel<<<sgrid, 128, 0, st>>>(d, -1, 1); ++nl;
   }
@@ -463,19 +516,35 @@ cudaError_t sqg_forecast(SqgState* s, const double* spec_in, double* spec_out, d
       sqg_stage_kernel<<<sgrid, 128, 0, st>>>(d, stage, last ? 0 : 1);
       nl += 6;
     }
-    if (traj != nullptr) {
-      double* out = traj + (size_t)step * nm * 2 * N * N;
+    const bool final_grid = grid_out != nullptr && step == n_steps - 1;
+    if (traj != nullptr || final_grid) {
+      double* out = traj != nullptr ? traj + (size_t)step * nm * 2 * N * N : grid_out;
       e = gemm(st, 1, 2 * N, (int)ld2, 2 * N, {s->Wt, 2 * N, 0}, {s->st2, ld2, 0}, s->yt, ld2, 0);
       if (e != cudaSuccess) return e;
       GemmOp a2{s->yt + (long long)N * ld2, ld2, NK}, b2{s->St, N, 0};
       e = gemm(st, nm * 2, N, N, NK, {s->yt, ld2, NK}, {s->Ct, N, 0}, out, N, (long long)N * N, &a2, &b2);
       if (e != cudaSuccess) return e;
       nl += 2;
+      if (traj != nullptr && final_grid) {
+        e = cudaMemcpyAsync(grid_out, out, sizeof(double) * (size_t)nm * 2 * N * N, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+      }
     }
+  }
+  if (grid_out != nullptr && n_steps == 0) {
+    // no step: the gridded state is the projection irfft2(rfft2(.)) of the input
+    sqg_pack_kernel<<<(unsigned)(((long long)nm * N * NK + 127) / 128), 128, 0, st>>>(
+        reinterpret_cast<const double2*>(s->x), s->st2, N, NK, nm);
+    e = gemm(st, 1, 2 * N, (int)ld2, 2 * N, {s->Wt, 2 * N, 0}, {s->st2, ld2, 0}, s->yt, ld2, 0);
+    if (e != cudaSuccess) return e;
+    GemmOp a2{s->yt + (long long)N * ld2, ld2, NK}, b2{s->St, N, 0};
+    e = gemm(st, nm * 2, N, N, NK, {s->yt, ld2, NK}, {s->Ct, N, 0}, grid_out, N, (long long)N * N, &a2, &b2);
+    if (e != cudaSuccess) return e;
+    nl += 3;
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  e = cudaMemcpyAsync(spec_out, s->x, state_bytes, cudaMemcpyDeviceToDevice, st);
+  if (spec_out != nullptr) e = cudaMemcpyAsync(spec_out, s->x, state_bytes, cudaMemcpyDeviceToDevice, st);
   if (n_launches) *n_launches = nl;
   return e;
 }

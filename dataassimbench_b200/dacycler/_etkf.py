@@ -2,9 +2,11 @@
 
 Mirrors `dabench.dacycler.ETKF` (dabench/dacycler/_etkf.py:19-62) and `DACycler.cycle`
 (dabench/dacycler/_dacycler.py:186-290).  The accelerated contract: the forecast
-model is the native `Lorenz96Model`, H is the default index gather and R the default
-`obs_error_sd**2 * I`.  Anything else (user-supplied dense H/R/B, callable h, other models)
-raises `NotImplementedError` -- there is deliberately no CPU fallback.
+model wraps one of the package's generators -- `Lorenz96Model` runs the device-resident cycler, `Lorenz63Model` /
+`SQGTurbModel` (or any Model with a `_forecast_members_device`) alternate the analysis kernels and the model's
+ensemble forecast on the device -- H is the default index gather and R diagonal.  Anything else (user-supplied
+dense H/B, callable h, models without a device forecast) raises `NotImplementedError` -- there is deliberately no
+CPU fallback.
 """
 import numpy as np
 
@@ -146,9 +148,11 @@ class ETKF(DACycler):
             raise NotImplementedError('user-supplied H / B matrices are outside the accelerated path '
                                       '(default index-gather H only)')
         gen = self._lorenz96_generator()
-        if gen is None:
+        generic = gen is None
+        if generic and not callable(getattr(self.model_obj, '_forecast_members_device', None)):
             raise NotImplementedError('the accelerated ETKF.cycle() needs model_obj to be a Model wrapping a '
-                                      'dataassimbench_b200.data.Lorenz96 generator (e.g. model.Lorenz96Model)')
+                                      'dataassimbench_b200.data generator (model.Lorenz96Model, Lorenz63Model, '
+                                      'SQGTurbModel), i.e. one with a device forecast for the whole ensemble')
         w = self._prepare_cycle(input_state, start_time, obs_vector, n_cycles, obs_error_sd,
                                 analysis_window, analysis_time_in_window)
         if self._data_vars != ['x'] or self._observed_vars != ['x']:
@@ -187,13 +191,14 @@ class ETKF(DACycler):
         sysidx = np.ascontiguousarray(sysidx.reshape(vals.shape), dtype=np.int64)
         cfg = _native.CycleConfig(
             system_dim=n_sys, ensemble_dim=n_ens, n_steps=self.steps_per_window - 1,
-            model_dt=float(gen.delta_t), forcing=float(gen.forcing_term),
+            model_dt=float(gen.delta_t) if gen is not None else float(self.delta_t),
+            forcing=float(gen.forcing_term) if gen is not None else 0.0,
             rho=float(self.multiplicative_inflation), obs_error_sd=float(sd),
             n_obs_times=vals.shape[0], n_obs=vals.shape[1], stationary=int(w['stationary']),
             n_cycles=int(n_cycles), t_pad=w['padded'].shape[1], rank=0, world=1)
         state_dim = [d for d in _xr.var_dims(input_state, 'x') if d != 'ensemble']
-        return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx, sd_slots=sd_slots,
-                    padded=np.ascontiguousarray(w['padded']), state_dim=state_dim[0] if state_dim else 'index')
+        return dict(cfg=cfg, X0=X0, vals=vals, sysidx=sysidx, sd_slots=sd_slots, generic=generic,
+                    stationary=bool(w['stationary']), padded=np.ascontiguousarray(w['padded']), state_dim=state_dim[0] if state_dim else 'index')
 
     # ------------------------------------------------------------------ grid sharding (one rank per GPU)
     def _shard_group(self, N, S):
@@ -245,6 +250,61 @@ class ETKF(DACycler):
             out[c0:c1] = got.cpu().numpy()
         return out
 
+    # ------------------------------------------------------------------ any other model with a device forecast
+    def _cycle_generic(self, p, return_forecast):
+        """The reference's per-cycle body (dabench/dacycler/_dacycler.py:110-141) for a model other than Lorenz-96:
+        the observation rows of every cycle are laid out once (time mask = rows dropped, NaN slots of a moving
+        network masked), then analysis (`dab_etkf_analysis_f64`) and the model's ensemble forecast alternate on the
+        device; the ensemble never visits the host.  What a cycle returns is row 0 of the model's trajectory, as
+        in the reference (:288-290) -- the analysis itself for Lorenz-63, one step past it for the SQGTurb wrapper."""
+        import torch
+        from .._runtime import handle
+        if return_forecast:
+            raise NotImplementedError('return_forecast=True is implemented for the Lorenz-96 cycler only')
+        if p['sd_slots'] is not None:
+            raise NotImplementedError('a vector obs_error_sd is implemented for the Lorenz-96 cycler only')
+        cfg = p['cfg']
+        k, N, n_cycles = cfg.ensemble_dim, cfg.system_dim, cfg.n_cycles
+        vals = p['vals'].cpu().numpy() if getattr(p['vals'], 'is_cuda', False) else p['vals']
+        H = handle()
+        stream = torch.cuda.current_stream().cuda_stream
+        rows_y, rows_i, offs = [], [], [0]
+        for c in range(n_cycles):
+            t = p['padded'][c]
+            t = t[t > 0] - 1
+            y, idx = vals[t].ravel(), p['sysidx'][t].ravel()
+            if not p['stationary']:
+                keep = ~np.isnan(y)
+                y, idx = y[keep], idx[keep]
+            if idx.size and (idx.min() < 0 or idx.max() >= N):
+                raise ValueError('system_index out of range for system_dim %d' % N)
+            rows_y.append(y); rows_i.append(idx); offs.append(offs[-1] + y.size)
+        y_all = torch.from_numpy(np.concatenate(rows_y) if rows_y else np.zeros(0)).cuda()
+        i_all = torch.from_numpy((np.concatenate(rows_i) if rows_i else np.zeros(0)).astype(np.int64)).cuda()
+        X = torch.from_numpy(p['X0']).cuda()
+        Xa = torch.empty_like(X)
+        out = torch.empty((n_cycles, k, N), dtype=torch.float64, device='cuda')
+        sd, rho = float(cfg.obs_error_sd), float(cfg.rho)
+        # a window without a valid observation is NOT the reference's empty-R branch (its R still has the padded
+        # rows, all masked: C = 0, inflation only): one masked dummy row says so to the analysis entry point
+        y0 = torch.zeros(1, dtype=torch.float64, device='cuda')
+        i0 = torch.zeros(1, dtype=torch.int64, device='cuda')
+        m0 = torch.zeros(1, dtype=torch.uint8, device='cuda')
+        empty_R = vals.shape[1] == 0 or p['padded'].shape[1] == 0
+        for c in range(n_cycles):
+            a, b = offs[c], offs[c + 1]
+            if b > a:
+                H.etkf_analysis(X, Xa, y_all[a:b], i_all[a:b], None, sd, rho, N, k, b - a, stream)
+            elif empty_R:
+                H.etkf_analysis(X, Xa, None, None, None, sd, rho, N, k, 0, stream)
+            else:
+                H.etkf_analysis(X, Xa, y0, i0, m0, sd, rho, N, k, 1, stream)
+            X, first = self.model_obj._forecast_members_device(Xa, self.steps_per_window)
+            out[c] = first
+            X = X.contiguous()
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy()
+
     # ------------------------------------------------------------------ the call
     def cycle(self, input_state, start_time, obs_vector, n_cycles, obs_error_sd=None,
               analysis_window=0.2, analysis_time_in_window=None, return_forecast=False):
@@ -259,6 +319,8 @@ class ETKF(DACycler):
                        analysis_window, analysis_time_in_window)
         cfg = p['cfg']
         k, N, S = cfg.ensemble_dim, cfg.system_dim, cfg.n_steps
+        if p['generic']:
+            return _xr.new_dataset({'x': (('cycle', 'ensemble', p['state_dim']), self._cycle_generic(p, return_forecast))})
         group = self._shard_group(N, S)
         if group is not None:
             if return_forecast:

@@ -179,6 +179,19 @@ class SQGTurb(Data):
         res = out if on_dev else out.cpu().numpy()
         return (res, traj[:n_steps]) if return_grid_traj else res
 
+    def forecast_members_grid(self, grid, n_steps, return_grid_traj=False):
+        """The same for GRIDDED members [k, 2, N, N] that live on the device (CUDA tensor in, CUDA tensors out):
+        rfft2 in, `n_steps` RK4 steps, irfft2 out, all in `dab_sqg_forecast_grid_f64`."""
+        import torch
+        H = self._setup_device()
+        x = grid.to(device='cuda', dtype=torch.float64).contiguous()
+        k = x.shape[0]
+        out = torch.empty_like(x)
+        traj = torch.empty((max(n_steps, 1), k, 2, self.N, self.N), dtype=torch.float64, device='cuda') \
+            if return_grid_traj else None
+        H.sqg_forecast_grid(x, out, None, traj, k, n_steps, torch.cuda.current_stream().cuda_stream)
+        return (out, traj[:n_steps]) if return_grid_traj else out
+
     def integrate(self, f, x0, t_final, delta_t=None, include_x0=True, t=None, **kwargs):
         """:441-504.  `f` is unused, as in the reference."""
         pvspec = self.map1dto2d(x0)

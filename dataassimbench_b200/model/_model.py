@@ -47,6 +47,17 @@ class Lorenz63Model(Model):
         new_vec = self.model_obj.generate(x0=_xr.var_array(state_vec, 'x'), n_steps=n_steps)
         return new_vec.isel(time=-1), new_vec
 
+    def _forecast_members_device(self, X, n_steps):
+        """All members at once on the device, for the cyclers: X [k, 3] (CUDA) -> (last point, first point) of the
+        `n_steps`-point trajectories `forecast` returns member by member."""
+        import torch
+        from .._runtime import handle
+        g = self.model_obj
+        out = torch.empty_like(X)
+        handle().l63_forecast(X, out, None, X.shape[0], int(n_steps) - 1, float(g.delta_t), float(g.sigma),
+                              float(g.rho), float(g.beta), torch.cuda.current_stream().cuda_stream)
+        return out, X
+
 
 class SQGTurbModel(Model):
     """Wraps a `data.SQGTurb` generator behind the same plugin point: `state_vec` holds the gridded potential
@@ -62,6 +73,22 @@ class SQGTurbModel(Model):
                          delta_t=delta_t or model_obj.delta_t, model_obj=model_obj)
 
     def forecast(self, state_vec, n_steps=2):
-        x0 = self.model_obj.fft2_2dto1d(_xr.var_array(state_vec, 'pv'))
-        new_vec = self.model_obj.generate(x0=x0, n_steps=n_steps)
-        return new_vec.isel(time=-1), new_vec
+        if 'pv' in state_vec:
+            pv = _xr.var_array(state_vec, 'pv')
+        else:       # the cyclers' flattened state `x[index]` (dabench/dacycler/_etkf.py:213 knows no other name)
+            pv = _xr.var_array(state_vec, 'x').reshape(self.model_obj.original_dim)
+        new_vec = self.model_obj.generate(x0=self.model_obj.fft2_2dto1d(pv), n_steps=n_steps)
+        if 'pv' in state_vec:
+            return new_vec.isel(time=-1), new_vec
+        flat = _xr.var_array(new_vec, 'pv').reshape(new_vec['pv'].shape[0], -1)
+        flat_ds = _xr.new_dataset({'x': (('time', 'index'), flat)}, coords={'time': _xr.var_array(new_vec, 'time')})
+        return flat_ds.isel(time=-1), flat_ds
+
+    def _forecast_members_device(self, X, n_steps):
+        """All members at once on the device, for the cyclers: X [k, 2 N N] flattened gridded states (CUDA) ->
+        (last row, first row) of the trajectories `forecast` returns member by member.  `generate(n_steps)` emits
+        the states after steps 1 .. n_steps + 1 (the reference's scan quirk), so the first row is one step past X."""
+        g = self.model_obj
+        k = X.shape[0]
+        last, traj = g.forecast_members_grid(X.reshape(k, 2, g.N, g.N), int(n_steps) + 1, return_grid_traj=True)
+        return last.reshape(k, -1), traj[0].reshape(k, -1)

@@ -106,6 +106,13 @@ typedef struct dab_sqg_config {
 DAB_API int dab_sqg_setup(dab_handle* h, const dab_sqg_config* cfg);
 DAB_API int dab_sqg_forecast_c128(dab_handle* h, const double* spec_in, double* spec_out, double* traj_grid,
                           int members, int n_steps, void* stream);
+/* The same for GRIDDED members -- what a Model.forecast wrapper around the generator sees (state_vec in grid space,
+ * SQGTurb.fft2_2dto1d in, :420-426, SQGTurb.ifft2 out, :496): rfft2 on the way in and irfft2 on the way out are two
+ * more constant-matrix products, so an ensemble cycles between analysis and forecast without leaving the device.
+ *   grid_in, grid_out  dev [members][2][n][n] real (may alias);  spec_out nullable: the final spectral states;
+ *   traj_grid as above.  n_steps = 0 returns the projection irfft2(rfft2(grid_in)). */
+DAB_API int dab_sqg_forecast_grid_f64(dab_handle* h, const double* grid_in, double* grid_out, double* spec_out,
+                              double* traj_grid, int members, int n_steps, void* stream);
 
 /* ---- K2: observation operator as a gather ----------------------------------------------
  * Replaces the dense one-hot H (DACycler._calc_default_H, dabench/dacycler/_dacycler.py:58-66),

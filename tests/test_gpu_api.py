@@ -557,3 +557,68 @@ def test_device_resident_observations_go_straight_into_the_cycler(stationary):
     else:
         # the host route drops NaN slots, the device route keeps them as weightless rows: same sums, other grouping
         assert rel_err(b, a) < 1e-10
+
+
+# ------------------------------------------------------------------ ETKF.cycle() with the other generators
+def _cycle_vs_oracle(dc, init_x, start_time, obs, sd, window, n_cycles, fc, delta_t, stationary=True):
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), init_x)})
+    out = dc.cycle(input_state=init, start_time=start_time, obs_vector=obs, obs_error_sd=sd,
+                   analysis_window=window, n_cycles=n_cycles)
+    ref = o_etkf.cycle(init_x, float(start_time), np.asarray(obs['x'].values).reshape(len(obs['time'].values), -1),
+                       np.asarray(obs['time'].values), np.asarray(obs['system_index'].values)[0], n_cycles, sd, fc,
+                       delta_t, stationary_observers=stationary, analysis_window=window, return_forecast=False,
+                       rho=dc.multiplicative_inflation, literal=True)
+    return np.asarray(out['x'].values), ref
+
+
+def test_etkf_cycle_with_a_lorenz63_model():
+    """The reference's ETKF takes any Model; here `Lorenz63Model`: analysis kernels and the
+    Lorenz-63 ensemble forecast alternate on the device.  Against the oracle cycle with the same RK4."""
+    from oracle import l63 as o_l63
+    gen = dab.data.Lorenz63(delta_t=0.01)
+    nature = gen.generate(n_steps=400)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(5, 400, 10)],
+                                random_location_count=2, error_sd=0.7, random_seed=5,
+                                stationary_observers=True).observe()
+    model = dab.model.Lorenz63Model(model_obj=dab.data.Lorenz63(delta_t=0.01))
+    dc = dab.dacycler.ETKF(system_dim=3, delta_t=0.01, ensemble_dim=6, model_obj=model, multiplicative_inflation=1.05)
+    x0 = nature['x'].values[0] + threefry.normal(3, (6, 3))
+    fc = lambda x, n: o_l63.generate_rk4(x, n, 0.01)
+    out, ref = _cycle_vs_oracle(dc, x0, 0.0, obs, 0.7, 0.1, 30, fc, 0.01)
+    assert out.shape == (30, 6, 3) and np.all(np.isfinite(out))
+    assert rel_err(out, ref) < 1e-9
+    # windows without observations (every second one): inflation only, not the empty-R collapse
+    obs2 = dab.observer.Observer(nature, times=nature['time'].values[np.arange(5, 400, 20)],
+                                 random_location_count=3, error_sd=0.7, random_seed=5).observe()
+    out2, ref2 = _cycle_vs_oracle(dc, x0, 0.0, obs2, 0.7, 0.1, 10, fc, 0.01)
+    assert rel_err(out2, ref2) < 1e-9
+    assert np.std(out2[1], axis=0).min() > 1e-3
+
+
+def test_etkf_cycle_with_an_sqgturb_model():
+    """`SQGTurbModel` behind ETKF.cycle(): the flattened gridded potential vorticity is the state, every cycle is
+    analysis -> rfft2 -> RK4 steps -> irfft2 on the device.  Against the oracle cycle whose forecast is the oracle
+    generator (same scan quirk: a cycle returns the state one step past its analysis)."""
+    from oracle import sqgturb as o_sqg
+    from test_gpu_sqgturb import members
+    N, k, sd = 16, 6, 50.0
+    pv = members(N, k + 1, seed=9)
+    gen = dab.data.SQGTurb(pv=pv[0], precision='double')
+    nat = gen.generate(n_steps=12)
+    flat = np.asarray(nat['pv'].values).reshape(13, -1)
+    nature = _xr.new_dataset({'x': (('time', 'index'), flat)},
+                             coords={'time': np.asarray(nat['time'].values), 'index': np.arange(flat.shape[1])},
+                             attrs={'system_dim': flat.shape[1], 'delta_t': 900.0})
+    obs = dab.observer.Observer(nature, times=np.asarray(nat['time'].values)[1::2], random_location_count=120,
+                                error_sd=sd, random_seed=3).observe()
+    model = dab.model.SQGTurbModel(model_obj=dab.data.SQGTurb(pv=pv[0], precision='double'))
+    dc = dab.dacycler.ETKF(system_dim=2 * N * N, delta_t=900, ensemble_dim=k, model_obj=model)
+    x0 = pv[1:].reshape(k, -1)
+    fc = lambda x, n: o_sqg.generate(x.reshape(2, N, N), n, precision='double')[0].reshape(n + 1, -1)
+    out, ref = _cycle_vs_oracle(dc, x0, 0.0, obs, sd, 1800.0, 4, fc, 900)
+    assert out.shape == (4, k, 2 * N * N) and np.all(np.isfinite(out))
+    assert rel_err(out, ref) < 1e-9
+    # the member-by-member plugin call the reference's ETKF would make gives the same forecast
+    one = _xr.new_dataset({'x': (('index',), out[0, 0])})
+    last, traj = model.forecast(one, n_steps=3)
+    assert traj['x'].shape == (4, 2 * N * N)
