@@ -51,7 +51,7 @@ struct GemmArgs {
 constexpr int GK = 16, LDA = GK + 4;
 
 template <int WT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, WT >= 4 ? 3 : 4)
 sqg_gemm_kernel(const GemmArgs g) {
   constexpr int BT = 16 * WT, LDB = BT + 4, NP = 2 * WT;     // NP = BT * GK / 128 elements per thread and operand
   __shared__ __align__(16) double As[BT * LDA];
@@ -69,19 +69,60 @@ sqg_gemm_kernel(const GemmArgs g) {
   const int kt = (g.K + GK - 1) / GK;
   const int total = kt * g.nseg;
   double ra[NP], rb[NP];
-  auto fetch = [&](int it) {
-    const int seg = it / kt, k0 = (it - seg * kt) * GK;
-    const double* A = g.A[seg].p + b * g.A[seg].bs;
-    const double* B = g.B[seg].p + b * g.B[seg].bs;
+  // Loader geometry, fixed for the whole kernel: element p of this thread is A[row (tid >> 4) + 8 p][k (tid & 15)] and
+  // B[k (tid + 128 p) / BT][column (tid + 128 p) % BT] of the tile.  Everything that does not change from k-tile to
+  // k-tile -- base pointers of the segment, the B offsets, which rows / columns exist -- is computed once (the first
+  // version recomputed it per element and spent 13 integer instructions per load: IMAD 2.5x the DMMA count).
+  unsigned a_ok = 0, b_ok = 0;
+  int a_off[NP], b_off[NP];                  // element offsets inside a k-tile (32-bit: the host checks 64 rs < 2^31)
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int idx = tid + 128 * p;
+    if (i0 + (idx >> 4) < g.m) a_ok |= 1u << p;
+    if (j0 + idx % BT < g.n) b_ok |= 1u << p;
+  }
+  const bool interior = i0 + BT <= g.m && j0 + BT <= g.n;
+  const int a_kk = tid & 15;
+  const double* Ab = nullptr;
+  const double* Bb = nullptr;
+  long long b_rs = 0;
+  auto segment = [&](int seg) {
+    const int ars = (int)g.A[seg].rs, brs = (int)g.B[seg].rs;
+    Ab = g.A[seg].p + b * g.A[seg].bs + (long long)(i0 + (tid >> 4)) * g.A[seg].rs + a_kk;
+    Bb = g.B[seg].p + b * g.B[seg].bs + j0;
+    b_rs = g.B[seg].rs;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const int idx = tid + 128 * p;
-      const int i = i0 + (idx >> 4), k = k0 + (idx & 15);
-      ra[p] = (i < g.m && k < g.K) ? A[(long long)i * g.A[seg].rs + k] : 0.0;
-      const int kb = k0 + idx / BT, j = j0 + idx % BT;
-      rb[p] = (kb < g.K && j < g.n) ? B[(long long)kb * g.B[seg].rs + j] : 0.0;
+      a_off[p] = 8 * p * ars;
+      b_off[p] = (idx / BT) * brs + idx % BT;
     }
   };
+  auto fetch = [&](int it) {
+    if (it == 0) segment(0);
+    else if (it == kt) segment(1);
+    const int k0 = (it >= kt ? it - kt : it) * GK;
+    const double* A = Ab + k0;
+    const double* B = Bb + (long long)k0 * b_rs;
+    if (interior && k0 + GK <= g.K) {                      // CTA-uniform: no predicates, no branches around loads
+#pragma unroll
+      for (int p = 0; p < NP; ++p) { ra[p] = A[a_off[p]]; rb[p] = B[b_off[p]]; }
+    } else if (k0 + GK <= g.K) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        ra[p] = (a_ok >> p & 1u) ? A[a_off[p]] : 0.0;
+        rb[p] = (b_ok >> p & 1u) ? B[b_off[p]] : 0.0;
+      }
+    } else {                                               // ragged last k-tile
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        ra[p] = ((a_ok >> p & 1u) && k0 + a_kk < g.K) ? A[a_off[p]] : 0.0;
+        rb[p] = ((b_ok >> p & 1u) && k0 + (tid + 128 * p) / BT < g.K) ? B[b_off[p]] : 0.0;
+      }
+    }
+  };
+  const int last_rem = g.K - (kt - 1) * GK;
+  const int last_ksteps = last_rem >= GK ? GK / 4 : (last_rem + 3) >> 2;
   fetch(0);
   for (int it = 0; it < total; ++it) {
     __syncthreads();
@@ -92,9 +133,8 @@ sqg_gemm_kernel(const GemmArgs g) {
       Bs[(idx / BT) * LDB + idx % BT] = rb[p];
     }
     __syncthreads();
-    const int k0 = (it % kt) * GK;
-    const int rem = g.K - k0;
-    const int ksteps = rem >= GK ? GK / 4 : (rem + 3) >> 2;     // a ragged last k-tile only pays for its own k-steps
+    // a ragged last k-tile (of either segment) only pays for its own k-steps
+    const int ksteps = (it == kt - 1 || it == total - 1) ? last_ksteps : GK / 4;
     if (it + 1 < total) fetch(it + 1);
     for (int ks = 0; ks < ksteps; ++ks) {
       double av[WT], bv[WT];
@@ -128,6 +168,8 @@ cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, Gem
   g.A[0] = A1; g.B[0] = B1; g.nseg = 1;
   if (A2 != nullptr) { g.A[1] = *A2; g.B[1] = *B2; g.nseg = 2; }
   g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.c_cs = c_cs; g.m = m; g.n = n; g.K = K;
+  for (int sgi = 0; sgi < g.nseg; ++sgi)
+    if (g.A[sgi].rs >= (1ll << 25) || g.B[sgi].rs >= (1ll << 25)) return cudaErrorInvalidValue;   // 32-bit tile offsets
   // tile edge with the least padded work, weighted by the fragment loads a DMMA costs at that warp tile
   // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured, 48 beats 32 by 20 % at equal padding
   int best = 64;
