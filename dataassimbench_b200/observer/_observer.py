@@ -1,7 +1,8 @@
 """Observation sampling: the input contract of `ETKF.cycle()`.
 
 Mirrors `dabench.observer.Observer` (dabench/observer/_observer.py:89-366) for single-variable
-1-D states (Lorenz-96).  Index sets must be bit-compatible with the reference, so the one
+states: 1-D (`x[time, index]`, Lorenz-96 / -63) or gridded (`pv[time, level, x, y]`, SQGTurb: one location draw
+per coordinate, with replacement, :223-234).  Index sets must be bit-compatible with the reference, so the one
 `numpy.random.default_rng(random_seed)` stream is consumed in the reference's order: times
 (:192-207), then locations (:209-271), then ONE normal draw covering every slot (:346-348).
 The draws are host-side NumPy.  The sampling itself -- `state_vec.sel(time=...).sel(locations)`,
@@ -43,14 +44,34 @@ class Observer:
             return int(self.random_location_count)
         return int(np.sum(rng.binomial(1, p=self.random_location_density, size=n)))
 
+    def _draw_locations(self, rng, coords, count):
+        """One `choice` per non-time coordinate, in the Dataset's order; with more than one coordinate the draws
+        are WITH replacement (dabench/observer/_observer.py:223-234, :258-269).  Returns flattened-state indices."""
+        replace = len(coords) > 1
+        picks = [rng.choice(c, size=count, replace=replace, shuffle=False) for c in coords]
+        if len(coords) == 1:
+            return np.asarray(picks[0], dtype=np.int64)
+        return np.ravel_multi_index(tuple(np.asarray(q, dtype=np.int64) for q in picks),
+                                    tuple(len(c) for c in coords)).astype(np.int64)
+
     def observe(self):
-        traj = _xr.var_data(self.state_vec, 'x')
+        # single-variable states: `x[time, index]` (Lorenz-96 / -63) or any `var[time, c1, c2, ...]` such as the
+        # SQGTurb `pv[time, level, x, y]`; locations are drawn per coordinate and sampled from the flattened state
+        names = [str(v) for v in self.state_vec.data_vars]
+        var = 'x' if 'x' in names else names[0]
+        self._var = var
+        dims = tuple(_xr.var_dims(self.state_vec, var))
+        if not dims or dims[0] != 'time':
+            raise ValueError("the state variable must have 'time' as its first dimension")
+        traj = _xr.var_data(self.state_vec, var)
         on_device = _is_cuda_tensor(traj)
         if not on_device:
-            traj = _xr.var_array(self.state_vec, 'x')
+            traj = _xr.var_array(self.state_vec, var)
         traj_t = _xr.var_array(self.state_vec, 'time')
+        grid_shape = tuple(traj.shape[1:])
+        traj = traj.reshape(traj.shape[0], -1)
         n_t, n_sys = traj.shape
-        index = np.arange(n_sys)
+        coords = [np.arange(n) for n in grid_shape]           # positional coordinates, as Data.generate builds them
         rng = np.random.default_rng(self.random_seed)
 
         if self.times is None:
@@ -68,7 +89,7 @@ class Observer:
         if self.stationary_observers:
             if self.locations is None:
                 count = self._draw_count(rng, n_sys)
-                locs = rng.choice(index, size=count, replace=False, shuffle=False)
+                locs = self._draw_locations(rng, coords, count)
             else:
                 locs = np.asarray(_loc_array(self.locations), dtype=np.int64)
             self.location_dim = len(locs)
@@ -80,7 +101,7 @@ class Observer:
                     counts = [int(self.random_location_count)] * self.time_dim
                 else:       # every count first, then every location draw (:246-268)
                     counts = [self._draw_count(rng, n_sys) for _ in range(self.time_dim)]
-                per_time = [rng.choice(index, size=c, replace=False, shuffle=False) for c in counts]
+                per_time = [self._draw_locations(rng, coords, c) for c in counts]
             else:
                 per_time = [np.asarray(_loc_array(l), dtype=np.int64) for l in self.locations]
                 counts = [len(l) for l in per_time]
@@ -105,10 +126,10 @@ class Observer:
                     clean[i, :c] = traj[pos[i], sysidx[i, :c]]
             values = clean + errors[0]
         return _xr.new_dataset(
-            {'x': (('time', 'observations'), values),
+            {var: (('time', 'observations'), values),
              'system_index': (('variable', 'time', 'observations'), sysidx[None]),
              'errors': (('variable', 'time', 'observations'), errors)},
-            coords={'time': self.times, 'variable': np.array(['x'])},
+            coords={'time': self.times, 'variable': np.array([var])},
             attrs={'stationary_observers': self.stationary_observers, 'error_sd': self.error_sd})
 
     def _sample_on_device(self, traj, pos, sysidx, counts, errors):

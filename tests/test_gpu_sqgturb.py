@@ -91,3 +91,23 @@ def test_sqg_model_forecast_plugin_contract():
     assert got.shape == (4, 2, N, N)
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-10
     assert np.array_equal(_xr.var_array(last, 'pv'), got[-1])
+
+
+def test_reference_obs_sqgturb_recipe_through_the_package():
+    """tests/observer_base_test.py:240-261 written against this package: default SQGTurb, 10 steps on the GPU, the
+    seeded Observer on the gridded trajectory -- every golden of the reference's test."""
+    import dataassimbench_b200 as dab
+    sqg = dab.data.SQGTurb()
+    ds = sqg.generate(n_steps=10)
+    obs_vec = dab.observer.Observer(ds, random_time_density=0.3, random_location_density=0.01, error_sd=25.).observe()
+    assert obs_vec['pv'].shape == (2, 204)
+    assert obs_vec['time'].shape[0] == 2
+    sysidx = np.asarray(obs_vec['system_index'].values)
+    errors = np.asarray(obs_vec['errors'].values)
+    vals = np.asarray(obs_vec['pv'].values)
+    assert sysidx[0, 0, 0] == 10130
+    flat = np.asarray(ds['pv'].values).reshape(11, -1)
+    assert vals[1, 123] == pytest.approx(flat[10, sysidx[0, 1, 123]] + errors[0, 1, 123])
+    assert vals[0, 44] == pytest.approx(2128.20749725)
+    assert errors[0, 1, 187] == pytest.approx(25.714826330507496)
+    assert np.allclose(np.asarray(obs_vec['time'].values), np.array([2700., 9000.]))

@@ -92,3 +92,29 @@ def test_host_mirror_argument_errors():
         SQGTurb(pv=np.zeros((2, 8, 8)), symmetric=False)
     g = SQGTurb()
     assert g.N == 96 and g.system_dim == 18432 and g.x0.dtype == np.complex64
+
+
+def test_observer_on_a_gridded_state_draws_like_the_reference():
+    """Observer on `pv[time, level, x, y]` (the reference's test_obs_sqgturb, tests/observer_base_test.py:240-261):
+    the seeded draws -- times, count, one `choice` per coordinate with replacement, errors -- reproduce the
+    reference's goldens; the values are the flattened state at those indices plus the errors."""
+    import dataassimbench_b200 as dab
+    from dataassimbench_b200 import _xr
+    rng = np.random.default_rng(0)
+    pv = rng.standard_normal((11, 2, 96, 96))
+    ds = _xr.new_dataset({'pv': (('time', 'level', 'x', 'y'), pv)},
+                         coords={'time': np.arange(11) * 900.0, 'level': np.arange(2), 'x': np.arange(96),
+                                 'y': np.arange(96)}, attrs={'system_dim': 18432, 'delta_t': 900.0})
+    obs = dab.observer.Observer(ds, random_time_density=0.3, random_location_density=0.01, error_sd=25.).observe()
+    assert obs['pv'].shape == (2, 204)
+    assert np.allclose(np.asarray(obs['time'].values), [2700., 9000.])
+    sysidx = np.asarray(obs['system_index'].values)
+    errors = np.asarray(obs['errors'].values)
+    assert sysidx.shape == (1, 2, 204) and sysidx[0, 0, 0] == 10130
+    assert errors[0, 1, 187] == pytest.approx(25.714826330507496)
+    vals = np.asarray(obs['pv'].values)
+    flat = pv.reshape(11, -1)
+    assert vals[1, 123] == pytest.approx(flat[10, sysidx[0, 1, 123]] + errors[0, 1, 123])
+    assert np.array_equal(vals, flat[[3, 10]][:, sysidx[0, 0]] + errors[0])
+    tsel, count, lev, xx, yy, err = reference_observer_draws(96, 11)
+    assert np.array_equal(sysidx[0, 0], lev * 96 * 96 + xx * 96 + yy) and np.array_equal(errors, err)
