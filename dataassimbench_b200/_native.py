@@ -187,6 +187,7 @@ class Handle:
                   hyperdiff, pvspec_eq):
         """Tables of the surface-QG generator (host arrays; copied to the device by the call)."""
         import numpy as np
+        self._sqg_owner = None          # data.SQGTurb marks the handle after a successful set-up of ITS tables
         f8 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
         arrs = [f8(kx), f8(ly), f8(hovermu), f8(tanhmu), f8(sinhmu), f8(ksqlsq), f8(hyperdiff),
                 np.ascontiguousarray(np.asarray(pvspec_eq, dtype=np.complex128))]

@@ -486,7 +486,7 @@ int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_out, doubl
 
 int dab_sqg_setup(dab_handle* h, const dab_sqg_config* cfg) {
   DAB_ARG(h, h != nullptr && cfg != nullptr);
-  DAB_ARG(h, cfg->n >= 4 && cfg->n % 4 == 0 && cfg->n <= 4096);
+  DAB_ARG(h, cfg->n >= 4 && cfg->n % 4 == 0 && cfg->n <= 1024);
   DAB_ARG(h, cfg->kx && cfg->ly && cfg->hovermu && cfg->tanhmu && cfg->sinhmu && cfg->ksqlsq && cfg->hyperdiff && cfg->pvspec_eq);
   DAB_CUDA(h, cudaSetDevice(h->device));
   DAB_CUDA(h, cudaDeviceSynchronize());
@@ -504,7 +504,7 @@ int dab_sqg_forecast_c128(dab_handle* h, const double* spec_in, double* spec_out
                           int n_steps, void* stream) {
   DAB_ARG(h, h != nullptr);
   if (h->sqg == nullptr) return fail(h, -1, "dab_sqg_forecast_c128: call dab_sqg_setup first");
-  DAB_ARG(h, members >= 0 && n_steps >= 0);
+  DAB_ARG(h, members >= 0 && members <= 4096 && n_steps >= 0);      // (member, field) is a grid dimension
   DAB_ARG(h, members == 0 || (spec_in != nullptr && spec_out != nullptr));
   if (members == 0) return 0;
   DAB_CUDA(h, cudaSetDevice(h->device));
@@ -518,7 +518,7 @@ int dab_sqg_forecast_grid_f64(dab_handle* h, const double* grid_in, double* grid
                               int members, int n_steps, void* stream) {
   DAB_ARG(h, h != nullptr);
   if (h->sqg == nullptr) return fail(h, -1, "dab_sqg_forecast_grid_f64: call dab_sqg_setup first");
-  DAB_ARG(h, members >= 0 && n_steps >= 0);
+  DAB_ARG(h, members >= 0 && members <= 4096 && n_steps >= 0);
   DAB_ARG(h, members == 0 || (grid_in != nullptr && grid_out != nullptr));
   if (members == 0) return 0;
   DAB_CUDA(h, cudaSetDevice(h->device));

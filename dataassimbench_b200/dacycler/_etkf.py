@@ -259,8 +259,6 @@ class ETKF(DACycler):
         in the reference (:288-290) -- the analysis itself for Lorenz-63, one step past it for the SQGTurb wrapper."""
         import torch
         from .._runtime import handle
-        if return_forecast:
-            raise NotImplementedError('return_forecast=True is implemented for the Lorenz-96 cycler only')
         if p['sd_slots'] is not None:
             raise NotImplementedError('a vector obs_error_sd is implemented for the Lorenz-96 cycler only')
         cfg = p['cfg']
@@ -283,7 +281,7 @@ class ETKF(DACycler):
         i_all = torch.from_numpy((np.concatenate(rows_i) if rows_i else np.zeros(0)).astype(np.int64)).cuda()
         X = torch.from_numpy(p['X0']).cuda()
         Xa = torch.empty_like(X)
-        out = torch.empty((n_cycles, k, N), dtype=torch.float64, device='cuda')
+        out = None
         sd, rho = float(cfg.obs_error_sd), float(cfg.rho)
         # a window without a valid observation is NOT the reference's empty-R branch (its R still has the padded
         # rows, all masked: C = 0, inflation only): one masked dummy row says so to the analysis entry point
@@ -299,8 +297,12 @@ class ETKF(DACycler):
                 H.etkf_analysis(X, Xa, None, None, None, sd, rho, N, k, 0, stream)
             else:
                 H.etkf_analysis(X, Xa, y0, i0, m0, sd, rho, N, k, 1, stream)
-            X, first = self.model_obj._forecast_members_device(Xa, self.steps_per_window)
-            out[c] = first
+            X, first, rows = self.model_obj._forecast_members_device(Xa, self.steps_per_window, return_forecast)
+            # what the reference keeps of a cycle's trajectory: all but its last row (:281-287), or row 0 (:288-290)
+            keep = rows[:-1].permute(1, 0, 2) if return_forecast else first
+            if out is None:
+                out = torch.empty((n_cycles,) + tuple(keep.shape), dtype=torch.float64, device='cuda')
+            out[c] = keep
             X = X.contiguous()
         torch.cuda.current_stream().synchronize()
         return out.cpu().numpy()
@@ -320,7 +322,9 @@ class ETKF(DACycler):
         cfg = p['cfg']
         k, N, S = cfg.ensemble_dim, cfg.system_dim, cfg.n_steps
         if p['generic']:
-            return _xr.new_dataset({'x': (('cycle', 'ensemble', p['state_dim']), self._cycle_generic(p, return_forecast))})
+            dims = ('cycle', 'ensemble', 'cycle_timestep', p['state_dim']) if return_forecast else \
+                ('cycle', 'ensemble', p['state_dim'])
+            return _xr.new_dataset({'x': (dims, self._cycle_generic(p, return_forecast))})
         group = self._shard_group(N, S)
         if group is not None:
             if return_forecast:

@@ -93,7 +93,7 @@ class SQGTurb(Data):
         ktot = np.sqrt(self.ksqlsq)
         ktotcutoff = ft(pi * ft(N) / self.L)
         self.hyperdiff = np.exp((-self.delta_t / self.diff_efold) * (ktot / ktotcutoff) ** self.diff_order).astype(ft)
-        self._device_ready = False
+        self._device_token = object()
 
     def _wavenumbers(self, n, n_half, pi):
         ft = self._ft
@@ -154,11 +154,16 @@ class SQGTurb(Data):
                                     "the tendency when dealias=True")
         H = handle()
         N = self.N
+        # the handle keeps ONE generator's tables and DFT matrices: upload them only when another generator (or
+        # nobody) set it up last -- a cycler calls this once per cycle
+        if getattr(H, '_sqg_owner', None) is self._device_token:
+            return H
         H.sqg_setup(N, float(self.delta_t), float(self._ft(1.0) / self.tdiab), float(self.r), int(self.ekman),
                     int(bool(self.symmetric)),
                     kx=self.ik_pad[0, :N // 2 + 1].imag, ly=self.il[:, 0].imag, hovermu=self.Hovermu,
                     tanhmu=self.tanhmu, sinhmu=self.sinhmu, ksqlsq=self.ksqlsq, hyperdiff=self.hyperdiff,
                     pvspec_eq=self.pvspec_eq)
+        H._sqg_owner = self._device_token
         return H
 
     def forecast_members(self, spec, n_steps, return_grid_traj=False):

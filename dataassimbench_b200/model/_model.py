@@ -47,16 +47,19 @@ class Lorenz63Model(Model):
         new_vec = self.model_obj.generate(x0=_xr.var_array(state_vec, 'x'), n_steps=n_steps)
         return new_vec.isel(time=-1), new_vec
 
-    def _forecast_members_device(self, X, n_steps):
-        """All members at once on the device, for the cyclers: X [k, 3] (CUDA) -> (last point, first point) of the
-        `n_steps`-point trajectories `forecast` returns member by member."""
+    def _forecast_members_device(self, X, n_steps, want_rows=False):
+        """All members at once on the device, for the cyclers: X [k, 3] (CUDA) -> (last point, first point, every
+        point [n_steps, k, 3] or None) of the `n_steps`-point trajectories `forecast` returns member by member."""
         import torch
         from .._runtime import handle
         g = self.model_obj
         out = torch.empty_like(X)
-        handle().l63_forecast(X, out, None, X.shape[0], int(n_steps) - 1, float(g.delta_t), float(g.sigma),
+        n = int(n_steps) - 1
+        traj = torch.empty((max(n, 1), X.shape[0], 3), dtype=torch.float64, device=X.device) if want_rows else None
+        handle().l63_forecast(X, out, traj if n > 0 else None, X.shape[0], n, float(g.delta_t), float(g.sigma),
                               float(g.rho), float(g.beta), torch.cuda.current_stream().cuda_stream)
-        return out, X
+        rows = torch.cat([X[None], traj[:n]], dim=0) if want_rows else None
+        return out, X, rows
 
 
 class SQGTurbModel(Model):
@@ -84,11 +87,13 @@ class SQGTurbModel(Model):
         flat_ds = _xr.new_dataset({'x': (('time', 'index'), flat)}, coords={'time': _xr.var_array(new_vec, 'time')})
         return flat_ds.isel(time=-1), flat_ds
 
-    def _forecast_members_device(self, X, n_steps):
+    def _forecast_members_device(self, X, n_steps, want_rows=False):
         """All members at once on the device, for the cyclers: X [k, 2 N N] flattened gridded states (CUDA) ->
-        (last row, first row) of the trajectories `forecast` returns member by member.  `generate(n_steps)` emits
-        the states after steps 1 .. n_steps + 1 (the reference's scan quirk), so the first row is one step past X."""
+        (last row, first row, every row or None) of the trajectories `forecast` returns member by member.
+        `generate(n_steps)` emits the states after steps 1 .. n_steps + 1 (the reference's scan quirk), so the first
+        row is one step past X and there are n_steps + 1 rows."""
         g = self.model_obj
         k = X.shape[0]
         last, traj = g.forecast_members_grid(X.reshape(k, 2, g.N, g.N), int(n_steps) + 1, return_grid_traj=True)
-        return last.reshape(k, -1), traj[0].reshape(k, -1)
+        rows = traj.reshape(traj.shape[0], k, -1)
+        return last.reshape(k, -1), rows[0], (rows if want_rows else None)

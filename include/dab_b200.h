@@ -90,7 +90,7 @@ DAB_API int dab_l63_forecast_f64(dab_handle* h, const double* x_in, double* x_ou
  * FP64 matrix products with all members batched (csrc/sqg_forecast.cu).
  * dab_sqg_setup copies the generator's constant tables (HOST pointers; built by the caller exactly as
  * SQGTurb.__init__ builds them, :150-248, float32 / complex64 casts included) and the DFT matrices to the device:
- *   n            grid points per direction (multiple of 4: the 3n/2 grid must be even)
+ *   n            grid points per direction (multiple of 4: the 3n/2 grid must be even; <= 1024); members <= 4096
  *   kx [n/2+1]   imag(ik_pad[0, :n/2+1]);  ly [n]  imag(il[:, 0]) (= il_pad on the rows _specpad fills)
  *   hovermu, tanhmu, sinhmu, ksqlsq, hyperdiff   [n][n/2+1];  pvspec_eq [2][n][n/2+1] complex128
  *   delta_t, inv_tdiab (= 1 / tdiab as the reference rounds it), r; ekman = (r >= 1e-10); symmetric

@@ -560,14 +560,15 @@ def test_device_resident_observations_go_straight_into_the_cycler(stationary):
 
 
 # ------------------------------------------------------------------ ETKF.cycle() with the other generators
-def _cycle_vs_oracle(dc, init_x, start_time, obs, sd, window, n_cycles, fc, delta_t, stationary=True):
+def _cycle_vs_oracle(dc, init_x, start_time, obs, sd, window, n_cycles, fc, delta_t, stationary=True,
+                     return_forecast=False):
     init = _xr.new_dataset({'x': (('ensemble', 'index'), init_x)})
     out = dc.cycle(input_state=init, start_time=start_time, obs_vector=obs, obs_error_sd=sd,
-                   analysis_window=window, n_cycles=n_cycles)
+                   analysis_window=window, n_cycles=n_cycles, return_forecast=return_forecast)
     ref = o_etkf.cycle(init_x, float(start_time), np.asarray(obs['x'].values).reshape(len(obs['time'].values), -1),
                        np.asarray(obs['time'].values), np.asarray(obs['system_index'].values)[0], n_cycles, sd, fc,
-                       delta_t, stationary_observers=stationary, analysis_window=window, return_forecast=False,
-                       rho=dc.multiplicative_inflation, literal=True)
+                       delta_t, stationary_observers=stationary, analysis_window=window,
+                       return_forecast=return_forecast, rho=dc.multiplicative_inflation, literal=True)
     return np.asarray(out['x'].values), ref
 
 
@@ -593,6 +594,9 @@ def test_etkf_cycle_with_a_lorenz63_model():
     out2, ref2 = _cycle_vs_oracle(dc, x0, 0.0, obs2, 0.7, 0.1, 10, fc, 0.01)
     assert rel_err(out2, ref2) < 1e-9
     assert np.std(out2[1], axis=0).min() > 1e-3
+    # return_forecast=True: every cycle's trajectory without its last point
+    out3, ref3 = _cycle_vs_oracle(dc, x0, 0.0, obs, 0.7, 0.1, 5, fc, 0.01, return_forecast=True)
+    assert out3.shape == (5, 6, 10, 3) and rel_err(out3, ref3) < 1e-9
 
 
 def test_etkf_cycle_with_an_sqgturb_model():
@@ -618,6 +622,8 @@ def test_etkf_cycle_with_an_sqgturb_model():
     out, ref = _cycle_vs_oracle(dc, x0, 0.0, obs, sd, 1800.0, 4, fc, 900)
     assert out.shape == (4, k, 2 * N * N) and np.all(np.isfinite(out))
     assert rel_err(out, ref) < 1e-9
+    out3, ref3 = _cycle_vs_oracle(dc, x0, 0.0, obs, sd, 1800.0, 2, fc, 900, return_forecast=True)
+    assert out3.shape == (2, k, 3, 2 * N * N) and rel_err(out3, ref3) < 1e-9
     # the member-by-member plugin call the reference's ETKF would make gives the same forecast
     one = _xr.new_dataset({'x': (('index',), out[0, 0])})
     last, traj = model.forecast(one, n_steps=3)
