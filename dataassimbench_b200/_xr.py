@@ -239,9 +239,76 @@ class MiniDataset:
                 out._vars[k] = MiniDataArray(v.dims, np.where(np.isnan(a), value, a), None, v.attrs, k)
         return out
 
+    @property
+    def dab(self):
+        """The reference's `ds.dab` accessor (dabench/data/_xarray_accessor.py:23-51)."""
+        return _DabAccessor(self)
+
     def __repr__(self):
         body = ", ".join("%s%s" % (k, tuple(v.dims)) for k, v in self._vars.items())
         return "<MiniDataset %s | coords: %s | attrs: %s>" % (body, list(self.coords), list(self.attrs))
+
+
+class _DabAccessor:
+    """`Dataset.dab`: `flatten()` stacks every non-time dimension of every variable into one trailing `system`
+    dimension (`to_stacked_array('system', ['time'])` in the reference), `split_train_val_test()` cuts the time
+    axis into consecutive pieces given as counts or as fractions."""
+
+    def __init__(self, ds):
+        self._ds = ds
+
+    def flatten(self):
+        ds = self._ds
+        has_time = 'time' in ds.coords
+        cols = []
+        for v in ds._vars.values():
+            a = np.asarray(v.data)
+            if has_time and 'time' in v.dims:
+                a = np.moveaxis(a, v.dims.index('time'), 0)
+                cols.append(a.reshape(a.shape[0], -1))
+            else:
+                cols.append(a.reshape(1, -1) if has_time else a.reshape(-1))
+        if has_time:
+            n_t = max(c.shape[0] for c in cols)
+            cols = [np.broadcast_to(c, (n_t, c.shape[1])) for c in cols]
+            return MiniDataArray(('time', 'system'), np.concatenate(cols, axis=1), {'time': ds.coords['time']}, ds.attrs)
+        return MiniDataArray(('system',), np.concatenate(cols), None, ds.attrs)
+
+    def split_train_val_test(self, split_lengths):
+        ds = self._ds
+        n_t = ds.sizes['time']
+        lengths = np.array(split_lengths)
+        if (lengths > 1.0).sum() == 0:                       # fractions of the time axis
+            lengths = np.round(lengths * n_t).astype(int)
+        total = int(np.sum(lengths))
+        if total != n_t:
+            import warnings
+            warnings.warn("Specified split lengths ({}) {} Xarray object's time dimension ({}).".format(
+                split_lengths, 'exceed' if total > n_t else 'are shorter than', n_t))
+        out, start = [], 0
+        for n in lengths:
+            # the reference never advances its start index (:47-50): every piece begins at 0; kept
+            out.append(ds.isel(time=slice(start, start + int(n))))
+        return tuple(out)
+
+
+if HAVE_XARRAY:                          # pragma: no cover - not available in this image
+    try:
+        @_xarray.register_dataset_accessor('dab')
+        class _XarrayDabAccessor:
+            def __init__(self, obj):
+                self._obj = obj
+
+            def flatten(self):
+                return self._obj.to_stacked_array('system', ['time'] if 'time' in self._obj.coords else [])
+
+            def split_train_val_test(self, split_lengths):
+                lengths = np.array(split_lengths)
+                if (lengths > 1.0).sum() == 0:
+                    lengths = np.round(lengths * self._obj.sizes['time']).astype(int)
+                return tuple(self._obj.isel(time=slice(0, int(n))) for n in lengths)
+    except Exception:
+        pass
 
 
 def new_dataset(data_vars, coords=None, attrs=None):

@@ -111,3 +111,22 @@ def test_reference_obs_sqgturb_recipe_through_the_package():
     assert vals[0, 44] == pytest.approx(2128.20749725)
     assert errors[0, 1, 187] == pytest.approx(25.714826330507496)
     assert np.allclose(np.asarray(obs_vec['time'].values), np.array([2700., 9000.]))
+
+
+def test_reference_sqgturb_variable_sizes_recipe():
+    """tests/data_sqgturb_test.py:16-46 written against this package (NumPy noise instead of jax.random)."""
+    import dataassimbench_b200 as dab
+    N = 96
+    rng = np.random.default_rng(42)
+    pv = (100 * rng.standard_normal((2, N, N))).astype(np.float32)
+    x, y = np.meshgrid(np.arange(0, 2. * np.pi, 2. * np.pi / N), np.arange(0., 2. * np.pi, 2. * np.pi / N))
+    pv[1] = pv[1] + 2000. * (np.sin(x.astype(np.float32) / 2) ** 40 * np.sin(y.astype(np.float32)) ** 20)
+    for k in range(2):
+        pv[k] = pv[k] - pv[k].mean()
+    sqgturb = dab.data.SQGTurb(pv=pv)
+    n_steps = 10
+    traj = sqgturb.generate(n_steps=n_steps)
+    assert traj.system_dim == 18432
+    assert traj.sizes['time'] == n_steps + 1
+    assert traj.dab.flatten().shape == (n_steps + 1, 18432)
+    assert np.all(np.isfinite(np.asarray(traj['pv'].values)))

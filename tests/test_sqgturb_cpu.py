@@ -118,3 +118,23 @@ def test_observer_on_a_gridded_state_draws_like_the_reference():
     assert np.array_equal(vals, flat[[3, 10]][:, sysidx[0, 0]] + errors[0])
     tsel, count, lev, xx, yy, err = reference_observer_draws(96, 11)
     assert np.array_equal(sysidx[0, 0], lev * 96 * 96 + xx * 96 + yy) and np.array_equal(errors, err)
+
+
+def test_dab_accessor_flatten_and_split():
+    """`ds.dab.flatten()` / `ds.dab.split_train_val_test()` (dabench/data/_xarray_accessor.py:23-51) on the Dataset
+    the generators return."""
+    from dataassimbench_b200 import _xr
+    pv = np.arange(5 * 2 * 4 * 4, dtype=np.float64).reshape(5, 2, 4, 4)
+    ds = _xr.new_dataset({'pv': (('time', 'level', 'x', 'y'), pv)},
+                         coords={'time': np.arange(5) * 900.0, 'level': np.arange(2), 'x': np.arange(4), 'y': np.arange(4)},
+                         attrs={'system_dim': 32})
+    flat = ds.dab.flatten()
+    assert flat.shape == (5, 32) and np.array_equal(np.asarray(flat.values), pv.reshape(5, -1))
+    one = ds.isel(time=2).dab.flatten()
+    assert one.shape == (32,) or one.shape == (1, 32)
+    a, b, c = ds.dab.split_train_val_test([2, 2, 1])
+    assert a.sizes['time'] == 2 and b.sizes['time'] == 2 and c.sizes['time'] == 1
+    a, b = ds.dab.split_train_val_test([0.6, 0.4])
+    assert a.sizes['time'] == 3 and b.sizes['time'] == 2
+    x = _xr.new_dataset({'x': (('time', 'index'), np.ones((3, 7)))}, coords={'time': np.arange(3.0), 'index': np.arange(7)})
+    assert x.dab.flatten().shape == (3, 7)
