@@ -171,7 +171,7 @@ cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, Gem
   for (int sgi = 0; sgi < g.nseg; ++sgi)
     if (g.A[sgi].rs >= (1ll << 25) || g.B[sgi].rs >= (1ll << 25)) return cudaErrorInvalidValue;   // 32-bit tile offsets
   // tile edge with the least padded work, weighted by the fragment loads a DMMA costs at that warp tile
-  // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured, 48 beats 32 by 20 % at equal padding
+  // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured on the y-inverse product: 48 beats 32 by 12 % at equal padding
   int best = 64;
   double best_cost = -1.0;
   for (int bt : {64, 48, 32}) {

@@ -175,6 +175,9 @@ class SQGTurb(Data):
         on_dev = isinstance(spec, torch.Tensor)
         x = spec if on_dev else torch.from_numpy(np.ascontiguousarray(np.asarray(spec, dtype=np.complex128)))
         x = x.to(device='cuda', dtype=torch.complex128).contiguous()
+        if x.ndim != 4 or tuple(x.shape[1:]) != (2, self.N, self.N // 2 + 1):
+            raise ValueError('spectral members must have shape (k, 2, %d, %d), got %s'
+                             % (self.N, self.N // 2 + 1, tuple(x.shape)))
         k = x.shape[0]
         out = torch.empty_like(x)
         traj = torch.empty((max(n_steps, 1), k, 2, self.N, self.N), dtype=torch.float64, device='cuda') \
@@ -190,6 +193,8 @@ class SQGTurb(Data):
         import torch
         H = self._setup_device()
         x = grid.to(device='cuda', dtype=torch.float64).contiguous()
+        if x.ndim != 4 or tuple(x.shape[1:]) != (2, self.N, self.N):
+            raise ValueError('gridded members must have shape (k, 2, %d, %d), got %s' % (self.N, self.N, tuple(x.shape)))
         k = x.shape[0]
         out = torch.empty_like(x)
         traj = torch.empty((max(n_steps, 1), k, 2, self.N, self.N), dtype=torch.float64, device='cuda') \

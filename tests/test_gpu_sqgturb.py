@@ -71,6 +71,11 @@ def test_sqg_forecast_needs_setup_and_valid_sizes():
         h.close()
     with pytest.raises(ValueError):
         SQGTurb(pv=np.zeros((2, 6, 6)))           # 3N/2 odd
+    g = SQGTurb(pv=np.ones((2, 8, 8)), precision='double')
+    with pytest.raises(ValueError, match='spectral members'):
+        g.forecast_members(np.zeros((1, 2, 8, 8), dtype=np.complex128), 1)
+    with pytest.raises(ValueError, match='gridded members'):
+        g.forecast_members_grid(torch.zeros((1, 2, 8, 5), device='cuda'), 1)
 
 
 def test_sqg_model_forecast_plugin_contract():
