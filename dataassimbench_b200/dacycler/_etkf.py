@@ -256,7 +256,7 @@ class ETKF(DACycler):
         the observation rows of every cycle are laid out once (time mask = rows dropped, NaN slots of a moving
         network masked), then analysis (`dab_etkf_analysis_f64`) and the model's ensemble forecast alternate on the
         device; the ensemble never visits the host.  What a cycle returns is row 0 of the model's trajectory, as
-        in the reference (:288-290) -- the analysis itself for Lorenz-63, one step past it for the SQGTurb wrapper."""
+        in the reference (:288-290): the analysis itself for the package's wrappers."""
         import torch
         from .._runtime import handle
         if p['sd_slots'] is not None:

@@ -63,10 +63,13 @@ class Lorenz63Model(Model):
 
 
 class SQGTurbModel(Model):
-    """Wraps a `data.SQGTurb` generator behind the same plugin point: `state_vec` holds the gridded potential
-    vorticity `pv[level, x, y]`; the generator itself steps in spectral space (dabench/data/_sqgturb.py:441-504), so
-    the wrapper transforms in (`fft2_2dto1d`, :420-426) and `generate` transforms out.  The returned trajectory keeps
-    the reference's scan quirk: its first row is one step past `state_vec`."""
+    """Wraps a `data.SQGTurb` generator behind the same plugin point.  `state_vec` holds the gridded potential
+    vorticity -- `pv[level, x, y]`, or the cyclers' flattened `x[index]` (dabench/dacycler/_etkf.py:213 knows no other
+    name) -- while the generator steps in spectral space (dabench/data/_sqgturb.py:441-504), so the wrapper
+    transforms in (`fft2`, :398-404) and out (`ifft2`, :496).  The trajectory follows the CYCLERS' contract, the one
+    `Lorenz96Model` has: `n_steps` points at spacing delta_t, the first being `state_vec` itself -- NOT the scan quirk
+    of `SQGTurb.generate()` (whose rows start one step late and end one step late): a cycler that forecast
+    `steps_per_window + 1` steps per window of `steps_per_window - 1` would run ahead of the observations."""
 
     def __init__(self, system_dim=None, delta_t=None, model_obj=None):
         if model_obj is None:
@@ -76,24 +79,33 @@ class SQGTurbModel(Model):
                          delta_t=delta_t or model_obj.delta_t, model_obj=model_obj)
 
     def forecast(self, state_vec, n_steps=2):
-        if 'pv' in state_vec:
-            pv = _xr.var_array(state_vec, 'pv')
-        else:       # the cyclers' flattened state `x[index]` (dabench/dacycler/_etkf.py:213 knows no other name)
-            pv = _xr.var_array(state_vec, 'x').reshape(self.model_obj.original_dim)
-        new_vec = self.model_obj.generate(x0=self.model_obj.fft2_2dto1d(pv), n_steps=n_steps)
-        if 'pv' in state_vec:
-            return new_vec.isel(time=-1), new_vec
-        flat = _xr.var_array(new_vec, 'pv').reshape(new_vec['pv'].shape[0], -1)
-        flat_ds = _xr.new_dataset({'x': (('time', 'index'), flat)}, coords={'time': _xr.var_array(new_vec, 'time')})
-        return flat_ds.isel(time=-1), flat_ds
+        import numpy as np
+        g = self.model_obj
+        gridded = 'pv' in state_vec.data_vars
+        pv = np.asarray(_xr.var_array(state_vec, 'pv' if gridded else 'x'), dtype=np.float64).reshape(g.original_dim)
+        n = int(n_steps) - 1
+        rows = pv[None]
+        if n > 0:
+            _, traj = g.forecast_members(np.fft.rfft2(pv)[None], n, return_grid_traj=True)
+            rows = np.concatenate([rows, traj[:, 0].cpu().numpy()], axis=0)
+        times = np.arange(rows.shape[0]) * float(g.delta_t)
+        if gridded:
+            coords = {'time': times}
+            coords.update({name: np.arange(d) for name, d in zip(g.coord_names, g.original_dim)})
+            ds = _xr.new_dataset({'pv': (('time',) + tuple(g.coord_names), rows)}, coords=coords)
+        else:
+            ds = _xr.new_dataset({'x': (('time', 'index'), rows.reshape(rows.shape[0], -1))}, coords={'time': times})
+        return ds.isel(time=-1), ds
 
     def _forecast_members_device(self, X, n_steps, want_rows=False):
         """All members at once on the device, for the cyclers: X [k, 2 N N] flattened gridded states (CUDA) ->
-        (last row, first row, every row or None) of the trajectories `forecast` returns member by member.
-        `generate(n_steps)` emits the states after steps 1 .. n_steps + 1 (the reference's scan quirk), so the first
-        row is one step past X and there are n_steps + 1 rows."""
+        (last row, first row, every row [n_steps, k, 2 N N] or None) of the trajectories `forecast` returns member by
+        member: rfft2, n_steps - 1 RK4 steps, irfft2 in one call (`dab_sqg_forecast_grid_f64`)."""
+        import torch
         g = self.model_obj
         k = X.shape[0]
-        last, traj = g.forecast_members_grid(X.reshape(k, 2, g.N, g.N), int(n_steps) + 1, return_grid_traj=True)
-        rows = traj.reshape(traj.shape[0], k, -1)
-        return last.reshape(k, -1), rows[0], (rows if want_rows else None)
+        n = int(n_steps) - 1
+        res = g.forecast_members_grid(X.reshape(k, 2, g.N, g.N), n, return_grid_traj=want_rows)
+        last, traj = res if want_rows else (res, None)
+        rows = torch.cat([X[None], traj.reshape(traj.shape[0], k, -1)], dim=0) if want_rows else None
+        return last.reshape(k, -1), X, rows

@@ -601,8 +601,8 @@ def test_etkf_cycle_with_a_lorenz63_model():
 
 def test_etkf_cycle_with_an_sqgturb_model():
     """`SQGTurbModel` behind ETKF.cycle(): the flattened gridded potential vorticity is the state, every cycle is
-    analysis -> rfft2 -> RK4 steps -> irfft2 on the device.  Against the oracle cycle whose forecast is the oracle
-    generator (same scan quirk: a cycle returns the state one step past its analysis)."""
+    analysis -> rfft2 -> RK4 steps -> irfft2 on the device.  Against the oracle cycle whose forecast plugin is the
+    oracle generator under the cyclers' trajectory contract (n points, the first is the analysis itself)."""
     from oracle import sqgturb as o_sqg
     from test_gpu_sqgturb import members
     N, k, sd = 16, 6, 50.0
@@ -618,13 +618,15 @@ def test_etkf_cycle_with_an_sqgturb_model():
     model = dab.model.SQGTurbModel(model_obj=dab.data.SQGTurb(pv=pv[0], precision='double'))
     dc = dab.dacycler.ETKF(system_dim=2 * N * N, delta_t=900, ensemble_dim=k, model_obj=model)
     x0 = pv[1:].reshape(k, -1)
-    fc = lambda x, n: o_sqg.generate(x.reshape(2, N, N), n, precision='double')[0].reshape(n + 1, -1)
+    T = o_sqg.tables(N, 'double')
+    fc = lambda x, n: np.concatenate([x[None], o_sqg.integrate(T, np.fft.rfft2(x.reshape(2, N, N)), n - 1)[1]
+                                      .reshape(n - 1, -1)])
     out, ref = _cycle_vs_oracle(dc, x0, 0.0, obs, sd, 1800.0, 4, fc, 900)
     assert out.shape == (4, k, 2 * N * N) and np.all(np.isfinite(out))
     assert rel_err(out, ref) < 1e-9
     out3, ref3 = _cycle_vs_oracle(dc, x0, 0.0, obs, sd, 1800.0, 2, fc, 900, return_forecast=True)
-    assert out3.shape == (2, k, 3, 2 * N * N) and rel_err(out3, ref3) < 1e-9
+    assert out3.shape == (2, k, 2, 2 * N * N) and rel_err(out3, ref3) < 1e-9
     # the member-by-member plugin call the reference's ETKF would make gives the same forecast
     one = _xr.new_dataset({'x': (('index',), out[0, 0])})
     last, traj = model.forecast(one, n_steps=3)
-    assert traj['x'].shape == (4, 2 * N * N)
+    assert traj['x'].shape == (3, 2 * N * N) and np.array_equal(np.asarray(traj['x'].values)[0], out[0, 0])

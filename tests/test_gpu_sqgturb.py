@@ -90,11 +90,14 @@ def test_sqg_model_forecast_plugin_contract():
     assert model.system_dim == 2 * N * N and model.delta_t == 900
     state = _xr.new_dataset({'pv': (('level', 'x', 'y'), pv)},
                             coords={'level': np.arange(2), 'x': np.arange(N), 'y': np.arange(N)})
-    last, traj = model.forecast(state, n_steps=3)
-    ref, _ = o_sqg.generate(pv, 3, precision='double')
+    last, traj = model.forecast(state, n_steps=4)
+    # the cyclers' contract: n_steps points, the first is the state itself, then one RK4 step per point
+    T = o_sqg.tables(N, 'double')
+    _, ref, _ = o_sqg.integrate(T, np.fft.rfft2(pv), 3)
     got = _xr.var_array(traj, 'pv')
-    assert got.shape == (4, 2, N, N)
-    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-10
+    assert got.shape == (4, 2, N, N) and np.array_equal(got[0], pv)
+    assert np.allclose(np.asarray(traj['time'].values), np.arange(4) * 900.0)
+    assert np.abs(got[1:] - ref).max() / np.abs(ref).max() < 1e-10
     assert np.array_equal(_xr.var_array(last, 'pv'), got[-1])
 
 
