@@ -630,3 +630,26 @@ def test_etkf_cycle_with_an_sqgturb_model():
     one = _xr.new_dataset({'x': (('index',), out[0, 0])})
     last, traj = model.forecast(one, n_steps=3)
     assert traj['x'].shape == (3, 2 * N * N) and np.array_equal(np.asarray(traj['x'].values)[0], out[0, 0])
+
+
+def test_etkf_cycle_lorenz63_with_moving_observers():
+    """The generic-model loop with a non-stationary network (ragged counts, NaN-padded slots masked,
+    dabench/dacycler/_dacycler.py:262-268) against the oracle cycle."""
+    from oracle import l63 as o_l63
+    gen = dab.data.Lorenz63(delta_t=0.01)
+    nature = gen.generate(n_steps=200)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(5, 200, 10)],
+                                random_location_density=0.6, error_sd=0.5, random_seed=11,
+                                stationary_observers=False).observe()
+    vals = np.asarray(obs['x'].values)
+    assert np.isnan(vals).any() and not np.isnan(vals).all()          # ragged: some slots are padding
+    model = dab.model.Lorenz63Model(model_obj=dab.data.Lorenz63(delta_t=0.01))
+    dc = dab.dacycler.ETKF(system_dim=3, delta_t=0.01, ensemble_dim=5, model_obj=model)
+    x0 = nature['x'].values[0] + threefry.normal(8, (5, 3))
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), x0)})
+    out = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, obs_error_sd=0.5, analysis_window=0.1,
+                   n_cycles=15)
+    fc = lambda x, n: o_l63.generate_rk4(x, n, 0.01)
+    ref = o_etkf.cycle(x0, 0.0, vals, np.asarray(obs['time'].values), np.asarray(obs['system_index'].values)[0], 15,
+                       0.5, fc, 0.01, stationary_observers=False, analysis_window=0.1, literal=True)
+    assert rel_err(np.asarray(out['x'].values), ref) < 1e-9
