@@ -653,3 +653,52 @@ def test_etkf_cycle_lorenz63_with_moving_observers():
     ref = o_etkf.cycle(x0, 0.0, vals, np.asarray(obs['time'].values), np.asarray(obs['system_index'].values)[0], 15,
                        0.5, fc, 0.01, stationary_observers=False, analysis_window=0.1, literal=True)
     assert rel_err(np.asarray(out['x'].values), ref) < 1e-9
+
+
+# ------------------------------------------------------------------ the reference's Lorenz-63 observer tests
+def test_reference_observer_l63_recipes_through_the_package():
+    """tests/observer_base_test.py:11-131 written against this package: the Lorenz-63 nature run comes from the GPU
+    (fixed-step RK4 instead of the reference's adaptive Dormand-Prince: the value goldens hold to np.allclose), the
+    seeded draws reproduce the reference's indices, times and errors."""
+    l63 = dab.data.Lorenz63()
+    ds = l63.generate(n_steps=10)
+    x = np.asarray(ds['x'].values)
+    # test_obs_l63
+    ov = dab.observer.Observer(ds, random_time_density=0.5, random_location_density=0.5, error_sd=0.7,
+                               random_seed=99).observe()
+    assert ov['x'].values.shape[0] == 8 and ov['time'].shape[0] == 8
+    assert np.array_equal(ov['system_index'].values, np.repeat(1, 8).reshape((1, 8, 1)))
+    assert ov['x'].values[0, 0] == pytest.approx(x[0, 1] + np.asarray(ov['errors'].values)[0, 0, 0])
+    assert np.allclose(ov['x'].values, np.array([[-14.77003751], [-14.82969835], [-16.49873315], [-16.21225914],
+                                                 [-16.08467213], [-16.69890358], [-15.45879053], [-15.12257015]]))
+    assert np.allclose(ov['errors'].values, np.array([[[0.22996249], [0.65467059], [-0.6143291], [-0.03212726],
+                                                       [0.26731022], [-0.31677728], [0.50516542], [-0.24651439]]]))
+    assert np.array_equal(ov['time'].values, np.array([0., 0.01, 0.02, 0.03, 0.04, 0.05, 0.07, 0.09]))
+    # test_obs_l63_count
+    ov = dab.observer.Observer(ds, random_time_count=5, random_location_count=2, error_sd=0.7).observe()
+    assert ov['x'].shape[0] == 5 and ov['time'].shape[0] == 5
+    assert np.array_equal(ov['system_index'].values, np.tile([1, 2], 5).reshape((1, 5, 2)))
+    assert np.allclose(ov['x'].values, np.array([[-16.71412359, 23.46140116], [-16.5006219, 24.10746168],
+                                                 [-17.11500315, 27.69793923], [-15.78352562, 29.22759993],
+                                                 [-14.87744996, 31.11579368]]))
+    assert np.allclose(np.asarray(ov['errors'].values)[0], np.array([[-1.22975335, 1.17910212],
+                                                                     [-0.32048999, -0.41749407],
+                                                                     [-0.73287729, 0.65225442],
+                                                                     [0.47248634, 0.87110884],
+                                                                     [0.6251612, 0.18410346]]))
+    assert np.array_equal(ov['time'].values, np.array([0.01, 0.03, 0.05, 0.06, 0.08]))
+    # test_obs_l63_diffseed
+    ov = dab.observer.Observer(ds, random_time_density=0.5, random_location_density=0.5, error_sd=0.0,
+                               random_seed=1).observe()
+    assert np.array_equal(ov['system_index'].values, np.tile([0, 2], 5).reshape((1, 5, 2)))
+    assert ov['x'].values[0, 0] == x[0, 0]
+    assert np.array_equal(ov['time'].values, np.array([0., 0.01, 0.03, 0.06, 0.08]))
+    assert np.allclose(ov['x'].values, x[[0, 1, 3, 6, 8]][:, [0, 2]])
+    assert np.array_equal(ov['errors'].values, np.repeat(0, 10).reshape(1, 5, 2))
+    # test_obs_l63_specific_locs
+    ov = dab.observer.Observer(ds, locations={'index': np.array([2])}, times=ds['time'].values[[4, 9]],
+                               error_sd=1.0).observe()
+    assert np.array_equal(ov['system_index'].values, np.repeat(2, 2).reshape((1, 2, 1)))
+    assert np.allclose(np.asarray(ov['x'].values) - np.asarray(ov['errors'].values)[0], np.array([[x[4, 2]], [x[9, 2]]]))
+    assert np.array_equal(ov['time'].values, np.array([0.04, 0.09]))
+    assert np.allclose(np.asarray(ov['errors'].values)[0], np.array([[0.0824943], [-0.46441841]]))
