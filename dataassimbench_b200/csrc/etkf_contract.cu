@@ -15,6 +15,8 @@
 // contracted with DMMA.8x8x4 (FP64 tensor core): warp w owns the 8-row strip w of C.
 // Every CTA writes its partial (C, g) to a workspace; `stats_reduce_kernel` sums the partials
 // in a fixed order (bit-reproducible, no atomics) and applies 1/sigma^2.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -258,9 +260,11 @@ size_t contract_partial_doubles(int k, int n_cta) {
 }
 
 int contract_grid(long long n_rows, int sms) {
+  static int mult = 0;                 // experiment knob: CTAs per SM the row ranges are cut for (default 1)
+  if (mult == 0) { const char* ev = getenv("DAB_K3_CTAS_PER_SM"); mult = ev ? atoi(ev) : 1; if (mult < 1 || mult > 4) mult = 1; }
   const long long nb = (n_rows + RB - 1) / RB;
   long long g = nb < 1 ? 1 : nb;
-  if (g > sms) g = sms;
+  if (g > (long long)sms * mult) g = (long long)sms * mult;
   return (int)g;
 }
 
