@@ -259,26 +259,30 @@ class ETKF(DACycler):
         in the reference (:288-290): the analysis itself for the package's wrappers."""
         import torch
         from .._runtime import handle
-        if p['sd_slots'] is not None:
-            raise NotImplementedError('a vector obs_error_sd is implemented for the Lorenz-96 cycler only')
         cfg = p['cfg']
         k, N, n_cycles = cfg.ensemble_dim, cfg.system_dim, cfg.n_cycles
         vals = p['vals'].cpu().numpy() if getattr(p['vals'], 'is_cuda', False) else p['vals']
         H = handle()
         stream = torch.cuda.current_stream().cuda_stream
-        rows_y, rows_i, offs = [], [], [0]
+        rows_y, rows_i, rows_s, offs = [], [], [], [0]
         for c in range(n_cycles):
             t = p['padded'][c]
             t = t[t > 0] - 1
             y, idx = vals[t].ravel(), p['sysidx'][t].ravel()
+            sds = p['sd_slots'][t].ravel() if p['sd_slots'] is not None else None
             if not p['stationary']:
                 keep = ~np.isnan(y)
                 y, idx = y[keep], idx[keep]
+                sds = sds[keep] if sds is not None else None
+            if sds is not None:
+                rows_s.append(sds)
             if idx.size and (idx.min() < 0 or idx.max() >= N):
                 raise ValueError('system_index out of range for system_dim %d' % N)
             rows_y.append(y); rows_i.append(idx); offs.append(offs[-1] + y.size)
         y_all = torch.from_numpy(np.concatenate(rows_y) if rows_y else np.zeros(0)).cuda()
         i_all = torch.from_numpy((np.concatenate(rows_i) if rows_i else np.zeros(0)).astype(np.int64)).cuda()
+        # a diagonal R with unequal entries: one sigma per row, on the device (dab_etkf_analysis_diag_f64)
+        s_all = torch.from_numpy(np.ascontiguousarray(np.concatenate(rows_s), dtype=np.float64)).cuda() if rows_s else None
         X = torch.from_numpy(p['X0']).cuda()
         Xa = torch.empty_like(X)
         out = None
@@ -292,7 +296,8 @@ class ETKF(DACycler):
         for c in range(n_cycles):
             a, b = offs[c], offs[c + 1]
             if b > a:
-                H.etkf_analysis(X, Xa, y_all[a:b], i_all[a:b], None, sd, rho, N, k, b - a, stream)
+                H.etkf_analysis(X, Xa, y_all[a:b], i_all[a:b], None, sd if s_all is None else s_all[a:b], rho, N, k,
+                                b - a, stream)
             elif empty_R:
                 H.etkf_analysis(X, Xa, None, None, None, sd, rho, N, k, 0, stream)
             else:

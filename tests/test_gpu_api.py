@@ -702,3 +702,27 @@ def test_reference_observer_l63_recipes_through_the_package():
     assert np.allclose(np.asarray(ov['x'].values) - np.asarray(ov['errors'].values)[0], np.array([[x[4, 2]], [x[9, 2]]]))
     assert np.array_equal(ov['time'].values, np.array([0.04, 0.09]))
     assert np.allclose(np.asarray(ov['errors'].values)[0], np.array([[0.0824943], [-0.46441841]]))
+
+
+def test_etkf_cycle_lorenz63_with_a_sigma_per_observation():
+    """A vector obs_error_sd (diagonal R with unequal entries, one weightless row) through the generic-model loop,
+    against the oracle analysis with the same per-observation weights and the oracle Lorenz-63 RK4."""
+    from oracle import l63 as o_l63
+    gen = dab.data.Lorenz63(delta_t=0.01)
+    nature = gen.generate(n_steps=100)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(0, 100, 10)],
+                                random_location_count=3, error_sd=0.5, random_seed=2).observe()
+    sdv = np.array([0.4, 0.0, 1.3])
+    model = dab.model.Lorenz63Model(model_obj=dab.data.Lorenz63(delta_t=0.01))
+    dc = dab.dacycler.ETKF(system_dim=3, delta_t=0.01, ensemble_dim=7, model_obj=model)
+    X0 = nature['x'].values[0] + threefry.normal(21, (7, 3))
+    init = _xr.new_dataset({'x': (('ensemble', 'index'), X0)})
+    out = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=8, obs_error_sd=sdv,
+                   analysis_window=0.1, analysis_time_in_window=0.0)
+    w = np.where(sdv == 0.0, 0.0, 1.0 / np.where(sdv == 0.0, 1.0, sdv) ** 2)
+    loc = np.asarray(obs['system_index'].values)[0][0]
+    Xc = X0.copy()
+    for c in range(8):
+        Xa = o_etkf.analysis_sparse(Xc, np.asarray(obs['x'].values)[c], loc, w, 1.0)
+        assert rel_err(np.asarray(out['x'].values)[c], Xa) < 1e-9, c
+        Xc = o_l63.rk4_forecast(Xa, 10, 0.01)
