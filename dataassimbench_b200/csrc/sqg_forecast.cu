@@ -170,12 +170,16 @@ cudaError_t gemm(cudaStream_t st, int batch, int m, int n, int K, GemmOp A1, Gem
   g.C = C; g.c_rs = c_rs; g.c_bs = c_bs; g.c_cs = c_cs; g.m = m; g.n = n; g.K = K;
   for (int sgi = 0; sgi < g.nseg; ++sgi)
     if (g.A[sgi].rs >= (1ll << 25) || g.B[sgi].rs >= (1ll << 25)) return cudaErrorInvalidValue;   // 32-bit tile offsets
-  // tile edge with the least padded work, weighted by the fragment loads a DMMA costs at that warp tile
-  // (1, 2/3, 1/2 per DMMA for 32 / 48 / 64): measured on the y-inverse product: 48 beats 32 by 12 % at equal padding
+  // tile edge: the padded work shared by the SMs -- or, when there are fewer CTAs than that takes, one CTA's own
+  // tile (small ensembles: a 48-edge grid of 64 CTAs leaves more than half of the GPU idle) -- weighted by the
+  // fragment loads a DMMA costs at that warp tile (1, 2/3, 1/2 per DMMA for 32 / 48 / 64: measured on the y-inverse
+  // product, 48 beats 32 by 12 % at equal padding)
   int best = 64;
   double best_cost = -1.0;
   for (int bt : {64, 48, 32}) {
-    const double w = (double)((m + bt - 1) / bt) * bt * (double)((n + bt - 1) / bt) * bt * (1.0 + 8.0 / bt);
+    const double padded = (double)((m + bt - 1) / bt) * bt * (double)((n + bt - 1) / bt) * bt * (double)batch;
+    const double per_sm = padded / 148.0, one_cta = (double)bt * bt;
+    const double w = (per_sm > one_cta ? per_sm : one_cta) * (1.0 + 8.0 / bt);
     if (best_cost < 0.0 || w < best_cost) { best = bt; best_cost = w; }
   }
   dim3 grid((unsigned)((n + best - 1) / best), (unsigned)((m + best - 1) / best), (unsigned)batch);
