@@ -1,7 +1,8 @@
 """3D-Var cycler with the reference's constructor and `cycle()` signature.
 
 Mirrors `dabench.dacycler.Var3D` (dabench/dacycler/_var3d.py:18-112) under `DACycler.cycle`
-(dabench/dacycler/_dacycler.py:186-290).  Accelerated contract: native `Lorenz96Model`, default H
+(dabench/dacycler/_dacycler.py:186-290).  Accelerated contract: a Model wrapping one of the package's generators (`Lorenz96Model`: the RK4 forecast kernel
+with one member; `Lorenz63Model` / `SQGTurbModel`: their device forecast through `_forecast_members_device`), default H
 (index gather), default R (`obs_error_sd**2 * I`).  With the default B (identity,
 `DACycler._calc_default_B`) the system `I + B H^T R^-1 H` the reference solves by conjugate
 gradients (tol 1e-5) is diagonal, and `dab_var3d_analysis_f64` solves it exactly; with a
@@ -38,9 +39,10 @@ class Var3D(DACycler):
             raise NotImplementedError('user-supplied H / R matrices are outside the accelerated path '
                                       '(default index-gather H and obs_error_sd**2 * I only)')
         gen = self._lorenz96_generator()
-        if gen is None:
+        if gen is None and not callable(getattr(self.model_obj, '_forecast_members_device', None)):
             raise NotImplementedError('the accelerated Var3D.cycle() needs model_obj to be a Model wrapping a '
-                                      'dataassimbench_b200.data.Lorenz96 generator (e.g. model.Lorenz96Model)')
+                                      'dataassimbench_b200.data generator (model.Lorenz96Model, Lorenz63Model, '
+                                      'SQGTurbModel), i.e. one with a device forecast')
         w = self._prepare_cycle(input_state, start_time, obs_vector, n_cycles, obs_error_sd,
                                 analysis_window, analysis_time_in_window)
         if self._data_vars != ['x'] or self._observed_vars != ['x']:
@@ -61,7 +63,9 @@ class Var3D(DACycler):
                 raise ValueError('B must be (system_dim, system_dim) = (%d, %d), got %s' % (x0.size, x0.size, B.shape))
         return dict(x0=x0, vals=vals, sysidx=sysidx, B=B, padded=np.asarray(w['padded'], dtype=np.int64),
                     stationary=w['stationary'], n_steps=self.steps_per_window - 1,
-                    model_dt=float(gen.delta_t), forcing=float(gen.forcing_term), sd=float(self.obs_error_sd),
+                    model_dt=float(gen.delta_t) if gen is not None else float(self.delta_t),
+                    forcing=float(gen.forcing_term) if gen is not None else 0.0, generic=gen is None,
+                    sd=float(self.obs_error_sd),
                     state_dim=_xr.var_dims(input_state, 'x')[0])
 
     @staticmethod
@@ -109,7 +113,14 @@ class Var3D(DACycler):
                 self.cg_iterations.append(H.var3d_analysis_b(xb, xa, N, d_loc, d_val, len(loc), p['sd'], Bd,
                                                              1e-5, 1000, stream))
             full[c, 0] = xa.cpu().numpy()
-            if S > 0:
+            if p['generic']:
+                # another generator behind the same plugin point: its whole-"ensemble" device forecast with one member
+                # (model.Lorenz63Model / SQGTurbModel); rows = the trajectory `forecast` would return
+                nxt, _, rows = self.model_obj._forecast_members_device(xa.view(1, N), self.steps_per_window, True)
+                if S > 1:
+                    full[c, 1:] = rows[1:S, 0].cpu().numpy()
+                xb.copy_(nxt.reshape(N))
+            elif S > 0:
                 # members are rows: one member of N points; the next background is the last step
                 H.l96_forecast(xa.view(1, N), xb.view(1, N), traj, N, 1, S, p['model_dt'], p['forcing'], stream)
                 if S > 1:

@@ -726,3 +726,48 @@ def test_etkf_cycle_lorenz63_with_a_sigma_per_observation():
         Xa = o_etkf.analysis_sparse(Xc, np.asarray(obs['x'].values)[c], loc, w, 1.0)
         assert rel_err(np.asarray(out['x'].values)[c], Xa) < 1e-9, c
         Xc = o_l63.rk4_forecast(Xa, 10, 0.01)
+
+
+def test_var3d_cycle_with_lorenz63_and_sqgturb_models():
+    """Var3D behind DACycler.cycle with the other generators (the reference's Var3D takes any Model): analysis on
+    the device, the model's own device forecast with one member; against the oracle's literal Var3D cycle with the
+    oracle generator as the plugin."""
+    from oracle import l63 as o_l63, sqgturb as o_sqg
+    from test_gpu_sqgturb import members
+    # Lorenz-63
+    nature = dab.data.Lorenz63(delta_t=0.01).generate(n_steps=120)
+    obs = dab.observer.Observer(nature, times=nature['time'].values[np.arange(0, 120, 10)], random_location_count=2,
+                                error_sd=0.5, random_seed=4).observe()
+    dc = dab.dacycler.Var3D(system_dim=3, delta_t=0.01, model_obj=dab.model.Lorenz63Model(
+        model_obj=dab.data.Lorenz63(delta_t=0.01)))
+    x0 = nature['x'].values[0] + np.array([0.5, -0.3, 0.8])
+    init = _xr.new_dataset({'x': (('index',), x0.copy())})
+    full = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=10, obs_error_sd=0.5,
+                    analysis_window=0.1, analysis_time_in_window=0.0, return_forecast=True)
+    fc = lambda x, n: o_l63.generate_rk4(x, n, 0.01)
+    ref = o_var3d.cycle(x0, 0.0, obs['x'].values, obs['time'].values, np.asarray(obs['system_index'].values)[0], 10,
+                        0.5, fc, 0.01, analysis_window=0.1, analysis_time_in_window=0.0, return_forecast=True,
+                        literal=True)
+    assert full['x'].shape == (10, 10, 3) and rel_err(np.asarray(full['x'].values), ref) < 1e-9
+    # SQGTurb, flattened gridded state
+    N = 16
+    pv = members(N, 2, seed=13)
+    gen = dab.data.SQGTurb(pv=pv[0], precision='double')
+    nat = gen.generate(n_steps=8)
+    flat = np.asarray(nat['pv'].values).reshape(9, -1)
+    nds = _xr.new_dataset({'x': (('time', 'index'), flat)},
+                          coords={'time': np.asarray(nat['time'].values), 'index': np.arange(flat.shape[1])})
+    obs = dab.observer.Observer(nds, times=np.asarray(nat['time'].values)[0::2][:4], random_location_count=60,
+                                error_sd=40.0, random_seed=6).observe()
+    dc = dab.dacycler.Var3D(system_dim=2 * N * N, delta_t=900, model_obj=dab.model.SQGTurbModel(
+        model_obj=dab.data.SQGTurb(pv=pv[0], precision='double')))
+    x0 = pv[1].ravel()
+    init = _xr.new_dataset({'x': (('index',), x0.copy())})
+    out = dc.cycle(input_state=init, start_time=0.0, obs_vector=obs, n_cycles=3, obs_error_sd=40.0,
+                   analysis_window=1800.0, analysis_time_in_window=0.0)
+    T = o_sqg.tables(N, 'double')
+    fc = lambda x, n: np.concatenate([x[None], o_sqg.integrate(T, np.fft.rfft2(x.reshape(2, N, N)), n - 1)[1]
+                                      .reshape(n - 1, -1)])
+    ref = o_var3d.cycle(x0, 0.0, obs['x'].values, obs['time'].values, np.asarray(obs['system_index'].values)[0], 3,
+                        40.0, fc, 900, analysis_window=1800.0, analysis_time_in_window=0.0, literal=False)
+    assert out['x'].shape == (3, 2 * N * N) and rel_err(np.asarray(out['x'].values), ref) < 1e-9

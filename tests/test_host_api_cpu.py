@@ -310,8 +310,14 @@ def test_var3d_rejects_what_it_does_not_accelerate():
     assert dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, B=2 * np.eye(6))._plan(init, 0.0, obs, 2)['B'][0, 0] == 2.0
     with pytest.raises(ValueError):
         dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=model, h=lambda x: x).cycle(init, 0.0, obs, 2)
+    class HostModel(dab.model.Model):                         # a user plugin without a device forecast: no fallback
+        def forecast(self, state_vec, n_steps):
+            return state_vec, state_vec
     with pytest.raises(NotImplementedError):
-        dab.dacycler.Var3D(system_dim=3, delta_t=0.01, model_obj=dab.model.Lorenz63Model()).cycle(init, 0.0, obs, 2)
+        dab.dacycler.Var3D(system_dim=6, delta_t=0.05, model_obj=HostModel(system_dim=6, delta_t=0.05)).cycle(init, 0.0, obs, 2)
+    with pytest.raises(NotImplementedError):
+        dab.dacycler.ETKF(system_dim=6, delta_t=0.05, model_obj=HostModel(system_dim=6, delta_t=0.05), ensemble_dim=4)._plan(
+            init.assign(x=(['ensemble', 'index'], np.zeros((4, 6)))), 0.0, obs, 2)
 
 
 def test_compact_default_operators_match_the_reference_dense_ones():
