@@ -154,3 +154,27 @@ def test_sqg_long_run_from_the_default_state_stays_on_the_oracle_trajectory():
     got = traj[:, 0].cpu().numpy()
     assert np.abs(got - ref_vals).max() / np.abs(ref_vals).max() < 1e-9
     assert np.abs(got[-1].mean(axis=(1, 2)) - ref_vals[-1].mean(axis=(1, 2))).max() < 1e-6
+
+
+def test_sqg_gridded_entry_point_is_the_spectral_one_between_two_transforms():
+    """dab_sqg_forecast_grid_f64: rfft2 in, the same RK4 steps, irfft2 out; zero steps = the identity on a real
+    grid (to rounding); the optional spectral output is the state the spectral entry point returns."""
+    from dataassimbench_b200._runtime import handle
+    N, k, n_steps = 32, 3, 2
+    pv = members(N, k, seed=21)
+    g = SQGTurb(pv=pv[0], precision='double')
+    dev = torch.from_numpy(pv).cuda()
+    same = g.forecast_members_grid(dev, 0)
+    assert np.abs(same.cpu().numpy() - pv).max() / np.abs(pv).max() < 1e-14
+    out, traj = g.forecast_members_grid(dev, n_steps, return_grid_traj=True)
+    spec, traj_s = g.forecast_members(np.fft.rfft2(pv), n_steps, return_grid_traj=True)
+    assert np.abs(out.cpu().numpy() - np.fft.irfft2(spec)).max() / np.abs(pv).max() < 1e-13
+    assert np.abs((traj - traj_s).cpu().numpy()).max() / np.abs(pv).max() < 1e-13
+    assert torch.equal(traj[-1], out)
+    H = handle()
+    spec_out = torch.empty((k, 2, N, N // 2 + 1), dtype=torch.complex128, device='cuda')
+    out2 = torch.empty_like(dev)
+    H.sqg_forecast_grid(dev, out2, spec_out, None, k, n_steps, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    assert np.abs(spec_out.cpu().numpy() - spec).max() / np.abs(spec).max() < 1e-13
